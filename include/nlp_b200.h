@@ -1,0 +1,149 @@
+/*
+ * nlp_b200.h -- C ABI of the B200-native IHub/LHub neighbourhood link-prediction path.
+ *
+ * The reference (puzzlef/neighborhood-link-prediction-openmp) has no FFI: its hot path is the
+ * C++ template family `predictLinks<Measure>[Omp]<MINDEGREE1,MAXFACTOR2,FORCEHEAP>(x, o)`
+ * in inc/predict.hxx:502-831, entered from the PREDICT_LINKS macro at main.cxx:48-57.  This
+ * header is the boundary a maintainer binds instead; the C++ shim
+ * include/predict_b200.hxx re-creates the 18 template entry points and the two structs on top
+ * of it, so main.cxx / batch.hxx use the GPU path unchanged.
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  One handle drives one GPU and is
+ * used by one host thread at a time (the reference call is blocking and serial as well).
+ * Every function returns an nlp_status; nlp_last_error() gives the message.  There is no CPU
+ * fallback: without a CUDA device nlp_create() fails with NLP_ERR_CUDA.
+ */
+#ifndef NLP_B200_H
+#define NLP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nlp_handle nlp_handle;
+
+typedef enum {
+  NLP_OK            = 0,
+  NLP_ERR_ARG       = 1,   /* bad argument (null pointer, unknown measure, unsorted offsets ...) */
+  NLP_ERR_CUDA      = 2,   /* CUDA runtime error, or no usable device                           */
+  NLP_ERR_NO_GRAPH  = 3,   /* nlp_predict before nlp_set_graph                                  */
+  NLP_ERR_CAPACITY  = 4,   /* candidate buffer cannot hold an unbounded (max_edges = -1) result  */
+  NLP_ERR_NO_RESULT = 5    /* nlp_fetch before nlp_predict                                      */
+} nlp_status;
+
+/* Similarity measures, in the order main.cxx:212-220 runs them.
+ * Score functions: inc/predict.hxx:521 (CN), 559 (JC), 597 (SI), 635 (SC), 673 (HP),
+ * 711 (HD), 749 (LHN), 788-789 (AA), 828-829 (RA).                                            */
+typedef enum {
+  NLP_COMMON_NEIGHBORS     = 0,
+  NLP_JACCARD_COEFFICIENT  = 1,
+  NLP_SORENSEN_INDEX       = 2,
+  NLP_SALTON_COSINE        = 3,
+  NLP_HUB_PROMOTED         = 4,
+  NLP_HUB_DEPRESSED        = 5,
+  NLP_LEICHT_HOLME_NERMAN  = 6,
+  NLP_ADAMIC_ADAR          = 7,
+  NLP_RESOURCE_ALLOCATION  = 8,
+  NLP_NUM_MEASURES         = 9
+} nlp_measure;
+
+#define NLP_UNBOUNDED UINT64_MAX   /* PredictLinkOptions::maxEdges default, size_t(-1) */
+
+/* Replaces PredictLinkOptions<W> (inc/predict.hxx:33-55) plus the template arguments
+ * <MINDEGREE1, MAXFACTOR2, FORCEHEAP> of inc/predict.hxx:214, which become runtime values. */
+typedef struct {
+  int32_t  measure;       /* nlp_measure                                                        */
+  uint32_t min_degree1;   /* MINDEGREE1: 0 = IHub; D > 0 = LHub, first-hop w with deg(w) > D are
+                             skipped as intermediates (inc/predict.hxx:301). Any value allowed. */
+  uint32_t max_factor2;   /* MAXFACTOR2 (inc/predict.hxx:292-296); 0 = off, as in main.cxx       */
+  int32_t  repeat;        /* PredictLinkOptions::repeat: scoring phase runs this many times and
+                             scoring_ms is the mean (inc/predict.hxx:426-430); <= 0 is run once  */
+  uint64_t max_edges;     /* PredictLinkOptions::maxEdges (NLP_UNBOUNDED = all candidates)       */
+  float    min_score;     /* PredictLinkOptions::minScore: keep score > min_score (predict.hxx:311) */
+} nlp_options;
+
+/* Replaces the scalar part of PredictLinkResult<K,W> (inc/predict.hxx:65-102) and adds the
+ * counters BASELINE.json's metric needs (wedges/s, roofline bytes).                             */
+typedef struct {
+  uint64_t count;               /* predicted edges = min(max_edges, #kept candidates)            */
+  float    time_ms;             /* PredictLinkResult::time        = scoring + select/merge       */
+  float    scoring_ms;          /* PredictLinkResult::scoringTime = mean over `repeat`           */
+  float    select_ms;           /* time_ms - scoring_ms (inc/predict.hxx:431-460)                */
+  float    frontier_ms;         /* part of scoring_ms spent building the work-balanced frontier  */
+  uint64_t first_hop;           /* first-hop entries of the sources this rank owns               */
+  uint64_t eligible_first_hop;  /* of those, entries passing the hub cutoff                      */
+  uint64_t wedges;              /* W(D): second-hop entries the reference would visit            */
+  uint64_t candidates;          /* distinct (u, v>u) pairs touched, incl. adjacent ones          */
+  uint64_t kept;                /* pairs with score > min_score                                  */
+  uint64_t emitted;             /* pairs written to the candidate buffer (after threshold prune) */
+  uint64_t frontier_sources;    /* sources with non-zero work                                    */
+  uint64_t bin_sources[8];      /* sources per path: [0]=8-lane [1]=32-lane [2..4]=hash 1K/4K/16K
+                                   [5]=global dense spill, [6..7] reserved                       */
+  uint32_t passes;              /* candidate-buffer passes (1 unless the buffer had to be pruned)*/
+  uint32_t reserved;
+} nlp_result;
+
+/* Create a predictor bound to CUDA device `device` (one process per GPU). */
+int nlp_create(nlp_handle** out, int device);
+int nlp_destroy(nlp_handle* h);
+
+/* CSR graph in: offsets[span+1] (64-bit, offsets[0] == 0, non-decreasing), keys[offsets[span]]
+ * (32-bit vertex ids < span, each row sorted ascending; rows may hold duplicates -- entries are
+ * counted, as the reference's forEachEdgeKey loops do).  HOST pointers; the library copies
+ * them to its GPU.  Mirrors the read API the templates use on DiGraph / DiGraphCsr:
+ * span(), degree(), hasVertex(), forEachEdgeKey() (inc/Graph.hxx:419,557,537,500).
+ * The graph stays resident for any number of nlp_predict calls (main.cxx runs 99 per batch). */
+int nlp_set_graph(nlp_handle* h, const uint64_t* offsets, const uint32_t* keys, uint32_t span);
+
+/* Same, for arrays that already live in this GPU's memory (borrowed, not copied; must stay
+ * valid until the next nlp_set_graph* / nlp_destroy).                                         */
+int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_t* d_keys,
+                         uint32_t span);
+
+/* Multi-GPU: this handle processes source vertices of partition `rank` of `world` (sources are
+ * dealt round-robin in work-sorted frontier order, so every rank gets the same wedge work).
+ * Default (0, 1).  Replaces the OpenMP `schedule(dynamic,2048)` split of inc/predict.hxx:287.  */
+int nlp_set_partition(nlp_handle* h, int rank, int world);
+
+/* Upper bound, in bytes, of GPU scratch (candidate buffer, spill tables) nlp_predict may use.
+ * 0 = default (a fraction of the free memory at first use).                                    */
+int nlp_set_scratch_limit(nlp_handle* h, uint64_t bytes);
+
+/* Run one prediction.  Blocking.  The predicted edges stay in GPU memory, sorted by
+ * (score desc, u asc, v asc), until the next nlp_predict / nlp_merge on this handle.           */
+int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res);
+
+/* Copy the last result to HOST arrays of at least `capacity` elements each (u < v).
+ * Copies min(capacity, count) edges.                                                           */
+int nlp_fetch(nlp_handle* h, uint32_t* u, uint32_t* v, float* score, uint64_t capacity);
+
+/* Device pointers of the last result (count elements each), for on-device consumers and for
+ * the multi-GPU all-gather.                                                                    */
+int nlp_result_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d_v,
+                      const float** d_score, uint64_t* count);
+
+/* Multi-GPU merge step (replaces the T-way heap merge of inc/predict.hxx:431-460): given the
+ * concatenated candidates of all ranks in THIS GPU's memory (n elements each), select the best
+ * max_edges in canonical order; the result replaces the handle's last result.
+ * select_ms (optional) receives the device time.                                               */
+int nlp_merge(nlp_handle* h, const uint32_t* d_u, const uint32_t* d_v, const float* d_score,
+              uint64_t n, uint64_t max_edges, float* select_ms);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+uint64_t nlp_launch_count(const nlp_handle* h);
+
+/* The cudaStream_t (as void*) all work of this handle is issued on. */
+void* nlp_stream(const nlp_handle* h);
+
+/* Message for the most recent non-OK status of this handle (or of nlp_create when h == NULL). */
+const char* nlp_last_error(const nlp_handle* h);
+
+const char* nlp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLP_B200_H */
