@@ -1,0 +1,161 @@
+"""ctypes binding of the C ABI in include/nlp_b200.h (the product path).
+
+This module never imports anything under oracle/ and has no CPU fallback: if the CUDA library
+is missing or no B200 is present it raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MEASURES = ["CN", "JC", "SI", "SC", "HP", "HD", "LHN", "AA", "RA"]   # main.cxx:212-220 order
+UNBOUNDED = (1 << 64) - 1
+STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH",
+          4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT"}
+
+EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
+           "nlp_set_scratch_limit", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
+           "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
+
+
+class Options(C.Structure):
+    _fields_ = [("measure", C.c_int32), ("min_degree1", C.c_uint32), ("max_factor2", C.c_uint32),
+                ("repeat", C.c_int32), ("max_edges", C.c_uint64), ("min_score", C.c_float)]
+
+
+class Result(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("time_ms", C.c_float), ("scoring_ms", C.c_float),
+                ("select_ms", C.c_float), ("frontier_ms", C.c_float), ("first_hop", C.c_uint64),
+                ("eligible_first_hop", C.c_uint64), ("wedges", C.c_uint64), ("candidates", C.c_uint64),
+                ("kept", C.c_uint64), ("emitted", C.c_uint64), ("frontier_sources", C.c_uint64),
+                ("bin_sources", C.c_uint64 * 8), ("passes", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        d = {}
+        for n, _ in self._fields_:
+            x = getattr(self, n)
+            d[n] = list(x) if n == "bin_sources" else (float(x) if n.endswith("_ms") else int(x))
+        return d
+
+
+class NlpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (STATUS.get(code, code), msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """dlopen libnlp_b200.so (building it with nvcc first if it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise FileNotFoundError(path)
+        _build.build()
+    lib = C.CDLL(path)
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    lib.nlp_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.nlp_destroy.argtypes = [vp]
+    lib.nlp_set_graph.argtypes = [vp, vp, vp, u32]
+    lib.nlp_set_graph_device.argtypes = [vp, vp, vp, u32]
+    lib.nlp_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    lib.nlp_set_scratch_limit.argtypes = [vp, u64]
+    lib.nlp_predict.argtypes = [vp, C.POINTER(Options), C.POINTER(Result)]
+    lib.nlp_fetch.argtypes = [vp, vp, vp, vp, u64]
+    lib.nlp_result_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    lib.nlp_merge.argtypes = [vp, vp, vp, vp, u64, u64, C.POINTER(C.c_float)]
+    lib.nlp_launch_count.argtypes = [vp]
+    lib.nlp_launch_count.restype = u64
+    lib.nlp_stream.argtypes = [vp]
+    lib.nlp_stream.restype = vp
+    lib.nlp_last_error.argtypes = [vp]
+    lib.nlp_last_error.restype = C.c_char_p
+    lib.nlp_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class Predictor:
+    """One handle = one GPU.  Thin Python mirror of include/nlp_b200.h for tests and bench.py."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.nlp_create(C.byref(h), device)
+        if rc != 0:
+            raise NlpError(rc, self.lib.nlp_last_error(None).decode())
+        self.h = h
+        self._keep = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NlpError(rc, self.lib.nlp_last_error(self.h).decode())
+
+    def set_graph(self, offsets, keys):
+        """Host CSR arrays (numpy uint64 offsets[S+1], uint32 keys[M]); copied to the GPU."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        self._check(self.lib.nlp_set_graph(self.h, offsets.ctypes.data,
+                                           keys.ctypes.data if keys.size else None,
+                                           offsets.shape[0] - 1))
+
+    def set_graph_pointers(self, offsets_ptr, keys_ptr, span, device=False, keep=None):
+        """Raw pointers (host, e.g. pinned torch tensors, or device when ``device=True``)."""
+        fn = self.lib.nlp_set_graph_device if device else self.lib.nlp_set_graph
+        self._check(fn(self.h, offsets_ptr, keys_ptr, span))
+        self._keep = keep
+
+    def set_partition(self, rank, world):
+        self._check(self.lib.nlp_set_partition(self.h, rank, world))
+
+    def set_scratch_limit(self, nbytes):
+        self._check(self.lib.nlp_set_scratch_limit(self.h, nbytes))
+
+    def predict(self, measure, min_degree1=4, max_edges=UNBOUNDED, min_score=0.0, repeat=1, max_factor2=0):
+        if isinstance(measure, str):
+            measure = MEASURES.index(measure)
+        o = Options(measure, min_degree1, max_factor2, repeat, max_edges, min_score)
+        r = Result()
+        self._check(self.lib.nlp_predict(self.h, C.byref(o), C.byref(r)))
+        return r.as_dict()
+
+    def fetch(self, count):
+        u = np.empty(count, np.uint32); v = np.empty(count, np.uint32); s = np.empty(count, np.float32)
+        if count:
+            self._check(self.lib.nlp_fetch(self.h, u.ctypes.data, v.ctypes.data, s.ctypes.data, count))
+        return u, v, s
+
+    def fetch_into(self, u_ptr, v_ptr, s_ptr, capacity):
+        """Copy the result into caller memory (host or device pointers)."""
+        self._check(self.lib.nlp_fetch(self.h, u_ptr, v_ptr, s_ptr, capacity))
+
+    def result_device(self):
+        pu, pv, ps, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self.lib.nlp_result_device(self.h, C.byref(pu), C.byref(pv), C.byref(ps), C.byref(n)))
+        return pu.value, pv.value, ps.value, int(n.value)
+
+    def merge(self, u_ptr, v_ptr, s_ptr, n, max_edges):
+        ms = C.c_float(0)
+        self._check(self.lib.nlp_merge(self.h, u_ptr, v_ptr, s_ptr, n, max_edges, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self.lib.nlp_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nlp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,685 @@
+// C ABI (include/nlp_b200.h) over the hand-written sm_100a kernels: host-side orchestration of
+// one prediction = frontier -> wedge enumeration / counting / scoring -> global top-K.
+// Replaces predictLinksWithIntersectionOmp (reference inc/predict.hxx:409-467).
+// There is no CPU fallback anywhere in this file: every step is a kernel launch.
+#include "../../include/nlp_b200.h"
+#include "common.cuh"
+#include "frontier.cuh"
+#include "wedge.cuh"
+#include "select.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace nlp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void*  p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct nlp_handle {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_frontier = nullptr, ev_scored = nullptr, ev_done = nullptr;
+  // graph
+  const uint64_t* d_off = nullptr;
+  const uint32_t* d_keys = nullptr;
+  DevBuf own_off, own_keys;
+  uint32_t S = 0;
+  uint64_t M = 0;
+  uint32_t maxdeg = 0;
+  bool has_graph = false;
+  DevBuf deg, work, elig, maxdeg_dev;
+  DevBuf list[NBINS], defer[NBINS];
+  DevBuf gtable;
+  uint32_t gtable_n = 0;
+  // control
+  DevBuf ctr, thr;
+  Counters* h_ctr = nullptr;          // pinned
+  unsigned long long* h_hist = nullptr;  // pinned, 12*256
+  SelectState* h_sel = nullptr;       // pinned
+  // candidates (ping-pong SoA)
+  DevBuf cu[2], cv[2], cs[2];
+  uint64_t cand_cap = 0;
+  // dense spill tables
+  DevBuf tables, touched;
+  // select / sort scratch
+  DevBuf counts, totals, hist, sel, cursor2;
+  // result
+  int res_buf = 0;
+  uint64_t res_count = 0;
+  bool has_result = false;
+  // config
+  int rank = 0, world = 1;
+  uint64_t scratch_limit = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+#define NLP_CUDA(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                          \
+      return NLP_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+int fail(nlp_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+int ensure(nlp_handle* h, DevBuf& b, size_t bytes, bool zero = false) {
+  if (bytes <= b.cap && b.p) return NLP_OK;
+  if (b.p) { NLP_CUDA(h, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  if (bytes == 0) bytes = 16;
+  NLP_CUDA(h, cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  if (zero) NLP_CUDA(h, cudaMemsetAsync(b.p, 0, bytes, h->stream));
+  return NLP_OK;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.cap = 0;
+}
+
+#define NLP_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != NLP_OK) return rc__; \
+  } while (0)
+
+#define NLP_LAUNCHED(h)                                   \
+  do {                                                    \
+    (h)->launches++;                                      \
+    NLP_CUDA(h, cudaGetLastError());                      \
+  } while (0)
+
+inline unsigned grid_for(uint64_t items, unsigned per_block, unsigned cap_blocks) {
+  uint64_t g = (items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap_blocks) g = cap_blocks;
+  return (unsigned)g;
+}
+
+int read_counters(nlp_handle* h) {
+  NLP_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLP_OK;
+}
+
+DevGraph dev_graph(const nlp_handle* h) {
+  DevGraph g;
+  g.off = h->d_off; g.keys = h->d_keys; g.deg = (const uint32_t*)h->deg.p; g.S = h->S;
+  return g;
+}
+
+// ---- graph -----------------------------------------------------------------------------------
+int finish_graph(nlp_handle* h) {
+  const uint32_t S = h->S;
+  NLP_TRY(ensure(h, h->deg, (size_t)S * 4));
+  NLP_TRY(ensure(h, h->work, (size_t)S * 4));
+  NLP_TRY(ensure(h, h->elig, ((size_t)S + 31) / 32 * 4));
+  NLP_TRY(ensure(h, h->maxdeg_dev, 16));
+  for (int b = 0; b < NBINS; ++b) {
+    NLP_TRY(ensure(h, h->list[b], (size_t)S * 4));
+    if (b >= 2) NLP_TRY(ensure(h, h->defer[b], (size_t)S * 4));
+  }
+  NLP_CUDA(h, cudaMemsetAsync(h->maxdeg_dev.p, 0, 16, h->stream));
+  uint64_t m = 0;
+  NLP_CUDA(h, cudaMemcpyAsync(&m, h->d_off + S, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (S) {
+    k_degrees<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->d_off, S, (uint32_t*)h->deg.p,
+                                                                        (uint32_t*)h->maxdeg_dev.p);
+    NLP_LAUNCHED(h);
+  }
+  uint32_t md = 0;
+  NLP_CUDA(h, cudaMemcpyAsync(&md, h->maxdeg_dev.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->M = m;
+  h->maxdeg = md;
+  h->gtable_n = 0;
+  h->has_graph = true;
+  h->has_result = false;
+  return NLP_OK;
+}
+
+// Adamic-Adar term table, gtable[d] = 1.0 / log((double)d) computed with the host libm so it
+// is the very double the reference's lambda produces (inc/predict.hxx:788).
+int ensure_gtable(nlp_handle* h) {
+  const uint32_t n = h->maxdeg + 1;
+  if (h->gtable_n == n && h->gtable.p) return NLP_OK;
+  std::vector<double> t(n);
+  for (uint32_t d = 0; d < n; ++d) t[d] = 1.0 / std::log((double)d);
+  NLP_TRY(ensure(h, h->gtable, (size_t)n * 8));
+  NLP_CUDA(h, cudaMemcpyAsync(h->gtable.p, t.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->gtable_n = n;
+  return NLP_OK;
+}
+
+// ---- top-K ------------------------------------------------------------------------------------
+// Sort the first n entries of candidate buffer `buf` by the canonical key; returns the buffer
+// that holds the sorted entries.
+int radix_sort(nlp_handle* h, int buf, uint64_t n, int* out_buf) {
+  *out_buf = buf;
+  if (n < 2) return NLP_OK;
+  NLP_CUDA(h, cudaMemsetAsync(h->hist.p, 0, 12 * 256 * 8, h->stream));
+  k_prehist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
+      (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, n,
+      (unsigned long long*)h->hist.p);
+  NLP_LAUNCHED(h);
+  NLP_CUDA(h, cudaMemcpyAsync(h->h_hist, h->hist.p, 12 * 256 * 8, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  const uint32_t nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  NLP_TRY(ensure(h, h->counts, (size_t)nblocks * 256 * 4));
+  for (int pass = 0; pass < 12; ++pass) {
+    bool constant = false;
+    for (int d = 0; d < 256; ++d)
+      if (h->h_hist[pass * 256 + d] == n) { constant = true; break; }
+    if (constant) continue;                      // every key has the same digit here
+    const int word = pass / 4, shift = (pass % 4) * 8;
+    const int o = buf ^ 1;
+    k_tilehist<<<nblocks, SORT_THREADS, 0, h->stream>>>((const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p,
+                                                        (const uint32_t*)h->cs[buf].p, n, word, shift,
+                                                        (uint32_t*)h->counts.p, nblocks);
+    NLP_LAUNCHED(h);
+    k_rowscan<<<256, 256, 0, h->stream>>>((uint32_t*)h->counts.p, nblocks, (uint32_t*)h->totals.p);
+    NLP_LAUNCHED(h);
+    k_scatter<<<nblocks, SORT_THREADS, 0, h->stream>>>(
+        (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p,
+        (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p, n, word, shift,
+        (const uint32_t*)h->counts.p, nblocks, (const uint32_t*)h->totals.p);
+    NLP_LAUNCHED(h);
+    buf = o;
+  }
+  *out_buf = buf;
+  return NLP_OK;
+}
+
+// Best min(n, K) of the n entries in buffer `buf`, canonical order.
+int top_k(nlp_handle* h, int buf, uint64_t n, uint64_t K, int* out_buf, uint64_t* out_n) {
+  if (K < n) {
+    // MSD radix select: narrow to (items before the K-th's bucket) + (that bucket)
+    NLP_CUDA(h, cudaMemsetAsync(h->sel.p, 0, sizeof(SelectState), h->stream));
+    const uint64_t slack = std::max<uint64_t>(K / 8, 65536);
+    uint64_t above = 0, bucket = n;
+    uint32_t bits = 0;
+    while (bits < 96 && above + bucket > K + slack) {
+      k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
+          (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, n,
+          (SelectState*)h->sel.p);
+      NLP_LAUNCHED(h);
+      k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K);
+      NLP_LAUNCHED(h);
+      NLP_CUDA(h, cudaMemcpyAsync(h->h_sel, h->sel.p, offsetof(SelectState, hist), cudaMemcpyDeviceToHost, h->stream));
+      NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+      above = h->h_sel->above; bucket = h->h_sel->bucket; bits = h->h_sel->bits;
+    }
+    if (bits > 0 && above + bucket < n) {
+      const int o = buf ^ 1;
+      NLP_CUDA(h, cudaMemsetAsync(h->cursor2.p, 0, 8, h->stream));
+      k_select_compact<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
+          (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, n,
+          (const SelectState*)h->sel.p, (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p,
+          (unsigned long long*)h->cursor2.p);
+      NLP_LAUNCHED(h);
+      buf = o;
+      n = above + bucket;
+    }
+  }
+  NLP_TRY(radix_sort(h, buf, n, out_buf));
+  *out_n = std::min(n, K);
+  return NLP_OK;
+}
+
+int ensure_candidates(nlp_handle* h, uint64_t cap) {
+  if (cap < 1024) cap = 1024;
+  if (cap <= h->cand_cap) return NLP_OK;
+  for (int b = 0; b < 2; ++b) {
+    NLP_TRY(ensure(h, h->cu[b], cap * 4));
+    NLP_TRY(ensure(h, h->cv[b], cap * 4));
+    NLP_TRY(ensure(h, h->cs[b], cap * 4));
+  }
+  h->cand_cap = cap;
+  h->has_result = false;
+  return NLP_OK;
+}
+
+// ---- wedge kernels ---------------------------------------------------------------------------
+struct HashCfg { int threads; int log2_slots; };
+
+inline HashCfg hash_cfg(int bin, bool flt) {
+  HashCfg c;
+  c.log2_slots = bin == 2 ? 10 : bin == 3 ? 12 : 14;
+  c.threads = flt ? 32 : (bin == 2 ? 64 : bin == 3 ? 128 : 512);
+  return c;
+}
+
+template <bool FLT, bool ADMIT>
+int launch_hash(nlp_handle* h, const Params& p, int bin, const uint32_t* list, uint32_t n, uint32_t* deferred) {
+  if (!n) return NLP_OK;
+  const HashCfg c = hash_cfg(bin, FLT);
+  const size_t smem = ((size_t)8) << c.log2_slots;
+  auto kern = k_hash<FLT, ADMIT>;
+  NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  int occ = 1;
+  NLP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, smem));
+  if (occ < 1) occ = 1;
+  const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms * occ);
+  kern<<<grid, c.threads, smem, h->stream>>>(p, list, n, bin, deferred, c.log2_slots);
+  NLP_LAUNCHED(h);
+  return NLP_OK;
+}
+
+template <bool FLT, bool ADMIT>
+int launch_dense(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t n, uint32_t* deferred,
+                 unsigned slots, uint64_t touched_cap) {
+  if (!n) return NLP_OK;
+  const unsigned grid = (unsigned)std::min<uint64_t>(n, slots);
+  k_dense<FLT, ADMIT><<<grid, FLT ? 32 : 512, 0, h->stream>>>(p, list, n, 5, deferred, (uint32_t*)h->tables.p,
+                                                              (uint32_t*)h->touched.p, touched_cap);
+  NLP_LAUNCHED(h);
+  return NLP_OK;
+}
+
+template <bool FLT>
+int launch_tiny(nlp_handle* h, const Params& p, int bin, const uint32_t* list, uint32_t n) {
+  if (!n) return NLP_OK;
+  if (bin == 0) {
+    k_tiny<8, FLT><<<grid_for(n, 8 * 4, h->num_sms * 16), 256, 0, h->stream>>>(p, list, n);
+  } else {
+    k_tiny<32, FLT><<<grid_for(n, 8, h->num_sms * 16), 256, 0, h->stream>>>(p, list, n);
+  }
+  NLP_LAUNCHED(h);
+  return NLP_OK;
+}
+
+template <bool FLT>
+int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_buf, uint64_t* out_fill) {
+  const uint32_t S = h->S;
+  const uint64_t K = opt->max_edges;
+  const bool lhub = opt->min_degree1 != 0;
+  Counters* hc = h->h_ctr;
+
+  NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
+  NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
+  const DevGraph g = dev_graph(h);
+  // (a) frontier
+  if (lhub) {
+    k_elig<<<grid_for(((uint64_t)S + 31) / 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        (const uint32_t*)h->deg.p, S, opt->min_degree1, (uint32_t*)h->elig.p);
+    NLP_LAUNCHED(h);
+    k_work<true><<<grid_for(((uint64_t)S + 31) / 32, 8, h->num_sms * 8), 256, 0, h->stream>>>(
+        g, (const uint32_t*)h->elig.p, h->rank, h->world, (uint32_t*)h->work.p, (Counters*)h->ctr.p);
+  } else {
+    k_work<false><<<grid_for(((uint64_t)S + 31) / 32, 8, h->num_sms * 8), 256, 0, h->stream>>>(
+        g, nullptr, h->rank, h->world, (uint32_t*)h->work.p, (Counters*)h->ctr.p);
+  }
+  NLP_LAUNCHED(h);
+  BinLists bl;
+  for (int b = 0; b < NBINS; ++b) bl.list[b] = (uint32_t*)h->list[b].p;
+  k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const uint32_t*)h->work.p, h->rank, h->world, bl,
+                                                                  (Counters*)h->ctr.p);
+  NLP_LAUNCHED(h);
+  NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
+  NLP_TRY(read_counters(h));
+
+  uint64_t nb[NBINS], total_need = 0;
+  for (int b = 0; b < NBINS; ++b) { nb[b] = hc->bin_count[b]; total_need += hc->bin_bound[b]; }
+  res->first_hop = hc->first_hop;
+  res->eligible_first_hop = hc->eligible_first_hop;
+  res->wedges = hc->wedges;
+  res->frontier_sources = hc->frontier;
+  for (int b = 0; b < 8; ++b) res->bin_sources[b] = b < NBINS ? nb[b] : 0;
+
+  // scratch plan: dense spill tables first, candidate buffer with what is left
+  size_t free_b = 0, total_b = 0;
+  NLP_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+  uint64_t budget = (uint64_t)free_b + h->tables.cap + h->touched.cap;
+  for (int b = 0; b < 2; ++b) budget += h->cu[b].cap + h->cv[b].cap + h->cs[b].cap;
+  budget = budget / 10 * 8;
+  if (h->scratch_limit && h->scratch_limit < budget) budget = h->scratch_limit;
+  unsigned dense_slots = 0;
+  uint64_t touched_cap = 0;
+  if (nb[5]) {
+    touched_cap = std::min<uint64_t>(hc->max_bound, S);
+    const uint64_t per_slot = (uint64_t)S * 4 + touched_cap * 4;
+    uint64_t want = FLT ? (uint64_t)h->num_sms * 16 : (uint64_t)h->num_sms * 2;
+    want = std::min<uint64_t>(want, nb[5]);
+    const uint64_t afford = std::max<uint64_t>(1, (budget / 3) / per_slot);
+    dense_slots = (unsigned)std::min<uint64_t>(want, afford);
+    const bool fresh = (uint64_t)dense_slots * S * 4 > h->tables.cap;
+    NLP_TRY(ensure(h, h->tables, (uint64_t)dense_slots * S * 4, true));
+    if (fresh) NLP_CUDA(h, cudaMemsetAsync(h->tables.p, 0, h->tables.cap, h->stream));
+    NLP_TRY(ensure(h, h->touched, (uint64_t)dense_slots * touched_cap * 4));
+    budget -= std::min<uint64_t>(budget, h->tables.cap + h->touched.cap);
+  }
+  const uint64_t cap_limit = std::min<uint64_t>(budget / 24, 0xfffffff0ull);
+  uint64_t want_cap = total_need;
+  if (K != NLP_UNBOUNDED) {
+    const uint64_t k4 = K > (1ull << 60) ? (1ull << 62) : 4 * K;
+    want_cap = std::min<uint64_t>(total_need, std::max<uint64_t>(k4, 1ull << 24) + S + (1ull << 20));
+  }
+  const uint64_t cap = std::min<uint64_t>(want_cap, cap_limit);
+  const bool admit = cap < total_need;
+  if (admit) {
+    const uint64_t kk = std::min<uint64_t>(K, total_need);
+    if (K == NLP_UNBOUNDED || cap < kk + S + 4096)
+      return fail(h, NLP_ERR_CAPACITY, "candidate buffer too small for this request (raise nlp_set_scratch_limit or bound max_edges)");
+  }
+  NLP_TRY(ensure_candidates(h, cap));
+
+  int cur = 0;
+  Params p;
+  p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
+  p.elig = lhub ? (const uint32_t*)h->elig.p : nullptr;
+  p.gtable = (const double*)h->gtable.p;
+  p.work = (const uint32_t*)h->work.p;
+  p.cap = cap; p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
+  auto bind = [&](int b) { p.cu = (uint32_t*)h->cu[b].p; p.cv = (uint32_t*)h->cv[b].p; p.cs = (float*)h->cs[b].p; };
+  bind(cur);
+
+  res->passes = 1;
+  if (!admit) {
+    // everything fits: one pass, no admission control, no host round trip until the end
+    NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
+    for (int b = 4; b >= 2; --b)
+      NLP_TRY((launch_hash<FLT, false>(h, p, b, (const uint32_t*)h->list[b].p, (uint32_t)nb[b], nullptr)));
+    NLP_TRY((launch_tiny<FLT>(h, p, 1, (const uint32_t*)h->list[1].p, (uint32_t)nb[1])));
+    NLP_TRY((launch_tiny<FLT>(h, p, 0, (const uint32_t*)h->list[0].p, (uint32_t)nb[0])));
+    NLP_TRY(read_counters(h));
+  } else {
+    // the buffer cannot hold every candidate: admit sources while there is room, then keep the
+    // best K (which fixes the pruning threshold) and continue with the deferred sources
+    uint32_t* lists[NBINS]; uint32_t* defers[NBINS];
+    for (int b = 0; b < NBINS; ++b) { lists[b] = (uint32_t*)h->list[b].p; defers[b] = (uint32_t*)h->defer[b].p; }
+    uint64_t remaining[NBINS];
+    for (int b = 0; b < NBINS; ++b) remaining[b] = nb[b];
+    uint64_t tiny_pos[2] = {0, 0};
+    uint64_t fill = 0;
+    for (;; res->passes++) {
+      // reset queues / deferred counts, seed the reservation with the current fill
+      NLP_CUDA(h, cudaMemsetAsync((char*)h->ctr.p + offsetof(Counters, deferred), 0, 16 * 8, h->stream));
+      NLP_CUDA(h, cudaMemcpyAsync((char*)h->ctr.p + offsetof(Counters, reserved), &fill, 8, cudaMemcpyHostToDevice, h->stream));
+      NLP_TRY((launch_dense<FLT, true>(h, p, lists[5], (uint32_t)remaining[5], defers[5], dense_slots, touched_cap)));
+      for (int b = 4; b >= 2; --b) NLP_TRY((launch_hash<FLT, true>(h, p, b, lists[b], (uint32_t)remaining[b], defers[b])));
+      NLP_TRY(read_counters(h));
+      fill = hc->cursor;
+      uint64_t fill_ub = fill;
+      for (int b = 1; b >= 0; --b) {
+        const uint64_t G = b ? 32 : 8;
+        const uint64_t left = nb[b] - tiny_pos[b];
+        const uint64_t take = std::min<uint64_t>(left, (cap - fill_ub) / G);
+        if (take) {
+          NLP_TRY((launch_tiny<FLT>(h, p, b, (const uint32_t*)h->list[b].p + tiny_pos[b], (uint32_t)take)));
+          tiny_pos[b] += take; fill_ub += take * G;
+        }
+      }
+      NLP_TRY(read_counters(h));
+      fill = hc->cursor;
+      bool done = tiny_pos[0] == nb[0] && tiny_pos[1] == nb[1];
+      for (int b = 2; b < NBINS; ++b) { remaining[b] = hc->deferred[b]; done = done && remaining[b] == 0; std::swap(lists[b], defers[b]); }
+      if (done) break;
+      if (fill > K) {
+        int ob; uint64_t on;
+        NLP_TRY(top_k(h, cur, fill, K, &ob, &on));
+        cur = ob; bind(cur); fill = on;
+        // threshold = the K-th best so far
+        Threshold t;
+        uint32_t tu, tv, ts;
+        NLP_CUDA(h, cudaMemcpyAsync(&tu, (uint32_t*)h->cu[cur].p + (on - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        NLP_CUDA(h, cudaMemcpyAsync(&tv, (uint32_t*)h->cv[cur].p + (on - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        NLP_CUDA(h, cudaMemcpyAsync(&ts, (uint32_t*)h->cs[cur].p + (on - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+        t.active = 1; t.key = desc_key(ts); t.u = tu; t.v = tv;
+        NLP_CUDA(h, cudaMemcpyAsync(h->thr.p, &t, sizeof t, cudaMemcpyHostToDevice, h->stream));
+        NLP_CUDA(h, cudaMemcpyAsync((char*)h->ctr.p + offsetof(Counters, cursor), &fill, 8, cudaMemcpyHostToDevice, h->stream));
+        NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+      }
+      if (res->passes > 100000) return fail(h, NLP_ERR_CAPACITY, "candidate buffer passes did not converge");
+    }
+  }
+  if (hc->overflow) return fail(h, NLP_ERR_CAPACITY, "internal: candidate buffer overflow");
+  res->candidates = hc->candidates;
+  res->kept = hc->kept;
+  res->emitted = hc->cursor;
+  *out_buf = cur;
+  *out_fill = hc->cursor;
+  return NLP_OK;
+}
+
+}  // namespace
+
+
+extern "C" {
+
+int nlp_create(nlp_handle** out, int device) {
+  if (!out) { g_create_error = "nlp_create: null output pointer"; return NLP_ERR_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("nlp_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path";
+    return NLP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "nlp_create: bad device index"; return NLP_ERR_ARG; }
+  nlp_handle* h = new nlp_handle();
+  h->device = device;
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string("nlp_create: ") + what + ": " + cudaGetErrorString(err);
+    delete h;
+    return (int)NLP_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major < 10) {
+    g_create_error = "nlp_create: kernels are built for sm_100a (B200) only";
+    delete h;
+    return NLP_ERR_CUDA;
+  }
+  h->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_frontier); cudaEventCreate(&h->ev_scored); cudaEventCreate(&h->ev_done);
+  if ((e = cudaMallocHost((void**)&h->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost((void**)&h->h_hist, 12 * 256 * 8)) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost((void**)&h->h_sel, sizeof(SelectState))) != cudaSuccess) return bail("cudaMallocHost", e);
+  int rc = NLP_OK;
+  if ((rc = ensure(h, h->ctr, sizeof(Counters), true)) || (rc = ensure(h, h->thr, sizeof(Threshold), true)) ||
+      (rc = ensure(h, h->totals, 256 * 4)) || (rc = ensure(h, h->hist, 12 * 256 * 8)) ||
+      (rc = ensure(h, h->sel, sizeof(SelectState), true)) || (rc = ensure(h, h->cursor2, 16, true))) {
+    g_create_error = h->err;
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return NLP_OK;
+}
+
+int nlp_destroy(nlp_handle* h) {
+  if (!h) return NLP_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  release(h->own_off); release(h->own_keys); release(h->deg); release(h->work); release(h->elig); release(h->maxdeg_dev);
+  for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
+  release(h->gtable); release(h->ctr); release(h->thr);
+  for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
+  release(h->tables); release(h->touched); release(h->counts); release(h->totals); release(h->hist);
+  release(h->sel); release(h->cursor2);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
+  if (h->h_hist) cudaFreeHost(h->h_hist);
+  if (h->h_sel) cudaFreeHost(h->h_sel);
+  cudaEventDestroy(h->ev_start); cudaEventDestroy(h->ev_frontier); cudaEventDestroy(h->ev_scored); cudaEventDestroy(h->ev_done);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return NLP_OK;
+}
+
+int nlp_set_graph(nlp_handle* h, const uint64_t* offsets, const uint32_t* keys, uint32_t span) {
+  if (!h) return NLP_ERR_ARG;
+  if (!offsets) return fail(h, NLP_ERR_ARG, "nlp_set_graph: null offsets");
+  if (offsets[0] != 0) return fail(h, NLP_ERR_ARG, "nlp_set_graph: offsets[0] must be 0");
+  const uint64_t M = offsets[span];
+  if (M && !keys) return fail(h, NLP_ERR_ARG, "nlp_set_graph: null keys");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  h->has_graph = false;
+  NLP_TRY(ensure(h, h->own_off, ((size_t)span + 1) * 8));
+  NLP_TRY(ensure(h, h->own_keys, (size_t)M * 4));
+  NLP_CUDA(h, cudaMemcpyAsync(h->own_off.p, offsets, ((size_t)span + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  if (M) NLP_CUDA(h, cudaMemcpyAsync(h->own_keys.p, keys, (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
+  h->d_off = (const uint64_t*)h->own_off.p;
+  h->d_keys = (const uint32_t*)h->own_keys.p;
+  h->S = span;
+  return finish_graph(h);
+}
+
+int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_t* d_keys, uint32_t span) {
+  if (!h) return NLP_ERR_ARG;
+  if (!d_offsets) return fail(h, NLP_ERR_ARG, "nlp_set_graph_device: null offsets");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  h->has_graph = false;
+  release(h->own_off); release(h->own_keys);
+  h->d_off = d_offsets;
+  h->d_keys = d_keys;
+  h->S = span;
+  return finish_graph(h);
+}
+
+int nlp_set_partition(nlp_handle* h, int rank, int world) {
+  if (!h) return NLP_ERR_ARG;
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, NLP_ERR_ARG, "nlp_set_partition: need 0 <= rank < world");
+  h->rank = rank; h->world = world;
+  return NLP_OK;
+}
+
+int nlp_set_scratch_limit(nlp_handle* h, uint64_t bytes) {
+  if (!h) return NLP_ERR_ARG;
+  h->scratch_limit = bytes;
+  return NLP_OK;
+}
+
+int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res) {
+  if (!h) return NLP_ERR_ARG;
+  if (!opt || !res) return fail(h, NLP_ERR_ARG, "nlp_predict: null argument");
+  if (opt->measure < 0 || opt->measure >= NLP_NUM_MEASURES) return fail(h, NLP_ERR_ARG, "nlp_predict: unknown measure");
+  if (!h->has_graph) return fail(h, NLP_ERR_NO_GRAPH, "nlp_predict: no graph set");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  memset(res, 0, sizeof *res);
+  h->has_result = false;
+  const bool flt = opt->measure == NLP_ADAMIC_ADAR || opt->measure == NLP_RESOURCE_ALLOCATION;
+  if (opt->measure == NLP_ADAMIC_ADAR) NLP_TRY(ensure_gtable(h));
+  NLP_TRY(ensure_candidates(h, 1024));
+  const int reps = opt->repeat > 0 ? opt->repeat : 1;
+  float scoring_sum = 0.f, frontier_sum = 0.f;
+  int buf = 0;
+  uint64_t fill = 0;
+  if (opt->max_edges == 0 || h->S == 0) {           // inc/predict.hxx:429: nothing to do
+    h->res_buf = 0; h->res_count = 0; h->has_result = true;
+    return NLP_OK;
+  }
+  for (int r = 0; r < reps; ++r) {
+    NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
+    if (flt) NLP_TRY(scoring_pass<true>(h, opt, res, &buf, &fill));
+    else     NLP_TRY(scoring_pass<false>(h, opt, res, &buf, &fill));
+    NLP_CUDA(h, cudaEventRecord(h->ev_scored, h->stream));
+    NLP_CUDA(h, cudaEventSynchronize(h->ev_scored));
+    float ms = 0.f, fms = 0.f;
+    NLP_CUDA(h, cudaEventElapsedTime(&ms, h->ev_start, h->ev_scored));
+    NLP_CUDA(h, cudaEventElapsedTime(&fms, h->ev_start, h->ev_frontier));
+    scoring_sum += ms; frontier_sum += fms;
+  }
+  int ob = buf;
+  uint64_t on = 0;
+  NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
+  NLP_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
+  NLP_CUDA(h, cudaEventSynchronize(h->ev_done));
+  float sel = 0.f;
+  NLP_CUDA(h, cudaEventElapsedTime(&sel, h->ev_scored, h->ev_done));
+  h->res_buf = ob; h->res_count = on; h->has_result = true;
+  res->count = on;
+  res->scoring_ms = scoring_sum / reps;
+  res->frontier_ms = frontier_sum / reps;
+  res->select_ms = sel;
+  res->time_ms = res->scoring_ms + sel;
+  return NLP_OK;
+}
+
+int nlp_fetch(nlp_handle* h, uint32_t* u, uint32_t* v, float* score, uint64_t capacity) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_result) return fail(h, NLP_ERR_NO_RESULT, "nlp_fetch: no result");
+  const uint64_t n = std::min<uint64_t>(capacity, h->res_count);
+  if (!n) return NLP_OK;
+  if (!u || !v || !score) return fail(h, NLP_ERR_ARG, "nlp_fetch: null output");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  const int b = h->res_buf;
+  NLP_CUDA(h, cudaMemcpyAsync(u, h->cu[b].p, n * 4, cudaMemcpyDefault, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(v, h->cv[b].p, n * 4, cudaMemcpyDefault, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(score, h->cs[b].p, n * 4, cudaMemcpyDefault, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLP_OK;
+}
+
+int nlp_result_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d_v, const float** d_score, uint64_t* count) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_result) return fail(h, NLP_ERR_NO_RESULT, "nlp_result_device: no result");
+  const int b = h->res_buf;
+  if (d_u) *d_u = (const uint32_t*)h->cu[b].p;
+  if (d_v) *d_v = (const uint32_t*)h->cv[b].p;
+  if (d_score) *d_score = (const float*)h->cs[b].p;
+  if (count) *count = h->res_count;
+  return NLP_OK;
+}
+
+int nlp_merge(nlp_handle* h, const uint32_t* d_u, const uint32_t* d_v, const float* d_score, uint64_t n,
+              uint64_t max_edges, float* select_ms) {
+  if (!h) return NLP_ERR_ARG;
+  if (n && (!d_u || !d_v || !d_score)) return fail(h, NLP_ERR_ARG, "nlp_merge: null input");
+  if (n >= 0xfffffff0ull) return fail(h, NLP_ERR_CAPACITY, "nlp_merge: too many candidates");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  // The inputs must not point into this handle's own result buffers (nlp_result_device):
+  // growing the candidate buffer frees them.  Copy the local result out first (nlp_fetch).
+  const int b = 0;
+  h->has_result = false;
+  NLP_TRY(ensure_candidates(h, n));
+  NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
+  if (n) {
+    NLP_CUDA(h, cudaMemcpyAsync(h->cu[b].p, d_u, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(h->cv[b].p, d_v, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(h->cs[b].p, d_score, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  int ob = b;
+  uint64_t on = 0;
+  NLP_TRY(top_k(h, b, n, max_edges, &ob, &on));
+  NLP_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
+  NLP_CUDA(h, cudaEventSynchronize(h->ev_done));
+  if (select_ms) NLP_CUDA(h, cudaEventElapsedTime(select_ms, h->ev_start, h->ev_done));
+  h->res_buf = ob; h->res_count = on; h->has_result = true;
+  return NLP_OK;
+}
+
+uint64_t nlp_launch_count(const nlp_handle* h) { return h ? h->launches : 0; }
+
+void* nlp_stream(const nlp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+const char* nlp_last_error(const nlp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+const char* nlp_version(void) { return "nlp_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

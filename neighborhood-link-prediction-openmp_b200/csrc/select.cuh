@@ -1,0 +1,243 @@
+// Kernel (e) of the north star: global top-K selection over the candidate buffer, replacing
+// the per-thread heaps and the serial T-way merge of inc/predict.hxx:313-336, 431-460.
+//
+// Candidates are ordered by the 96-bit key (desc_key(score), u, v) -- the canonical
+// (score desc, u asc, v asc) order -- with a hand-written stable LSD radix sort (8-bit digits,
+// digits that are constant over the whole buffer are skipped).  When the buffer holds more than
+// K candidates, an MSD radix select first narrows it to the K best (plus the tie bucket of the
+// K-th) so only ~K entries are sorted.
+#pragma once
+#include "common.cuh"
+
+namespace nlp {
+
+enum { SORT_THREADS = 256, SORT_WARPS = 8, SORT_ROUNDS = 16, SORT_TILE = SORT_THREADS * SORT_ROUNDS };
+
+// word 0 = v, 1 = u, 2 = desc_key(score); LSD passes run word 0 digit 0 ... word 2 digit 3
+__device__ __forceinline__ uint32_t sort_word(int word, uint32_t u, uint32_t v, uint32_t s) {
+  return word == 0 ? v : word == 1 ? u : desc_key(s);
+}
+
+// hist[12][256]: digit histograms of all 12 passes in one read of the buffer
+__global__ void __launch_bounds__(256) k_prehist(const uint32_t* __restrict__ cu, const uint32_t* __restrict__ cv,
+                                                 const uint32_t* __restrict__ cs, uint64_t n,
+                                                 unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t sh[12 * 256];
+  for (int i = threadIdx.x; i < 12 * 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t w0 = cv[i], w1 = cu[i], w2 = desc_key(cs[i]);
+    #pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      atomicAdd(&sh[(0 + d) * 256 + ((w0 >> (8 * d)) & 255u)], 1u);
+      atomicAdd(&sh[(4 + d) * 256 + ((w1 >> (8 * d)) & 255u)], 1u);
+      atomicAdd(&sh[(8 + d) * 256 + ((w2 >> (8 * d)) & 255u)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 12 * 256; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// counts[d * nblocks + b] = number of items of tile b whose digit is d
+__global__ void __launch_bounds__(SORT_THREADS) k_tilehist(const uint32_t* __restrict__ cu, const uint32_t* __restrict__ cv,
+                                                            const uint32_t* __restrict__ cs, uint64_t n, int word, int shift,
+                                                            uint32_t* __restrict__ counts, uint32_t nblocks) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * SORT_TILE;
+  const uint32_t* __restrict__ src = word == 0 ? cv : word == 1 ? cu : cs;
+  #pragma unroll 4
+  for (int r = 0; r < SORT_ROUNDS; ++r) {
+    const uint64_t i = base + (uint64_t)r * SORT_THREADS + threadIdx.x;
+    if (i < n) {
+      uint32_t x = src[i];
+      if (word == 2) x = desc_key(x);
+      atomicAdd(&sh[(x >> shift) & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  counts[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// One block per digit: in-place exclusive scan of that digit's row of tile counts.
+__global__ void __launch_bounds__(256) k_rowscan(uint32_t* __restrict__ counts, uint32_t nblocks,
+                                                 uint32_t* __restrict__ totals) {
+  __shared__ uint32_t part[256];
+  uint32_t* row = counts + (uint64_t)blockIdx.x * nblocks;
+  const uint32_t per = (nblocks + 255u) / 256u;
+  const uint32_t lo = min(threadIdx.x * per, nblocks), hi = min(lo + per, nblocks);
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; ++i) s += row[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {          // Hillis-Steele inclusive scan
+    uint32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - s;
+  for (uint32_t i = lo; i < hi; ++i) { const uint32_t c = row[i]; row[i] = run; run += c; }
+  if (threadIdx.x == 255) totals[blockIdx.x] = part[255];
+}
+
+// Stable scatter of one tile: ranks inside a warp come from match.any, warps are ordered by
+// a shared-memory scan, tiles by the scanned count matrix.
+__global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __restrict__ iu, const uint32_t* __restrict__ iv,
+                                                           const uint32_t* __restrict__ is, uint32_t* __restrict__ ou,
+                                                           uint32_t* __restrict__ ov, uint32_t* __restrict__ os, uint64_t n,
+                                                           int word, int shift, const uint32_t* __restrict__ counts,
+                                                           uint32_t nblocks, const uint32_t* __restrict__ totals) {
+  __shared__ uint32_t s_hist[SORT_WARPS][256];
+  __shared__ uint32_t s_tot[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
+  s_tot[tid] = totals[tid];
+  __syncthreads();
+  uint32_t ru[SORT_ROUNDS], rv[SORT_ROUNDS], rs[SORT_ROUNDS], pre[SORT_ROUNDS];
+  const uint64_t wbase = (uint64_t)blockIdx.x * SORT_TILE + (uint64_t)warp * (32 * SORT_ROUNDS);
+  const unsigned lt = (1u << lane) - 1u;
+  #pragma unroll
+  for (int r = 0; r < SORT_ROUNDS; ++r) {
+    const uint64_t i = wbase + (uint64_t)r * 32 + lane;
+    const bool valid = i < n;
+    ru[r] = valid ? iu[i] : 0u; rv[r] = valid ? iv[i] : 0u; rs[r] = valid ? is[i] : 0u;
+    const uint32_t d = (sort_word(word, ru[r], rv[r], rs[r]) >> shift) & 255u;
+    const unsigned m = __match_any_sync(NLP_FULL, valid ? d : (256u + lane));
+    const uint32_t before = valid ? s_hist[warp][d] : 0u;
+    pre[r] = before + __popc(m & lt);
+    __syncwarp();
+    if (valid && (__ffs(m) - 1) == lane) s_hist[warp][d] = before + __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  {   // thread t owns digit t: global base + tile prefix + warps before
+    uint32_t run = 0;
+    for (int d = 0; d < tid; ++d) run += s_tot[d];
+    run += counts[(uint64_t)tid * nblocks + blockIdx.x];
+    #pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t c = s_hist[w][tid]; s_hist[w][tid] = run; run += c; }
+  }
+  __syncthreads();
+  #pragma unroll
+  for (int r = 0; r < SORT_ROUNDS; ++r) {
+    const uint64_t i = wbase + (uint64_t)r * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (sort_word(word, ru[r], rv[r], rs[r]) >> shift) & 255u;
+      const uint32_t pos = s_hist[warp][d] + pre[r];
+      ou[pos] = ru[r]; ov[pos] = rv[r]; os[pos] = rs[r];
+    }
+  }
+}
+
+// ---- MSD radix select ------------------------------------------------------------------------
+// State of the narrowing: items whose 96-bit key has `prefix` in its top `bits` bits are still
+// undecided; `above` items are already known to rank before them.
+struct SelectState {
+  uint32_t pre_hi, pre_mid, pre_lo;   // prefix words (desc_key(score), u, v), masked
+  uint32_t bits;                      // resolved leading bits (multiple of 8)
+  unsigned long long above;           // items strictly before the undecided bucket
+  unsigned long long bucket;          // items in the undecided bucket
+  unsigned long long hist[256];
+};
+
+__device__ __forceinline__ bool select_matches(const SelectState* st, uint32_t w2, uint32_t w1, uint32_t w0) {
+  const uint32_t b = st->bits;
+  if (b == 0) return true;
+  if (b <= 32) return (w2 >> (32 - b)) == (st->pre_hi >> (32 - b));
+  if (w2 != st->pre_hi) return false;
+  if (b <= 64) return (w1 >> (64 - b)) == (st->pre_mid >> (64 - b));
+  if (w1 != st->pre_mid) return false;
+  return (w0 >> (96 - b)) == (st->pre_lo >> (96 - b));
+}
+
+__device__ __forceinline__ uint32_t select_digit(uint32_t bits, uint32_t w2, uint32_t w1, uint32_t w0) {
+  // next 8 bits after `bits` leading ones
+  const uint32_t word = bits < 32 ? w2 : bits < 64 ? w1 : w0;
+  const uint32_t sh = 24 - (bits & 31u);
+  return (word >> sh) & 255u;
+}
+
+__global__ void __launch_bounds__(256) k_select_hist(const uint32_t* __restrict__ cu, const uint32_t* __restrict__ cv,
+                                                     const uint32_t* __restrict__ cs, uint64_t n, SelectState* st) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t bits = st->bits;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t w2 = desc_key(cs[i]);
+    uint32_t w1 = 0, w0 = 0;
+    if (bits >= 32) w1 = cu[i];
+    if (bits >= 64) w0 = cv[i];
+    if (select_matches(st, w2, w1, w0)) atomicAdd(&sh[select_digit(bits, w2, w1, w0)], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// Single thread: pick the digit bucket that holds the K-th item, extend the prefix by 8 bits.
+__global__ void k_select_step(SelectState* st, unsigned long long K) {
+  unsigned long long above = st->above;
+  int d = 0;
+  for (; d < 255; ++d) {
+    if (above + st->hist[d] >= K) break;
+    above += st->hist[d];
+  }
+  const uint32_t bits = st->bits;
+  const uint32_t sh = 24 - (bits & 31u);
+  if (bits < 32) st->pre_hi |= (uint32_t)d << sh;
+  else if (bits < 64) st->pre_mid |= (uint32_t)d << sh;
+  else st->pre_lo |= (uint32_t)d << sh;
+  st->above = above;
+  st->bucket = st->hist[d];
+  st->bits = bits + 8;
+  for (int i = 0; i < 256; ++i) st->hist[i] = 0;
+}
+
+// Keep every item whose key prefix is <= the selected prefix (i.e. `above` + the tie bucket).
+__global__ void __launch_bounds__(256) k_select_compact(const uint32_t* __restrict__ cu, const uint32_t* __restrict__ cv,
+                                                        const uint32_t* __restrict__ cs, uint64_t n, const SelectState* st,
+                                                        uint32_t* __restrict__ ou, uint32_t* __restrict__ ov,
+                                                        uint32_t* __restrict__ os, unsigned long long* cursor) {
+  const uint32_t b = st->bits;
+  const int lane = threadIdx.x & 31;
+  const uint64_t n32 = (n + 31u) & ~31ull;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n32; i += (uint64_t)gridDim.x * blockDim.x) {
+    bool keep = false;
+    uint32_t u = 0, v = 0, s = 0;
+    if (i < n) {
+      u = cu[i]; v = cv[i]; s = cs[i];
+      const uint32_t w2 = desc_key(s);
+      // compare the top b bits of (w2, u, v) with the prefix
+      int cmp = 0;   // -1 before, 0 equal, 1 after
+      const uint32_t b2 = b < 32 ? b : 32;
+      const uint32_t x2 = b2 ? (w2 >> (32 - b2)) : 0u, p2 = b2 ? (st->pre_hi >> (32 - b2)) : 0u;
+      cmp = x2 < p2 ? -1 : x2 > p2 ? 1 : 0;
+      if (cmp == 0 && b > 32) {
+        const uint32_t b1 = b < 64 ? b - 32 : 32;
+        const uint32_t x1 = u >> (32 - b1), p1 = st->pre_mid >> (32 - b1);
+        cmp = x1 < p1 ? -1 : x1 > p1 ? 1 : 0;
+        if (cmp == 0 && b > 64) {
+          const uint32_t b0 = b - 64;
+          const uint32_t x0 = v >> (32 - b0), p0 = st->pre_lo >> (32 - b0);
+          cmp = x0 < p0 ? -1 : x0 > p0 ? 1 : 0;
+        }
+      }
+      keep = cmp <= 0;
+    }
+    const unsigned m = __ballot_sync(NLP_FULL, keep);
+    if (!m) continue;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(NLP_FULL, base, leader);
+    if (keep) {
+      const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+      ou[pos] = u; ov[pos] = v; os[pos] = s;
+    }
+  }
+}
+
+}  // namespace nlp

@@ -1,0 +1,206 @@
+"""Deterministic synthetic workloads (no network, so no SuiteSparse downloads).
+
+Every generator is a pure function of its seed built on a counter-based integer hash
+(splitmix64), written with torch integer ops so the same code gives the *same graph* on CPU
+and on GPU (bench.py builds the big ones on the device, tests build small ones on the host).
+
+All graphs come out the way the reference's loader leaves them for the predictor
+(main.cxx:243-245): symmetric, no self-loops, sorted + deduplicated rows, vertex ids 1-based
+with vertex 0 empty (mtx.hxx:240: span = n + 1), as CSR ``offsets`` (int64) / ``keys`` (int32).
+"""
+import math
+
+import torch
+
+_M64 = (1 << 64) - 1
+
+
+def _s64(c):
+    """Python int -> the signed 64-bit value with the same bit pattern."""
+    c &= _M64
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _lsr(x, k):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def mix64(x):
+    """splitmix64 finaliser on an int64 tensor (wrapping arithmetic, logical shifts)."""
+    x = x + _s64(0x9E3779B97F4A7C15)
+    x = (x ^ _lsr(x, 30)) * _s64(0xBF58476D1CE4E5B9)
+    x = (x ^ _lsr(x, 27)) * _s64(0x94D049BB133111EB)
+    return x ^ _lsr(x, 31)
+
+
+def hash_u64(idx, seed, stream=0):
+    """Uniform 64 random bits per element of ``idx`` (int64 tensor), as int64 bit patterns."""
+    return mix64(mix64(idx + _s64(seed * 0x632BE59BD9B4E019 + stream * 0xD1342543DE82EF95)))
+
+
+def hash_unit(idx, seed, stream=0):
+    """Uniform doubles in [0, 1)."""
+    return _lsr(hash_u64(idx, seed, stream), 11).to(torch.float64) * (1.0 / (1 << 53))
+
+
+# ---------------------------------------------------------------------------------------------
+def csr_from_pairs(a, b, n):
+    """Undirected pairs (a[i], b[i]), 1 <= a,b <= n  ->  symmetric, loop-free, deduplicated CSR.
+
+    Returns (offsets int64[S+1], keys int32[M]) with S = n + 1.
+    """
+    dev = a.device
+    keep = a != b
+    a, b = a[keep], b[keep]
+    lo, hi = torch.minimum(a, b), torch.maximum(a, b)
+    und = torch.unique(lo * (n + 1) + hi)                       # one key per undirected edge
+    lo, hi = und // (n + 1), und % (n + 1)
+    del und
+    src = torch.cat([lo, hi]); dst = torch.cat([hi, lo])
+    del lo, hi
+    comp, _ = torch.sort(src * (n + 1) + dst)
+    del src, dst
+    src = comp // (n + 1)
+    keys = (comp % (n + 1)).to(torch.int32)
+    del comp
+    deg = torch.bincount(src, minlength=n + 1)
+    offsets = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=offsets[1:])
+    return offsets, keys
+
+
+def undirected_pairs(offsets, keys):
+    """(lo, hi) with lo < hi, one row per undirected edge of a symmetric CSR."""
+    S = offsets.numel() - 1
+    deg = offsets[1:] - offsets[:-1]
+    src = torch.repeat_interleave(torch.arange(S, device=offsets.device, dtype=torch.int64), deg)
+    dst = keys.to(torch.int64)
+    m = src < dst
+    return src[m], dst[m]
+
+
+def remove_edges(offsets, keys, fraction, seed):
+    """Remove ~``fraction`` of the undirected edges (hash-selected, deterministic).
+
+    Stands in for generateEdgeDeletions + applyBatchUpdate (batch.hxx:99-112, 239-247; that
+    sampler is host harness, out of the hot path).  Returns (offsets', keys', removed_lo,
+    removed_hi); the number of removed edges is the prediction count K (main.cxx:50).
+    """
+    n = offsets.numel() - 2
+    lo, hi = undirected_pairs(offsets, keys)
+    r = hash_unit(lo * (n + 1) + hi, seed, 7)
+    gone = r < fraction
+    o2, k2 = csr_from_pairs(lo[~gone], hi[~gone], n)
+    return o2, k2, lo[gone], hi[gone]
+
+
+# ---------------------------------------------------------------------------------------------
+def rmat(scale, edge_factor=16, seed=42, abc=(0.57, 0.19, 0.19), permute=False, device="cpu", chunk=1 << 24):
+    """R-MAT (Chakrabarti et al.) with 2**scale vertices and edge_factor * 2**scale edge draws."""
+    n = 1 << scale
+    m = edge_factor * n
+    a, b, c = abc
+    ta, tab, tabc = int(a * 65536), int((a + b) * 65536), int((a + b + c) * 65536)
+    us, vs = [], []
+    for start in range(0, m, chunk):
+        cnt = min(chunk, m - start)
+        idx = torch.arange(start, start + cnt, device=device, dtype=torch.int64)
+        u = torch.zeros(cnt, dtype=torch.int64, device=device)
+        v = torch.zeros(cnt, dtype=torch.int64, device=device)
+        for lvl in range(scale):
+            if lvl % 4 == 0:
+                bits = hash_u64(idx, seed, 1 + lvl // 4)
+            r = _lsr(bits, 16 * (lvl % 4)) & 0xFFFF
+            ubit = (r >= tab).to(torch.int64)                       # quadrants c, d: lower half
+            vbit = (((r >= ta) & (r < tab)) | (r >= tabc)).to(torch.int64)   # quadrants b, d
+            u = (u << 1) | ubit
+            v = (v << 1) | vbit
+        us.append(u); vs.append(v)
+    u = torch.cat(us); v = torch.cat(vs)
+    if permute:
+        perm = torch.argsort(hash_u64(torch.arange(n, device=device, dtype=torch.int64), seed, 99))
+        u, v = perm[u], perm[v]
+    return csr_from_pairs(u + 1, v + 1, n)
+
+
+def road_lattice(side, keep=0.6, seed=44, device="cpu"):
+    """2-D grid, every grid edge kept with probability ``keep`` (avg degree ~ 4*keep)."""
+    n = side * side
+    idx = torch.arange(n, device=device, dtype=torch.int64)
+    x = idx % side
+    right = (x < side - 1) & (hash_unit(idx, seed, 1) < keep)
+    down = (idx < n - side) & (hash_unit(idx, seed, 2) < keep)
+    a = torch.cat([idx[right], idx[down]]) + 1
+    b = torch.cat([idx[right] + 1, idx[down] + side]) + 1
+    return csr_from_pairs(a, b, n)
+
+
+def web_crawl(n, avg_out=19, alpha=2.1, window=10000, local=0.9, max_out=None, seed=45, device="cpu",
+              chunk=1 << 24):
+    """Web-crawl-shaped graph: power-law out-degrees, ``local`` of the links inside a +-window id
+    range (host locality), the rest to power-law-popular targets (heavy in-degree hubs)."""
+    ids = torch.arange(n, device=device, dtype=torch.int64)
+    r = hash_unit(ids, seed, 1)
+    dmin = max(1.0, avg_out * (alpha - 2.0) / (alpha - 1.0))
+    out = torch.floor(dmin * (1.0 - r) ** (-1.0 / (alpha - 1.0))).to(torch.int64)
+    out = torch.clamp(out, max=max_out if max_out else max(64, n // 50))
+    cs = torch.cumsum(out, 0)
+    m = int(cs[-1])
+    starts = cs - out
+    us, vs = [], []
+    for s0 in range(0, m, chunk):
+        cnt = min(chunk, m - s0)
+        e = torch.arange(s0, s0 + cnt, device=device, dtype=torch.int64)
+        src = torch.searchsorted(cs, e, right=True)
+        r1, r2 = hash_unit(e, seed, 2), hash_unit(e, seed, 3)
+        off = torch.floor((r2 * 2.0 - 1.0) * window).to(torch.int64)
+        near = torch.clamp(src + off, 0, n - 1)
+        pop = torch.floor(n * r2 ** 4.0).to(torch.int64)             # popular targets: low "rank"
+        pop = (pop * 0x9E3779B1 + 12345) % n                          # scatter the hubs over ids
+        dst = torch.where(r1 < local, near, pop)
+        us.append(src); vs.append(dst)
+    del starts
+    return csr_from_pairs(torch.cat(us) + 1, torch.cat(vs) + 1, n)
+
+
+def planted_partition(n, communities, deg_in=12, deg_out=2, seed=47, device="cpu"):
+    """Clustered graph (vertex i in community i % communities): link prediction has a
+    non-trivial F1 here, unlike on R-MAT."""
+    ids = torch.arange(n, device=device, dtype=torch.int64)
+    size = n // communities
+    us, vs = [], []
+    for k in range(deg_in):
+        j = (hash_u64(ids, seed, 10 + k) & 0x7FFFFFFF) % max(size, 1)
+        us.append(ids); vs.append(torch.clamp((ids % communities) + j * communities, max=n - 1))
+    for k in range(deg_out):
+        us.append(ids); vs.append((hash_u64(ids, seed, 50 + k) & 0x7FFFFFFFFFFF) % n)
+    return csr_from_pairs(torch.cat(us) + 1, torch.cat(vs) + 1, n)
+
+
+def duplicate_some_entries(offsets, keys, every=7):
+    """Multiset rows: repeat every ``every``-th adjacency entry, like the
+    duplicates the reference's symmetrizeOmp leaves behind.  Rows stay sorted; may be asymmetric."""
+    M = keys.numel()
+    idx = torch.arange(M, device=keys.device, dtype=torch.int64)
+    rep = torch.ones(M, dtype=torch.int64, device=keys.device)
+    rep[idx % every == 0] = 2
+    S = offsets.numel() - 1
+    deg = offsets[1:] - offsets[:-1]
+    src = torch.repeat_interleave(torch.arange(S, device=keys.device, dtype=torch.int64), deg)
+    keys2 = torch.repeat_interleave(keys, rep)
+    src2 = torch.repeat_interleave(src, rep)
+    deg2 = torch.bincount(src2, minlength=S)
+    off2 = torch.zeros(S + 1, dtype=torch.int64, device=keys.device)
+    torch.cumsum(deg2, 0, out=off2[1:])
+    return off2, keys2
+
+
+def to_numpy(offsets, keys):
+    import numpy as np
+    return (offsets.cpu().numpy().astype(np.uint64), keys.cpu().numpy().astype(np.uint32))
+
+
+def describe(offsets, keys):
+    deg = offsets[1:] - offsets[:-1]
+    return {"span": int(offsets.numel() - 1), "entries": int(keys.numel()), "max_degree": int(deg.max()),
+            "avg_degree": float(keys.numel()) / max(1, int((deg > 0).sum()))}
