@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- LHub link-prediction rate (predicted edges/s) of the B200 path, next to the
+reference's host-OpenMP path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rmat22] [--degree 16]
+    python bench.py --impl reference ...      # the unmodified reference on the host cores
+
+One *step* = one batch of the reference harness (main.cxx:208-221) at one hub threshold: the
+graph with 10% of its edges removed is handed over, then all nine similarity measures are run
+as LHub (MINDEGREE1 = --degree) asking for exactly the number of removed edges, like
+PREDICT_LINKS does (main.cxx:50).  Metric: predicted edges per second of whole-job time.
+
+  value : graph already resident in HBM, results left in HBM (device time, CUDA events).
+  e2e   : the same step through the C ABI with HOST buffers -- nlp_set_graph() from pinned host
+          memory and nlp_fetch() of every measure's (u, v, score) list inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np    # noqa: E402
+import torch          # noqa: E402
+
+WORKLOADS = {
+    # name: (generator kwargs, removed fraction, description)
+    "rmat22": dict(kind="rmat", scale=22, ef=16, seed=43, frac=0.1,
+                   desc="R-MAT scale-22 ef-16 (0.57,0.19,0.19) ids permuted, 0.1|E| removed (BASELINE configs[1])"),
+    "rmat20": dict(kind="rmat", scale=20, ef=16, seed=43, frac=0.1, desc="R-MAT scale-20 (smoke size)"),
+    "rmat18": dict(kind="rmat", scale=18, ef=16, seed=42, frac=0.01, desc="R-MAT scale-18, 1e-2|E| removed (configs[0])"),
+    "rmat16": dict(kind="rmat", scale=16, ef=16, seed=42, frac=0.1, desc="R-MAT scale-16 (tiny)"),
+}
+MEASURES = ["CN", "JC", "SI", "SC", "HP", "HD", "LHN", "AA", "RA"]
+METRIC = "lhub_predicted_edges_per_s"
+
+
+def build_workload(name, device):
+    import nlp_b200 as N
+    w = WORKLOADS[name]
+    t0 = time.time()
+    off, keys = N.graphs.rmat(w["scale"], w["ef"], w["seed"], permute=True, device=device)
+    off, keys, rl, rh = N.graphs.remove_edges(off, keys, w["frac"], w["seed"] + 1000)
+    K = int(rl.numel())
+    del rl, rh
+    if device != "cpu":
+        torch.cuda.synchronize()
+    info = {"workload": name, "description": w["desc"], "span": int(off.numel() - 1), "entries": int(keys.numel()),
+            "predict_count_K": K, "build_s": round(time.time() - t0, 2)}
+    return off, keys, K, info
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:   # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:   # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:   # noqa: BLE001
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reference_step(R, K, degree, measures, threads):
+    """One step on the unmodified reference (OpenMP templates).  Returns (edges, ref_ms, wall_s)."""
+    edges, ref_ms = 0, 0.0
+    t0 = time.perf_counter()
+    for m in measures:
+        u, v, s, tm, ts = R.predict(m, degree, max_edges=K, omp=True, threads=threads, canonical=False)
+        edges += len(u)
+        ref_ms += tm
+    return edges, ref_ms, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle_py as O
+    if not O.ref_available():
+        # the oracle port stands in when the compiled reference did not travel
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnlpref.so missing"}))
+        return 0
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    off, keys, K, info = build_workload(args.workload, dev)
+    import nlp_b200 as N
+    offn, keysn = N.graphs.to_numpy(off, keys)
+    del off, keys
+    R = O.RefGraph(offn, keysn)
+    threads = os.cpu_count() or 1
+    # bounded sample: as many of the nine measures per step as fit ~150 s for the whole run
+    t0 = time.perf_counter()
+    e1, ms1, w1 = reference_step(R, K, args.degree, ["JC"], threads)
+    if e1 < K:
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "reference OpenMP merge is undefined when #candidates < maxEdges (inc/predict.hxx:424,452)"}))
+        return 0
+    total_steps = args.steps + args.warmup
+    per_measure = max(w1, 1e-3)
+    nm = int(max(1, min(len(MEASURES), 150.0 / (per_measure * total_steps))))
+    order = ["JC", "AA", "CN", "SC", "RA", "SI", "HP", "HD", "LHN"]
+    sample = [m for m in MEASURES if m in order[:nm]]
+    for _ in range(args.warmup):
+        reference_step(R, K, args.degree, sample, threads)
+    edges = 0; ref_ms = 0.0; wall = 0.0
+    for _ in range(args.steps):
+        e, ms, w = reference_step(R, K, args.degree, sample, threads)
+        edges += e; ref_ms += ms; wall += w
+    value = edges / (ref_ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 counts, f32 scores",
+        "data": "synthetic",
+        "config": dict(info, min_degree1=args.degree, measures=sample, l2="inputs larger than L2"),
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": threads, "kind": "reference",
+                         "sample": "%d of 9 measures per step (%s), full graph, reference's own `time` field"
+                                   % (len(sample), ",".join(sample))},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_edges_per_s": edges / wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import nlp_b200 as N
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = "cuda:%d" % local
+    off, keys, K, info = build_workload(args.workload, dev)
+    S = int(off.numel() - 1); M = int(keys.numel())
+    # host copies in pinned memory (e2e leg) -- int64/int32 tensors carry the uint64/uint32 bits
+    h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
+    pred = N.Predictor(local)
+    pred.set_partition(rank, world)
+    stream = torch.cuda.ExternalStream(pred.lib.nlp_stream(pred.h), device=dev)
+    measures = MEASURES
+    D = args.degree
+    h_out = [torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(collect=None):
+        edges = 0
+        for m in measures:
+            if world > 1:
+                r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
+            else:
+                r = pred.predict(m, D, max_edges=K); n = r["count"]
+            edges += n
+            if collect is not None:
+                collect.append(r)
+        return edges
+
+    def one_step_e2e():
+        pred.set_graph_pointers(h_off.data_ptr(), h_keys.data_ptr(), S, device=False, keep=(h_off, h_keys))
+        edges = 0
+        for m in measures:
+            if world > 1:
+                r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
+            else:
+                r = pred.predict(m, D, max_edges=K); n = r["count"]
+            pred.fetch_into(h_out[0].data_ptr(), h_out[1].data_ptr(), h_out[2].data_ptr(), n)
+            edges += n
+        return edges
+
+    def timed(fn, steps, collect=False):
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        results = [] if collect else None
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        edges = 0
+        for _ in range(steps):
+            edges += fn(results) if collect else fn()
+        ev1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return edges, ms, wall, results
+
+    # ---- value: graph resident in HBM ---------------------------------------------------------
+    pred.set_graph_pointers(off.data_ptr(), keys.data_ptr(), S, device=True, keep=(off, keys))
+    for _ in range(args.warmup):
+        one_step()
+    launches0 = pred.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    edges, ms, wall, results = timed(one_step, args.steps, collect=True)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = pred.launch_count() - launches0
+    value = edges / (ms / 1e3)
+
+    # ---- e2e: host buffers in, host results out ----------------------------------------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        one_step_e2e()
+    e_edges, e_ms, e_wall, _ = timed(one_step_e2e, args.steps)
+    e2e_value = e_edges / (e_ms / 1e3)
+    h2d = (S + 1) * 8 + M * 4
+    d2h = int(e_edges / args.steps) * 12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant phase --------------------------------------------------------
+    names = ["frontier(k_elig+k_work+k_bin)", "k_dense", "k_hash(16K)", "k_hash(4K)", "k_hash(1K)", "k_tiny<32>", "k_tiny<8>", "select+sort"]
+    phase = [sum(r["phase_ms"][i] for r in results) for i in range(8)]
+    nrun = len(results)
+    peak, peak_src = peaks()
+    W = sum(r["wedges"] for r in results); C = sum(r["candidates"] for r in results)
+    E = sum(r["emitted"] for r in results); Kout = sum(r["count"] for r in results)
+    wedge_ms = sum(phase[1:7])
+    # algorithmic bytes, split by the phase that moves them
+    bytes_frontier = nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world)
+    bytes_wedge = 4 * W + 4 * C + 12 * E
+    bytes_select = 12 * Kout
+    cands = [("frontier: k_work (first-hop scan, hub test, work sums)", phase[0], bytes_frontier),
+             ("wedge kernels (k_dense/k_hash/k_tiny: 2-hop scan + count + score)", wedge_ms, bytes_wedge),
+             ("select+sort (radix top-K)", phase[7], bytes_select)]
+    dom = max(cands, key=lambda c: c[1])
+    achieved = dom[2] / (dom[1] / 1e3) / 1e9 if dom[1] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": dom[1] / max(1e-9, sum(phase)),
+                "algorithmic_bytes_per_step": dom[2] / args.steps}
+    total_alg = bytes_frontier + bytes_wedge + bytes_select
+    step_frac = total_alg / (ms / 1e3) / 1e9 / peak
+
+    # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample -------
+    cpu = None
+    try:
+        from oracle import oracle_py as O
+        if O.ref_available():
+            offn, keysn = N.graphs.to_numpy(off, keys)
+            R = O.RefGraph(offn, keysn)
+            threads = os.cpu_count() or 1
+            sample = ["JC", "AA"]
+            e, rms, w = reference_step(R, K, D, sample, threads)
+            if e == K * len(sample):
+                cpu = {"value": e / (rms / 1e3), "unit": "edges/s", "cores": threads, "kind": "reference",
+                       "sample": "one pass of %s (2 of 9 measures) on the full graph, reference OpenMP templates, "
+                                 "reference's own `time` field (%.0f ms wall)" % ("+".join(sample), w * 1e3)}
+            else:
+                cpu = {"value": None, "unit": "edges/s", "cores": threads, "kind": "reference",
+                       "sample": "reference returned fewer than K edges (UB regime)"}
+            R.close()
+        else:
+            t0 = time.perf_counter()
+            offn, keysn = N.graphs.to_numpy(off, keys)
+            u, v, s, st = O.oracle_predict(offn, keysn, "JC", D, max_edges=K)
+            w = time.perf_counter() - t0
+            cpu = {"value": len(u) / w, "unit": "edges/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "one JC pass of the C oracle (OpenMP) on the full graph"}
+    except Exception as ex:   # noqa: BLE001
+        cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32 counts, f32 scores (f64 terms for AA/RA/Salton)", "data": "synthetic",
+        "config": dict(info, min_degree1=D, measures=measures, l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6),
+                       parallelism="sources partitioned over %d GPU(s), CSR replicated" % world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e_ms / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "wedges_per_s": W / (sum(r["scoring_ms"] for r in results) / 1e3),
+        "step_hbm_frac": step_frac,
+        "phase_ms_per_step": {n: p / args.steps for n, p in zip(names, phase)},
+        "wall_ms_per_step": wall * 1e3 / args.steps,
+        "bins": results[0]["bin_sources"][:6],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="rmat22", choices=sorted(WORKLOADS))
+    ap.add_argument("--degree", type=int, default=16, help="MINDEGREE1 of the LHub runs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

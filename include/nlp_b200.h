@@ -84,6 +84,11 @@ typedef struct {
                                    [5]=global dense spill, [6..7] reserved                       */
   uint32_t passes;              /* candidate-buffer passes (1 unless the buffer had to be pruned)*/
   uint32_t reserved;
+  float    phase_ms[8];         /* device time per phase of the LAST scoring repeat (CUDA events on
+                                   the handle's stream): [0] frontier (eligibility+work+binning)
+                                   [1] dense spill [2] hash 16K [3] hash 4K [4] hash 1K
+                                   [5] 32-lane [6] 8-lane [7] final select+sort.  [1..6] are 0
+                                   when the buffer had to be pruned (passes > 1).                */
 } nlp_result;
 
 /* Create a predictor bound to CUDA device `device` (one process per GPU). */
@@ -103,9 +108,11 @@ int nlp_set_graph(nlp_handle* h, const uint64_t* offsets, const uint32_t* keys, 
 int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_t* d_keys,
                          uint32_t span);
 
-/* Multi-GPU: this handle processes source vertices of partition `rank` of `world` (sources are
- * dealt round-robin in work-sorted frontier order, so every rank gets the same wedge work).
- * Default (0, 1).  Replaces the OpenMP `schedule(dynamic,2048)` split of inc/predict.hxx:287.  */
+/* Multi-GPU: this handle processes the source vertices of partition `rank` of `world`: blocks
+ * of 32 consecutive vertex ids are dealt round-robin to the ranks, which interleaves the
+ * degree-correlated id ranges so every rank gets a near-equal share of each work bin.  The
+ * graph itself is replicated.  Default (0, 1).  Replaces the OpenMP `schedule(dynamic,2048)`
+ * split of inc/predict.hxx:287.                                                                */
 int nlp_set_partition(nlp_handle* h, int rank, int world);
 
 /* Upper bound, in bytes, of GPU scratch (candidate buffer, spill tables) nlp_predict may use.
@@ -116,7 +123,8 @@ int nlp_set_scratch_limit(nlp_handle* h, uint64_t bytes);
  * (score desc, u asc, v asc), until the next nlp_predict / nlp_merge on this handle.           */
 int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res);
 
-/* Copy the last result to HOST arrays of at least `capacity` elements each (u < v).
+/* Copy the last result to caller arrays of at least `capacity` elements each (u < v); the
+ * pointers may be host memory (the normal case) or memory of this GPU.
  * Copies min(capacity, count) edges.                                                           */
 int nlp_fetch(nlp_handle* h, uint32_t* u, uint32_t* v, float* score, uint64_t capacity);
 

@@ -30,13 +30,14 @@ class Result(C.Structure):
                 ("select_ms", C.c_float), ("frontier_ms", C.c_float), ("first_hop", C.c_uint64),
                 ("eligible_first_hop", C.c_uint64), ("wedges", C.c_uint64), ("candidates", C.c_uint64),
                 ("kept", C.c_uint64), ("emitted", C.c_uint64), ("frontier_sources", C.c_uint64),
-                ("bin_sources", C.c_uint64 * 8), ("passes", C.c_uint32), ("reserved", C.c_uint32)]
+                ("bin_sources", C.c_uint64 * 8), ("passes", C.c_uint32), ("reserved", C.c_uint32),
+                ("phase_ms", C.c_float * 8)]
 
     def as_dict(self):
         d = {}
         for n, _ in self._fields_:
             x = getattr(self, n)
-            d[n] = list(x) if n == "bin_sources" else (float(x) if n.endswith("_ms") else int(x))
+            d[n] = list(x) if n in ("bin_sources", "phase_ms") else (float(x) if n.endswith("_ms") else int(x))
         return d
 
 

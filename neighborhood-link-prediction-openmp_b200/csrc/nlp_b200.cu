@@ -33,6 +33,8 @@ struct nlp_handle {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_frontier = nullptr, ev_scored = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_phase[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool phases_valid = false;
   // graph
   const uint64_t* d_off = nullptr;
   const uint32_t* d_keys = nullptr;
@@ -397,14 +399,22 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   bind(cur);
 
   res->passes = 1;
+  h->phases_valid = false;
   if (!admit) {
     // everything fits: one pass, no admission control, no host round trip until the end
+    NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
     NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
-    for (int b = 4; b >= 2; --b)
+    NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
+    for (int b = 4; b >= 2; --b) {
       NLP_TRY((launch_hash<FLT, false>(h, p, b, (const uint32_t*)h->list[b].p, (uint32_t)nb[b], nullptr)));
+      NLP_CUDA(h, cudaEventRecord(h->ev_phase[6 - b], h->stream));
+    }
     NLP_TRY((launch_tiny<FLT>(h, p, 1, (const uint32_t*)h->list[1].p, (uint32_t)nb[1])));
+    NLP_CUDA(h, cudaEventRecord(h->ev_phase[5], h->stream));
     NLP_TRY((launch_tiny<FLT>(h, p, 0, (const uint32_t*)h->list[0].p, (uint32_t)nb[0])));
+    NLP_CUDA(h, cudaEventRecord(h->ev_phase[6], h->stream));
     NLP_TRY(read_counters(h));
+    h->phases_valid = true;
   } else {
     // the buffer cannot hold every candidate: admit sources while there is room, then keep the
     // best K (which fixes the pruning threshold) and continue with the deferred sources
@@ -498,6 +508,7 @@ int nlp_create(nlp_handle** out, int device) {
   h->num_sms = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_frontier); cudaEventCreate(&h->ev_scored); cudaEventCreate(&h->ev_done);
+  for (int i = 0; i < 7; ++i) cudaEventCreate(&h->ev_phase[i]);
   if ((e = cudaMallocHost((void**)&h->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_hist, 12 * 256 * 8)) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_sel, sizeof(SelectState))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -526,6 +537,7 @@ int nlp_destroy(nlp_handle* h) {
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->h_hist) cudaFreeHost(h->h_hist);
   if (h->h_sel) cudaFreeHost(h->h_sel);
+  for (int i = 0; i < 7; ++i) cudaEventDestroy(h->ev_phase[i]);
   cudaEventDestroy(h->ev_start); cudaEventDestroy(h->ev_frontier); cudaEventDestroy(h->ev_scored); cudaEventDestroy(h->ev_done);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -618,6 +630,10 @@ int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res) {
   res->frontier_ms = frontier_sum / reps;
   res->select_ms = sel;
   res->time_ms = res->scoring_ms + sel;
+  NLP_CUDA(h, cudaEventElapsedTime(&res->phase_ms[0], h->ev_start, h->ev_frontier));
+  if (h->phases_valid)
+    for (int i = 1; i <= 6; ++i) NLP_CUDA(h, cudaEventElapsedTime(&res->phase_ms[i], h->ev_phase[i - 1], h->ev_phase[i]));
+  res->phase_ms[7] = sel;
   return NLP_OK;
 }
 

@@ -14,6 +14,7 @@ _spec.loader.exec_module(_pkg)
 build = _pkg.build
 binding = _pkg.binding
 graphs = _pkg.graphs
+distributed = _pkg.distributed
 Predictor = _pkg.Predictor
 MEASURES = _pkg.MEASURES
 UNBOUNDED = _pkg.UNBOUNDED

@@ -1,0 +1,162 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the golden
+vectors of the reference -- bit-exact for counts, scores and the predicted edge set."""
+import numpy as np
+import pytest
+
+import golden_util as G
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pred(nlp):
+    p = nlp.Predictor(0)
+    yield p
+    p.close()
+
+
+def _graph(nlp, name):
+    g = nlp.graphs
+    table = {
+        "rmat12": lambda: g.rmat(12, 16, 31),
+        "rmat14p": lambda: g.rmat(14, 16, 32, permute=True),
+        "road60": lambda: g.road_lattice(60, 0.6, 33),
+        "pp4k": lambda: g.planted_partition(4000, 50, 10, 2, 34),
+        "pp4k_multiset": lambda: g.duplicate_some_entries(*g.planted_partition(4000, 50, 10, 2, 35), every=4),
+        "web20k": lambda: g.web_crawl(20000, 10, window=500, seed=36),
+    }
+    return g.to_numpy(*table[name]())
+
+
+@pytest.mark.parametrize("name", G.fixture_names())
+def test_gpu_matches_reference_golden(pred, name):
+    z = G.load(name)
+    pred.set_graph(z["offsets"], z["keys"])
+    for m in G.MEASURES:
+        for D in G.DEGREES:
+            r = pred.predict(m, D)
+            u, v, s = pred.fetch(r["count"])
+            err = G.check_against(z, m, D, u, v, s)
+            assert err is None, "%s %s" % (name, err)
+
+
+@pytest.mark.parametrize("name", ["rmat12", "rmat14p", "road60", "pp4k", "pp4k_multiset", "web20k"])
+@pytest.mark.parametrize("D", [0, 2, 4, 32, 1024])
+def test_gpu_matches_oracle(pred, oracle, nlp, name, D):
+    off, keys = _graph(nlp, name)
+    pred.set_graph(off, keys)
+    K = max(3, len(keys) // 20)
+    for m in nlp.MEASURES:
+        for k in (K, nlp.UNBOUNDED) if (D != 0 or name != "rmat14p") else (K,):
+            err, r, st = parity.check_case(pred, oracle, off, keys, m, D, k, tag=name)
+            assert err is None, err
+
+
+def test_tie_rule_and_known_answer(pred):
+    off, keys = parity.kat_graph()
+    pred.set_graph(off, keys)
+    r = pred.predict("JC", 0, max_edges=3)
+    u, v, s = pred.fetch(r["count"])
+    assert list(zip(u.tolist(), v.tolist())) == [(1, 2), (3, 4), (1, 7)]
+    assert s.view(np.uint32).tolist() == [0x3f2aaaab, 0x3f2aaaab, 0x3eaaaaab]
+    r = pred.predict("AA", 0)
+    u, v, s = pred.fetch(r["count"])
+    assert s.view(np.uint32).tolist()[:3] == [0x4016967a, 0x4016967a, 0x3fb8aa3b]
+
+
+def test_edge_cases(pred, oracle, nlp):
+    # empty graph / no edges / max_edges = 0 / min_score / max_factor2 / arbitrary D
+    pred.set_graph(np.zeros(1, np.uint64), np.empty(0, np.uint32))
+    assert pred.predict("JC", 4)["count"] == 0
+    pred.set_graph(np.zeros(11, np.uint64), np.empty(0, np.uint32))
+    assert pred.predict("CN", 0)["count"] == 0
+    off, keys = parity.kat_graph()
+    pred.set_graph(off, keys)
+    assert pred.predict("JC", 0, max_edges=0)["count"] == 0
+    off, keys = _graph(nlp, "rmat12")
+    pred.set_graph(off, keys)
+    for m, D, kw in (("JC", 0, dict(min_score=0.25)), ("CN", 7, dict(min_score=2.0)), ("HP", 0, dict(max_factor2=2)),
+                     ("AA", 3, dict(max_factor2=1)), ("SC", 5, dict(min_score=-1.0)), ("RA", 100000, {})):
+        err, r, st = parity.check_case(pred, oracle, off, keys, m, D, 5000, tag="edge", **kw)
+        assert err is None, err
+    with pytest.raises(nlp.NlpError):
+        pred.predict(11, 4)
+
+
+def test_pruned_buffer_passes(pred, oracle, nlp):
+    """Force the candidate buffer to be far smaller than the candidate set: sources are admitted
+    while there is room, the buffer is cut to the best K (threshold), deferred sources follow."""
+    off, keys = _graph(nlp, "rmat14p")
+    pred.set_graph(off, keys)
+    try:
+        K = 2000
+        S = len(off) - 1
+        pred.set_scratch_limit((K + S + 4096 + 50000) * 24 * 10 // 8 + (64 << 20))
+        for m, D in (("CN", 0), ("JC", 0), ("AA", 0), ("JC", 1024)):
+            err, r, st = parity.check_case(pred, oracle, off, keys, m, D, K, tag="pruned")
+            assert err is None, err
+            if D == 0:
+                assert r["passes"] > 1, r
+    finally:
+        pred.set_scratch_limit(0)
+
+
+def test_partitions_merge_to_single_gpu_result(pred, oracle, nlp):
+    """Two ranks emulated one after the other on one GPU: local top-K of each source partition,
+    concatenated and merged with nlp_merge, equals the unpartitioned result."""
+    import torch
+    off, keys = _graph(nlp, "rmat12")
+    pred.set_graph(off, keys)
+    K = 3000
+    for m, D in (("JC", 0), ("AA", 4), ("CN", 16)):
+        parts = []
+        for rank in range(3):
+            pred.set_partition(rank, 3)
+            r = pred.predict(m, D, max_edges=K)
+            parts.append(pred.fetch(r["count"]))
+        pred.set_partition(0, 1)
+        u = torch.from_numpy(np.concatenate([p[0] for p in parts]).view(np.int32)).cuda()
+        v = torch.from_numpy(np.concatenate([p[1] for p in parts]).view(np.int32)).cuda()
+        s = torch.from_numpy(np.concatenate([p[2] for p in parts])).cuda()
+        pred.merge(u.data_ptr(), v.data_ptr(), s.data_ptr(), u.numel(), K)
+        got = pred.fetch(min(K, u.numel()))
+        want = oracle.oracle_predict(off, keys, m, D, max_edges=K)[:3]
+        assert parity.compare(got, want, "merge %s D=%d" % (m, D)) is None
+
+
+def test_properties_at_scale(pred, nlp):
+    """BASELINE-sized properties that need no oracle: sorted canonical order, u < v, no existing
+    edge predicted, idempotence, top-K is a prefix of top-2K, counters consistent."""
+    import torch
+    g = nlp.graphs
+    o, k = g.rmat(20, 16, 43, permute=True, device="cuda")
+    o, k, rl, rh = g.remove_edges(o, k, 0.1, 1043)
+    K = int(rl.numel())
+    S = o.numel() - 1
+    pred.set_graph_pointers(o.data_ptr(), k.data_ptr(), S, device=True, keep=(o, k))
+    for m in ("JC", "AA"):
+        r = pred.predict(m, 16, max_edges=K)
+        assert r["count"] == K and r["kept"] >= K
+        u, v, s = pred.fetch(K)
+        assert (u < v).all()
+        key = np.lexsort((v, u, -s.astype(np.float64)))
+        assert (key == np.arange(K)).all(), "result not in canonical order"
+        # no predicted pair is an existing edge
+        comp = torch.from_numpy(u.astype(np.int64) * (S + 1) + v.astype(np.int64)).cuda()
+        deg = (o[1:] - o[:-1])
+        src = torch.repeat_interleave(torch.arange(S, device="cuda"), deg)
+        ecomp = src * (S + 1) + k.to(torch.int64)
+        assert not torch.isin(comp, ecomp).any()
+        r2 = pred.predict(m, 16, max_edges=K)
+        u2, v2, s2 = pred.fetch(K)
+        assert parity.compare((u2, v2, s2), (u, v, s), "idempotence") is None
+        r3 = pred.predict(m, 16, max_edges=K // 2)
+        u3, v3, s3 = pred.fetch(K // 2)
+        assert parity.compare((u3, v3, s3), (u[:K // 2], v[:K // 2], s[:K // 2]), "prefix") is None
+        assert r["first_hop"] == int(k.numel()) and r["wedges"] >= r["candidates"] >= r["kept"]
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
