@@ -367,17 +367,16 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
     want = std::min<uint64_t>(want, nb[5]);
     const uint64_t afford = std::max<uint64_t>(1, (budget / 3) / per_slot);
     dense_slots = (unsigned)std::min<uint64_t>(want, afford);
-    const bool fresh = (uint64_t)dense_slots * S * 4 > h->tables.cap;
-    NLP_TRY(ensure(h, h->tables, (uint64_t)dense_slots * S * 4, true));
-    if (fresh) NLP_CUDA(h, cudaMemsetAsync(h->tables.p, 0, h->tables.cap, h->stream));
+    NLP_TRY(ensure(h, h->tables, (uint64_t)dense_slots * S * 4, true));   // zeroed when (re)allocated
     NLP_TRY(ensure(h, h->touched, (uint64_t)dense_slots * touched_cap * 4));
-    budget -= std::min<uint64_t>(budget, h->tables.cap + h->touched.cap);
+    budget -= std::min<uint64_t>(budget, (uint64_t)dense_slots * per_slot);
   }
   const uint64_t cap_limit = std::min<uint64_t>(budget / 24, 0xfffffff0ull);
   uint64_t want_cap = total_need;
   if (K != NLP_UNBOUNDED) {
-    const uint64_t k4 = K > (1ull << 60) ? (1ull << 62) : 4 * K;
-    want_cap = std::min<uint64_t>(total_need, std::max<uint64_t>(k4, 1ull << 24) + S + (1ull << 20));
+    // room for every candidate when that is cheap; otherwise 16 K (at least 2^27 entries = 3 GB)
+    const uint64_t k16 = K > (1ull << 58) ? (1ull << 62) : 16 * K;
+    want_cap = std::min<uint64_t>(total_need, std::max<uint64_t>(k16, 1ull << 27) + S + (1ull << 20));
   }
   const uint64_t cap = std::min<uint64_t>(want_cap, cap_limit);
   const bool admit = cap < total_need;
