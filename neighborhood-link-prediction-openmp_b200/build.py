@@ -1,12 +1,12 @@
 """Build the CUDA shared library (sm_100a only) in-tree with nvcc."""
+import glob
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libnlp_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "nlp_b200.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "frontier.cuh", "wedge.cuh", "select.cuh")] + \
-          [os.path.join(HERE, "..", "include", "nlp_b200.h")]
+HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [os.path.join(HERE, "..", "include", "nlp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
 

@@ -12,6 +12,10 @@ namespace nlp {
 enum Measure { M_CN = 0, M_JC, M_SI, M_SC, M_HP, M_HD, M_LHN, M_AA, M_RA };
 
 enum { NBINS = 6 };
+// Rows longer than LONG_ROW first-hop entries are cut into CHUNK-entry pieces by the frontier
+// pass (one block per piece), so that a hub's row never serialises a single warp.
+constexpr uint32_t LONG_ROW = 2048;
+constexpr uint32_t CHUNK = 2048;
 // Source bins (north_star kernel (a)): which path a source vertex takes.
 //   0: 8-lane sub-warp groups   (work <= 8)        1: 32-lane warp (work <= 32)
 //   2: smem hash, 1K slots      (bound <= 768)     3: smem hash, 4K slots (bound <= 3072)
@@ -63,6 +67,14 @@ struct Params {
   const uint32_t* elig;     // LHub eligibility bitmask (bit w = deg(w) <= D), null for IHub
   const double*   gtable;   // Adamic-Adar: gtable[d] = 1.0 / log((double)d), host libm values
   const uint32_t* work;     // [S] saturated work(u)
+  // LHub: eligible first-hop entries (deg(w) <= D, deg(w) > 0) compacted by the frontier pass.
+  // Row u's entries start at ekeys[off[u]]; a short row holds ecount[u] of them, a long row
+  // (deg(u) > LONG_ROW) holds chunk_cnt[chunk_base[u] + c] at ekeys[off[u] + c * CHUNK].
+  // Null for IHub (every first-hop entry is eligible: the row itself is the list).
+  const uint32_t* ekeys;
+  const uint32_t* ecount;
+  const unsigned long long* chunk_base;
+  const uint32_t* chunk_cnt;
   uint32_t* cu; uint32_t* cv; float* cs;   // candidate buffer (SoA)
   unsigned long long cap;
   Counters* ctr;

@@ -1,26 +1,47 @@
 // Kernel (a) of the north star: the work-balanced frontier.
-//   k_degrees : deg[u] = off[u+1]-off[u]                       (once per graph)
-//   k_elig    : LHub eligibility bitmask, bit w = deg(w) <= D  (replaces the dependent random
-//               degree load of inc/predict.hxx:301 by an L2-resident 1-bit lookup)
-//   k_work    : work(u) = sum_{eligible w in N(u)} deg(w)      (wedges the reference would scan
-//               for u, inc/predict.hxx:298-304) -- one coalesced pass over the adjacency
-//   k_bin     : drop zero-work sources (inc/predict.hxx:287-289 visits them all) and bin the
-//               rest by work into the sub-warp / warp / block-hash / dense-spill paths
+//   k_degrees      deg[u] = off[u+1]-off[u]; number of 2048-entry chunks of every long row
+//                  (once per graph)
+//   k_chunk_fill   chunk -> source row table for the long rows (once per graph)
+//   k_elig         LHub eligibility bitmask, bit w = deg(w) <= D (replaces the dependent random
+//                  degree load of inc/predict.hxx:301 by an L2-resident 1-bit lookup)
+//   k_work_short   one coalesced pass over the adjacency of all short rows: per source
+//   k_work_long    work(u) = sum_{eligible w in N(u)} deg(w) (wedges the reference would scan for
+//                  u, inc/predict.hxx:298-304) and, for LHub, the COMPACTED list of eligible
+//                  first-hop entries, so the wedge kernels never touch a hub's row again.
+//                  Long rows are cut into 2048-entry chunks (one block each) so a 10^5..10^6-degree
+//                  hub does not serialise one warp.
+//   k_bin          drop zero-work sources (inc/predict.hxx:287-289 visits them all) and bin the
+//                  rest by work into the sub-warp / block-hash / dense-spill paths
 #pragma once
 #include "common.cuh"
 
 namespace nlp {
 
 __global__ void __launch_bounds__(256) k_degrees(const uint64_t* __restrict__ off, uint32_t S,
-                                                 uint32_t* __restrict__ deg, uint32_t* maxdeg) {
+                                                 uint32_t* __restrict__ deg, unsigned long long* __restrict__ nchunks,
+                                                 uint32_t* maxdeg) {
   uint32_t local = 0;
   for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < S; u += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t d = (uint32_t)(off[u + 1] - off[u]);
     deg[u] = d;
+    nchunks[u] = d > LONG_ROW ? (d + CHUNK - 1) / CHUNK : 0u;
     local = max(local, d);
   }
   local = __reduce_max_sync(NLP_FULL, local);
   if ((threadIdx.x & 31) == 0 && local) atomicMax(maxdeg, local);
+}
+
+// chunk_base = exclusive scan of nchunks; chunk_src[chunk_base[u] + c] = u
+__global__ void __launch_bounds__(256) k_chunk_fill(const uint32_t* __restrict__ deg, const unsigned long long* __restrict__ chunk_base,
+                                                    uint32_t S, uint32_t* __restrict__ chunk_src) {
+  for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < S; u += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t d = deg[u];
+    if (d > LONG_ROW) {
+      const uint32_t n = (d + CHUNK - 1) / CHUNK;
+      const unsigned long long b = chunk_base[u];
+      for (uint32_t c = 0; c < n; ++c) chunk_src[b + c] = (uint32_t)u;
+    }
+  }
 }
 
 // One thread builds one 32-bit word of the mask.
@@ -44,66 +65,98 @@ __host__ __device__ inline bool owns_row_block(uint64_t rb, int rank, int world)
   return world <= 1 || (int)(rb % (uint64_t)world) == rank;
 }
 
-// One warp streams the adjacency of 32 consecutive rows (one contiguous, coalesced range of
-// `keys`), looks up eligibility of every first-hop entry and segment-sums deg(w) per row.
+struct WorkOut {
+  unsigned long long* work64;   // [S]   exact work(u)
+  uint32_t* ecount;             // [S]   compacted eligible entries of a short row
+  uint32_t* ekeys;              // [M]   compacted eligible first-hop entries, row u at off[u]
+  uint32_t* chunk_cnt;          // [NC]  compacted entries of every long-row chunk
+};
+
+// One warp streams the adjacency of the short rows among 32 consecutive rows, packed back to
+// back (coalesced), looks up eligibility of every first-hop entry, segment-sums deg(w) per row
+// and (LHub) writes the eligible entries with deg(w) > 0 compacted to the front of the row's
+// slot in `ekeys`, order preserved.
 template <bool LHUB>
-__global__ void __launch_bounds__(256) k_work(DevGraph g, const uint32_t* __restrict__ elig, int rank, int world,
-                                              uint32_t* __restrict__ work, Counters* ctr) {
+__global__ void __launch_bounds__(256) k_work_short(DevGraph g, const uint32_t* __restrict__ elig, int rank, int world,
+                                                    WorkOut o, Counters* ctr) {
   __shared__ unsigned long long acc[8][32];
+  __shared__ uint32_t cnt[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
   const uint64_t nrb = ((uint64_t)g.S + 31u) >> 5;
   unsigned long long t_first = 0, t_elig = 0, t_wedges = 0;
   for (uint64_t rb = blockIdx.x * 8ull + wib; rb < nrb; rb += gridDim.x * 8ull) {
     if (!owns_row_block(rb, rank, world)) continue;
     const uint64_t row = rb * 32u + lane;
-    const uint64_t r0 = row < g.S ? row : g.S;
-    const uint64_t r1 = row < g.S ? row + 1 : g.S;
-    const uint64_t b0 = g.off[r0];
-    const uint64_t e_end = g.off[r1];
-    const uint64_t B = __shfl_sync(NLP_FULL, b0, 0);
-    const uint64_t E = __shfl_sync(NLP_FULL, e_end, 31);
+    uint64_t b0 = 0;
+    uint32_t d = 0;
+    if (row < g.S) { b0 = g.off[row]; d = (uint32_t)(g.off[row + 1] - b0); }
+    const uint32_t sl = d > LONG_ROW ? 0u : d;
+    uint32_t inc = sl;
+    #pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+      const uint32_t t = __shfl_up_sync(NLP_FULL, inc, k);
+      if (lane >= k) inc += t;
+    }
+    const uint32_t T = __shfl_sync(NLP_FULL, inc, 31);
     acc[wib][lane] = 0;
+    cnt[wib][lane] = 0;
     __syncwarp();
-    for (uint64_t base = B; base < E; base += 32) {
-      const uint64_t idx = base + lane;
-      const bool valid = idx < E;
-      uint32_t c = 0;
-      bool el = false;
-      if (valid) {
-        const uint32_t w = __ldg(g.keys + idx);
-        el = LHUB ? (((__ldg(elig + (w >> 5)) >> (w & 31)) & 1u) != 0u) : true;
-        if (el) c = __ldg(g.deg + w);
-      }
-      // row of this entry: smallest j with e_end[j] > idx
-      int j = 0;
+    for (uint32_t base = 0; base < T; base += 32) {
+      const uint32_t t = base + lane;
+      const bool valid = t < T;
+      int j = 0;                                   // smallest j with inc[j] > t
       #pragma unroll
       for (int step = 16; step >= 1; step >>= 1) {
-        const uint64_t x = __shfl_sync(NLP_FULL, e_end, j + step - 1);
-        if (x <= idx) j += step;
+        const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
+        if (x <= t) j += step;
+      }
+      const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
+      const uint32_t slj  = __shfl_sync(NLP_FULL, sl, j);
+      const uint64_t b0j  = __shfl_sync(NLP_FULL, b0, j);
+      uint32_t w = 0, c = 0;
+      bool el = false;
+      if (valid) {
+        w = __ldg(g.keys + b0j + (t - (incj - slj)));
+        el = LHUB ? (((__ldg(elig + (w >> 5)) >> (w & 31)) & 1u) != 0u) : true;
+        if (el) c = __ldg(g.deg + w);
       }
       t_first += valid ? 1u : 0u;
       t_elig += el ? 1u : 0u;
       t_wedges += c;
       const int j0 = __shfl_sync(NLP_FULL, j, 0);
       const bool uni = __all_sync(NLP_FULL, !valid || j == j0);
-      if (uni) {   // whole batch inside one (long) row: one shared-memory update
+      if (uni) {   // whole batch inside one row: one shared-memory update
         const uint32_t lo = __reduce_add_sync(NLP_FULL, c & 0xffffu);
         const uint32_t hi = __reduce_add_sync(NLP_FULL, c >> 16);
         if (lane == 0) acc[wib][j0] += (unsigned long long)lo + ((unsigned long long)hi << 16);
       } else if (c) {
         atomicAdd(&acc[wib][j], (unsigned long long)c);
       }
+      if (LHUB) {
+        const bool keep = c != 0;
+        const unsigned km = __ballot_sync(NLP_FULL, keep);
+        if (km) {
+          const unsigned m = uni ? __ballot_sync(NLP_FULL, valid) : __match_any_sync(NLP_FULL, valid ? (unsigned)j : 32u + lane);
+          const uint32_t before = valid ? cnt[wib][j] : 0u;
+          if (keep) o.ekeys[b0j + before + __popc(m & km & lt)] = w;
+          __syncwarp();
+          if (valid && (__ffs(m) - 1) == lane) cnt[wib][j] = before + __popc(m & km);
+        }
+      }
       __syncwarp();
     }
-    const unsigned long long a = acc[wib][lane];
-    if (row < g.S) work[row] = a > 0xffffffffull ? 0xffffffffu : (uint32_t)a;
+    if (row < g.S) {
+      o.work64[row] = acc[wib][lane];       // 0 for long rows: k_work_long adds to it
+      if (LHUB) o.ecount[row] = cnt[wib][lane];
+    }
     __syncwarp();
   }
   #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) {
-    t_first  += __shfl_xor_sync(NLP_FULL, t_first, d);
-    t_elig   += __shfl_xor_sync(NLP_FULL, t_elig, d);
-    t_wedges += __shfl_xor_sync(NLP_FULL, t_wedges, d);
+  for (int k = 16; k >= 1; k >>= 1) {
+    t_first  += __shfl_xor_sync(NLP_FULL, t_first, k);
+    t_elig   += __shfl_xor_sync(NLP_FULL, t_elig, k);
+    t_wedges += __shfl_xor_sync(NLP_FULL, t_wedges, k);
   }
   if (lane == 0) {
     if (t_first)  atomicAdd(&ctr->first_hop, t_first);
@@ -112,60 +165,164 @@ __global__ void __launch_bounds__(256) k_work(DevGraph g, const uint32_t* __rest
   }
 }
 
+// One block per 2048-entry chunk of a long row.
+template <bool LHUB>
+__global__ void __launch_bounds__(256) k_work_long(DevGraph g, const uint32_t* __restrict__ elig, int rank, int world,
+                                                   const uint32_t* __restrict__ chunk_src,
+                                                   const unsigned long long* __restrict__ chunk_base, uint32_t nchunks,
+                                                   WorkOut o, Counters* ctr) {
+  __shared__ uint32_t warp_keep[8];
+  __shared__ unsigned long long warp_sum[8][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const uint32_t u = chunk_src[c];
+    if (!owns_row_block(u >> 5, rank, world)) continue;
+    const uint32_t ci = (uint32_t)(c - chunk_base[u]);
+    const uint64_t rb = g.off[u], re = g.off[u + 1];
+    const uint64_t cb = rb + (uint64_t)ci * CHUNK;
+    const uint64_t ce = cb + CHUNK < re ? cb + CHUNK : re;
+    unsigned long long t_first = 0, t_elig = 0, t_wedges = 0;
+    uint32_t written = 0;                            // block-uniform running count of kept entries
+    for (uint64_t base = cb; base < ce; base += 256) {
+      const uint64_t e = base + tid;
+      const bool valid = e < ce;
+      uint32_t w = 0, cw = 0;
+      bool el = false;
+      if (valid) {
+        w = __ldg(g.keys + e);
+        el = LHUB ? (((__ldg(elig + (w >> 5)) >> (w & 31)) & 1u) != 0u) : true;
+        if (el) cw = __ldg(g.deg + w);
+      }
+      t_first += valid ? 1u : 0u;
+      t_elig += el ? 1u : 0u;
+      t_wedges += cw;
+      if (LHUB) {
+        const bool keep = cw != 0;
+        const unsigned km = __ballot_sync(NLP_FULL, keep);
+        if (lane == 0) warp_keep[warp] = __popc(km);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint32_t x = warp_keep[k]; if (k < warp) before += x; total += x; }
+        if (keep) o.ekeys[cb + written + before + __popc(km & lt)] = w;
+        written += total;
+        __syncthreads();
+      }
+    }
+    #pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+      t_first  += __shfl_xor_sync(NLP_FULL, t_first, k);
+      t_elig   += __shfl_xor_sync(NLP_FULL, t_elig, k);
+      t_wedges += __shfl_xor_sync(NLP_FULL, t_wedges, k);
+    }
+    if (lane == 0) { warp_sum[warp][0] = t_first; warp_sum[warp][1] = t_elig; warp_sum[warp][2] = t_wedges; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long a = 0, b = 0, w = 0;
+      for (int k = 0; k < 8; ++k) { a += warp_sum[k][0]; b += warp_sum[k][1]; w += warp_sum[k][2]; }
+      if (w) atomicAdd(&o.work64[u], w);
+      if (LHUB) o.chunk_cnt[c] = written;
+      atomicAdd(&ctr->first_hop, a);
+      if (b) atomicAdd(&ctr->eligible_first_hop, b);
+      if (w) atomicAdd(&ctr->wedges, w);
+    }
+    __syncthreads();
+  }
+}
+
 struct BinLists { uint32_t* list[NBINS]; };
 
-__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du) {
-  if (work <= 8u && du <= 64u) return 0;
-  if (work <= 32u && du <= 256u) return 1;
+// flt: the float measures send every source above the 1K-slot hash bin to the sort-based path
+__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, bool flt) {
+  if (du <= LONG_ROW) {
+    if (work <= 8u) return 0;
+    if (work <= 32u) return 1;
+  }
   if (bound <= bin_limit(2)) return 2;
+  if (flt) return 3;
   if (bound <= bin_limit(3)) return 3;
   if (bound <= bin_limit(4)) return 4;
   return 5;
 }
 
-__global__ void __launch_bounds__(256) k_bin(DevGraph g, const uint32_t* __restrict__ work, int rank, int world,
-                                             BinLists bl, Counters* ctr) {
+__global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long long* __restrict__ work64, int rank, int world,
+                                             bool flt, uint32_t* __restrict__ work, BinLists bl, Counters* ctr) {
+  __shared__ unsigned long long s_cnt[NBINS], s_sum[NBINS], s_base[NBINS], s_max;
   const int lane = threadIdx.x & 31;
-  const uint64_t S32 = ((uint64_t)g.S + 31u) & ~31ull;
-  for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < S32; u += (uint64_t)gridDim.x * blockDim.x) {
+  if (threadIdx.x < NBINS) { s_cnt[threadIdx.x] = 0; s_sum[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  // every block handles one contiguous tile of vertices, so it needs one global atomic per bin
+  const uint64_t per = (((uint64_t)g.S + gridDim.x - 1) / gridDim.x + 255u) & ~255ull;
+  const uint64_t lo = blockIdx.x * per, hi = lo + per < g.S ? lo + per : g.S;
+  // pass 1: classify + count
+  for (uint64_t base = lo; base < hi; base += 256) {
+    const uint64_t u = base + threadIdx.x;
     int bin = -1;
     uint32_t need = 0;
-    if (u < g.S && owns_row_block(u >> 5, rank, world)) {
-      const uint32_t w = work[u];
+    if (u < hi && owns_row_block(u >> 5, rank, world)) {
+      const unsigned long long w64 = work64[u];
+      const uint32_t w = w64 > 0xffffffffull ? 0xffffffffu : (uint32_t)w64;
+      work[u] = w;
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        bin = choose_bin(w, bound, g.deg[u]);
-        need = bin < 2 ? w : bound;
-        if (bound == 0) bin = -1;    // last vertex: no v > u exists
+        if (bound) { bin = choose_bin(w, bound, g.deg[u], flt); need = bin < 2 ? w : bound; }
       }
     }
-    const unsigned any = __ballot_sync(NLP_FULL, bin >= 0);
-    if (!any) continue;
     #pragma unroll
     for (int b = 0; b < NBINS; ++b) {
       const unsigned m = __ballot_sync(NLP_FULL, bin == b);
       if (!m) continue;
-      const int leader = __ffs(m) - 1;
-      unsigned long long sum = (bin == b) ? need : 0;
-      unsigned long long mx = (bin == b) ? need : 0;
+      unsigned long long sum = (bin == b) ? need : 0, mx = sum;
       #pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) {
-        sum += __shfl_xor_sync(NLP_FULL, sum, d);
-        const unsigned long long o = __shfl_xor_sync(NLP_FULL, mx, d);
+      for (int k = 16; k >= 1; k >>= 1) {
+        sum += __shfl_xor_sync(NLP_FULL, sum, k);
+        const unsigned long long o = __shfl_xor_sync(NLP_FULL, mx, k);
         mx = o > mx ? o : mx;
       }
-      unsigned long long base = 0;
-      if (lane == leader) {
-        base = atomicAdd(&ctr->bin_count[b], (unsigned long long)__popc(m));
-        atomicAdd(&ctr->bin_bound[b], sum);
-        if (b == 5) atomicMax(&ctr->max_bound, mx);
+      if (lane == 0) {
+        atomicAdd(&s_cnt[b], (unsigned long long)__popc(m));
+        atomicAdd(&s_sum[b], sum);
+        if (b >= 3) atomicMax(&s_max, mx);
       }
-      base = __shfl_sync(NLP_FULL, base, leader);
-      if (bin == b) bl.list[b][base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)u;
     }
-    if (lane == 0) atomicAdd(&ctr->frontier, (unsigned long long)__popc(any));
   }
+  __syncthreads();
+  if (threadIdx.x < NBINS) {
+    const unsigned long long c = s_cnt[threadIdx.x];
+    s_base[threadIdx.x] = c ? atomicAdd(&ctr->bin_count[threadIdx.x], c) : 0;
+    if (c) atomicAdd(&ctr->bin_bound[threadIdx.x], s_sum[threadIdx.x]);
+    s_cnt[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0 && s_max) atomicMax(&ctr->max_bound, s_max);
+  __syncthreads();
+  // pass 2: same classification (work[] was just written by this block), now append
+  unsigned long long frontier = 0;
+  for (uint64_t base = lo; base < hi; base += 256) {
+    const uint64_t u = base + threadIdx.x;
+    int bin = -1;
+    if (u < hi && owns_row_block(u >> 5, rank, world)) {
+      const uint32_t w = work[u];
+      if (w) {
+        const uint32_t room = g.S - 1u - (uint32_t)u;
+        const uint32_t bound = w < room ? w : room;
+        if (bound) bin = choose_bin(w, bound, g.deg[u], flt);
+      }
+    }
+    #pragma unroll
+    for (int b = 0; b < NBINS; ++b) {
+      const unsigned m = __ballot_sync(NLP_FULL, bin == b);
+      if (!m) continue;
+      unsigned long long at = 0;
+      if (lane == 0) at = atomicAdd(&s_cnt[b], (unsigned long long)__popc(m));
+      at = __shfl_sync(NLP_FULL, at, 0);
+      if (bin == b) bl.list[b][s_base[b] + at + __popc(m & ((1u << lane) - 1u))] = (uint32_t)u;
+      if (lane == 0) frontier += __popc(m);
+    }
+  }
+  if (lane == 0 && frontier) atomicAdd(&ctr->frontier, frontier);
 }
 
 }  // namespace nlp

@@ -4,6 +4,7 @@
 // There is no CPU fallback anywhere in this file: every step is a kernel launch.
 #include "../../include/nlp_b200.h"
 #include "common.cuh"
+#include "scan.cuh"
 #include "frontier.cuh"
 #include "wedge.cuh"
 #include "select.cuh"
@@ -43,7 +44,11 @@ struct nlp_handle {
   uint64_t M = 0;
   uint32_t maxdeg = 0;
   bool has_graph = false;
-  DevBuf deg, work, elig, maxdeg_dev;
+  DevBuf deg, work, work64, elig, maxdeg_dev;
+  DevBuf chunk_base, chunk_src, chunk_cnt;   // long rows (deg > LONG_ROW) cut into CHUNK-entry pieces
+  uint64_t nchunks = 0;
+  DevBuf ecount, ekeys;                      // LHub: compacted eligible first-hop lists
+  DevBuf scan_tiles, scan_total;
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
   uint32_t gtable_n = 0;
@@ -133,10 +138,34 @@ DevGraph dev_graph(const nlp_handle* h) {
 }
 
 // ---- graph -----------------------------------------------------------------------------------
+// out[i] = sum of in[0..i); returns the grand total in *total (host).  in/out may alias for u64.
+template <class TIn>
+int exclusive_scan(nlp_handle* h, const TIn* in, uint64_t n, unsigned long long* out, uint64_t* total) {
+  *total = 0;
+  if (!n) return NLP_OK;
+  const uint32_t ntiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+  NLP_TRY(ensure(h, h->scan_tiles, (size_t)ntiles * 8));
+  NLP_TRY(ensure(h, h->scan_total, 16));
+  k_scan_tiles<TIn><<<ntiles, SCAN_THREADS, 0, h->stream>>>(in, n, (unsigned long long*)h->scan_tiles.p);
+  NLP_LAUNCHED(h);
+  k_scan_spine<<<1, SCAN_THREADS, 0, h->stream>>>((unsigned long long*)h->scan_tiles.p, ntiles,
+                                                  (unsigned long long*)h->scan_total.p);
+  NLP_LAUNCHED(h);
+  k_scan_apply<TIn><<<ntiles, SCAN_THREADS, 0, h->stream>>>(in, n, (const unsigned long long*)h->scan_tiles.p, out);
+  NLP_LAUNCHED(h);
+  unsigned long long t = 0;
+  NLP_CUDA(h, cudaMemcpyAsync(&t, h->scan_total.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  *total = t;
+  return NLP_OK;
+}
+
 int finish_graph(nlp_handle* h) {
   const uint32_t S = h->S;
   NLP_TRY(ensure(h, h->deg, (size_t)S * 4));
   NLP_TRY(ensure(h, h->work, (size_t)S * 4));
+  NLP_TRY(ensure(h, h->work64, (size_t)S * 8));
+  NLP_TRY(ensure(h, h->chunk_base, (size_t)S * 8));
   NLP_TRY(ensure(h, h->elig, ((size_t)S + 31) / 32 * 4));
   NLP_TRY(ensure(h, h->maxdeg_dev, 16));
   for (int b = 0; b < NBINS; ++b) {
@@ -146,10 +175,22 @@ int finish_graph(nlp_handle* h) {
   NLP_CUDA(h, cudaMemsetAsync(h->maxdeg_dev.p, 0, 16, h->stream));
   uint64_t m = 0;
   NLP_CUDA(h, cudaMemcpyAsync(&m, h->d_off + S, 8, cudaMemcpyDeviceToHost, h->stream));
+  h->nchunks = 0;
   if (S) {
     k_degrees<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->d_off, S, (uint32_t*)h->deg.p,
+                                                                        (unsigned long long*)h->chunk_base.p,
                                                                         (uint32_t*)h->maxdeg_dev.p);
     NLP_LAUNCHED(h);
+    // chunk table of the long rows: chunk_base[u] = first chunk of row u, chunk_src[c] = its row
+    NLP_TRY(exclusive_scan<unsigned long long>(h, (const unsigned long long*)h->chunk_base.p, S,
+                                               (unsigned long long*)h->chunk_base.p, &h->nchunks));
+    NLP_TRY(ensure(h, h->chunk_src, (size_t)h->nchunks * 4));
+    NLP_TRY(ensure(h, h->chunk_cnt, (size_t)h->nchunks * 4));
+    if (h->nchunks) {
+      k_chunk_fill<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+          (const uint32_t*)h->deg.p, (const unsigned long long*)h->chunk_base.p, S, (uint32_t*)h->chunk_src.p);
+      NLP_LAUNCHED(h);
+    }
   }
   uint32_t md = 0;
   NLP_CUDA(h, cudaMemcpyAsync(&md, h->maxdeg_dev.p, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -278,9 +319,10 @@ template <bool FLT, bool ADMIT>
 int launch_hash(nlp_handle* h, const Params& p, int bin, const uint32_t* list, uint32_t n, uint32_t* deferred) {
   if (!n) return NLP_OK;
   const HashCfg c = hash_cfg(bin, FLT);
-  const size_t smem = ((size_t)8) << c.log2_slots;
+  // slots {key,value} + u16 list of the claimed slots (at most bin_limit of them)
+  const size_t smem = (((size_t)8) << c.log2_slots) + (size_t)bin_limit(bin) * 2;
   auto kern = k_hash<FLT, ADMIT>;
-  NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   int occ = 1;
   NLP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, smem));
   if (occ < 1) occ = 1;
@@ -324,21 +366,42 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
   const DevGraph g = dev_graph(h);
   // (a) frontier
+  WorkOut wo;
+  wo.work64 = (unsigned long long*)h->work64.p;
+  wo.ecount = nullptr; wo.ekeys = nullptr;
+  wo.chunk_cnt = (uint32_t*)h->chunk_cnt.p;
+  const uint64_t nrb = ((uint64_t)S + 31) / 32;
+  const unsigned gshort = grid_for(nrb, 8, h->num_sms * 16);
+  const unsigned glong = (unsigned)std::min<uint64_t>(h->nchunks, (uint64_t)h->num_sms * 16);
   if (lhub) {
-    k_elig<<<grid_for(((uint64_t)S + 31) / 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+    NLP_TRY(ensure(h, h->ecount, (size_t)S * 4));
+    NLP_TRY(ensure(h, h->ekeys, (size_t)h->M * 4));
+    wo.ecount = (uint32_t*)h->ecount.p; wo.ekeys = (uint32_t*)h->ekeys.p;
+    k_elig<<<grid_for(nrb, 256, h->num_sms * 8), 256, 0, h->stream>>>(
         (const uint32_t*)h->deg.p, S, opt->min_degree1, (uint32_t*)h->elig.p);
     NLP_LAUNCHED(h);
-    k_work<true><<<grid_for(((uint64_t)S + 31) / 32, 8, h->num_sms * 8), 256, 0, h->stream>>>(
-        g, (const uint32_t*)h->elig.p, h->rank, h->world, (uint32_t*)h->work.p, (Counters*)h->ctr.p);
+    k_work_short<true><<<gshort, 256, 0, h->stream>>>(g, (const uint32_t*)h->elig.p, h->rank, h->world, wo, (Counters*)h->ctr.p);
+    NLP_LAUNCHED(h);
+    if (glong) {
+      k_work_long<true><<<glong, 256, 0, h->stream>>>(g, (const uint32_t*)h->elig.p, h->rank, h->world,
+                                                       (const uint32_t*)h->chunk_src.p, (const unsigned long long*)h->chunk_base.p,
+                                                       (uint32_t)h->nchunks, wo, (Counters*)h->ctr.p);
+      NLP_LAUNCHED(h);
+    }
   } else {
-    k_work<false><<<grid_for(((uint64_t)S + 31) / 32, 8, h->num_sms * 8), 256, 0, h->stream>>>(
-        g, nullptr, h->rank, h->world, (uint32_t*)h->work.p, (Counters*)h->ctr.p);
+    k_work_short<false><<<gshort, 256, 0, h->stream>>>(g, nullptr, h->rank, h->world, wo, (Counters*)h->ctr.p);
+    NLP_LAUNCHED(h);
+    if (glong) {
+      k_work_long<false><<<glong, 256, 0, h->stream>>>(g, nullptr, h->rank, h->world,
+                                                        (const uint32_t*)h->chunk_src.p, (const unsigned long long*)h->chunk_base.p,
+                                                        (uint32_t)h->nchunks, wo, (Counters*)h->ctr.p);
+      NLP_LAUNCHED(h);
+    }
   }
-  NLP_LAUNCHED(h);
   BinLists bl;
   for (int b = 0; b < NBINS; ++b) bl.list[b] = (uint32_t*)h->list[b].p;
-  k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const uint32_t*)h->work.p, h->rank, h->world, bl,
-                                                                  (Counters*)h->ctr.p);
+  k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
+                                                                  false, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -391,6 +454,10 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   Params p;
   p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
   p.elig = lhub ? (const uint32_t*)h->elig.p : nullptr;
+  p.ekeys = lhub ? (const uint32_t*)h->ekeys.p : nullptr;
+  p.ecount = lhub ? (const uint32_t*)h->ecount.p : nullptr;
+  p.chunk_base = (const unsigned long long*)h->chunk_base.p;
+  p.chunk_cnt = (const uint32_t*)h->chunk_cnt.p;
   p.gtable = (const double*)h->gtable.p;
   p.work = (const uint32_t*)h->work.p;
   p.cap = cap; p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
@@ -527,7 +594,9 @@ int nlp_destroy(nlp_handle* h) {
   if (!h) return NLP_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  release(h->own_off); release(h->own_keys); release(h->deg); release(h->work); release(h->elig); release(h->maxdeg_dev);
+  release(h->own_off); release(h->own_keys); release(h->deg); release(h->work); release(h->work64); release(h->elig); release(h->maxdeg_dev);
+  release(h->chunk_base); release(h->chunk_src); release(h->chunk_cnt); release(h->ecount); release(h->ekeys);
+  release(h->scan_tiles); release(h->scan_total);
   for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
