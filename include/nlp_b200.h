@@ -83,13 +83,26 @@ typedef struct {
   uint64_t bin_sources[8];      /* sources per path: [0]=8-lane [1]=32-lane [2..4]=hash 1K/4K/16K
                                    [5]=global dense spill, [6..7] reserved                       */
   uint32_t passes;              /* candidate-buffer passes (1 unless the buffer had to be pruned)*/
-  uint32_t reserved;
+  uint32_t path;                /* nlp_path the prediction ran on (NLP_PATH_SOURCE or NLP_PATH_PAIR) */
   float    phase_ms[8];         /* device time per phase of the LAST scoring repeat (CUDA events on
-                                   the handle's stream): [0] frontier (eligibility+work+binning)
-                                   [1] dense spill [2] hash 16K [3] hash 4K [4] hash 1K
-                                   [5] 32-lane [6] 8-lane [7] final select+sort.  [1..6] are 0
-                                   when the buffer had to be pruned (passes > 1).                */
+                                   the handle's stream).  NLP_PATH_SOURCE: [0] frontier
+                                   (eligibility+work+binning) [1] dense spill [2] hash 16K
+                                   [3] hash 4K [4] hash 1K [5] 32-lane [6] 8-lane; [1..6] are 0 when
+                                   the buffer had to be pruned (passes > 1).  NLP_PATH_PAIR:
+                                   [0] eligible rows + item descriptors + scans [1] wedge-record
+                                   emission [2] radix sort by (u, v) [3] run reduce + scoring.
+                                   Both: [7] final select+sort.                                  */
+  uint64_t pair_records;        /* NLP_PATH_PAIR: wedge records (u, v>u) emitted and sorted      */
 } nlp_result;
+
+/* Which kernels run the scoring phase.  Results are identical; the choice is about speed.
+ *   NLP_PATH_SOURCE  one team per source vertex u: frontier over all first-hop entries, wedges
+ *                    counted in shared-memory hash tables / global spill tables (IHub always).
+ *   NLP_PATH_PAIR    LHub only, graphs with symmetric rows only (checked on the device): every
+ *                    eligible row w emits its (u, v>u) pairs, the pairs are radix-sorted and
+ *                    run-length reduced.  Falls back to NLP_PATH_SOURCE when not admissible.
+ *   NLP_PATH_AUTO    NLP_PATH_PAIR when admissible, else NLP_PATH_SOURCE (default).             */
+typedef enum { NLP_PATH_AUTO = 0, NLP_PATH_SOURCE = 1, NLP_PATH_PAIR = 2 } nlp_path;
 
 /* Create a predictor bound to CUDA device `device` (one process per GPU). */
 int nlp_create(nlp_handle** out, int device);
@@ -114,6 +127,9 @@ int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_
  * graph itself is replicated.  Default (0, 1).  Replaces the OpenMP `schedule(dynamic,2048)`
  * split of inc/predict.hxx:287.                                                                */
 int nlp_set_partition(nlp_handle* h, int rank, int world);
+
+/* Force a scoring path (testing / measurement); default NLP_PATH_AUTO. */
+int nlp_set_path(nlp_handle* h, int path);
 
 /* Upper bound, in bytes, of GPU scratch (candidate buffer, spill tables) nlp_predict may use.
  * 0 = default (a fraction of the free memory at first use).                                    */

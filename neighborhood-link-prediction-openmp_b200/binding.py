@@ -16,7 +16,7 @@ STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH
           4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT"}
 
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
-           "nlp_set_scratch_limit", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
+           "nlp_set_scratch_limit", "nlp_set_path", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
            "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
@@ -30,8 +30,8 @@ class Result(C.Structure):
                 ("select_ms", C.c_float), ("frontier_ms", C.c_float), ("first_hop", C.c_uint64),
                 ("eligible_first_hop", C.c_uint64), ("wedges", C.c_uint64), ("candidates", C.c_uint64),
                 ("kept", C.c_uint64), ("emitted", C.c_uint64), ("frontier_sources", C.c_uint64),
-                ("bin_sources", C.c_uint64 * 8), ("passes", C.c_uint32), ("reserved", C.c_uint32),
-                ("phase_ms", C.c_float * 8)]
+                ("bin_sources", C.c_uint64 * 8), ("passes", C.c_uint32), ("path", C.c_uint32),
+                ("phase_ms", C.c_float * 8), ("pair_records", C.c_uint64)]
 
     def as_dict(self):
         d = {}
@@ -68,6 +68,7 @@ def load_library(build_if_missing=True):
     lib.nlp_set_graph_device.argtypes = [vp, vp, vp, u32]
     lib.nlp_set_partition.argtypes = [vp, C.c_int, C.c_int]
     lib.nlp_set_scratch_limit.argtypes = [vp, u64]
+    lib.nlp_set_path.argtypes = [vp, C.c_int]
     lib.nlp_predict.argtypes = [vp, C.POINTER(Options), C.POINTER(Result)]
     lib.nlp_fetch.argtypes = [vp, vp, vp, vp, u64]
     lib.nlp_result_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
@@ -115,6 +116,10 @@ class Predictor:
 
     def set_partition(self, rank, world):
         self._check(self.lib.nlp_set_partition(self.h, rank, world))
+
+    def set_path(self, path):
+        """0 = auto, 1 = source-centric kernels, 2 = LHub pair path (when admissible)."""
+        self._check(self.lib.nlp_set_path(self.h, path))
 
     def set_scratch_limit(self, nbytes):
         self._check(self.lib.nlp_set_scratch_limit(self.h, nbytes))

@@ -8,6 +8,7 @@
 #include "frontier.cuh"
 #include "wedge.cuh"
 #include "select.cuh"
+#include "pairs.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -49,6 +50,10 @@ struct nlp_handle {
   uint64_t nchunks = 0;
   DevBuf ecount, ekeys;                      // LHub: compacted eligible first-hop lists
   DevBuf scan_tiles, scan_total;
+  // pair path (LHub on symmetric graphs)
+  DevBuf it_u, it_cnt, it_dw, it_ptr, it_off, sym_flag;
+  int sym_state = 0;                         // 0 unknown, 1 symmetric rows, 2 not symmetric
+  int path_mode = NLP_PATH_AUTO;
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
   uint32_t gtable_n = 0;
@@ -198,6 +203,7 @@ int finish_graph(nlp_handle* h) {
   h->M = m;
   h->maxdeg = md;
   h->gtable_n = 0;
+  h->sym_state = 0;
   h->has_graph = true;
   h->has_result = false;
   return NLP_OK;
@@ -220,6 +226,24 @@ int ensure_gtable(nlp_handle* h) {
 // ---- top-K ------------------------------------------------------------------------------------
 // Sort the first n entries of candidate buffer `buf` by the canonical key; returns the buffer
 // that holds the sorted entries.
+int radix_pass(nlp_handle* h, int& buf, uint64_t n, uint32_t nblocks, int pass, bool has3) {
+  const int word = pass / 4, shift = (pass % 4) * 8;
+  const int o = buf ^ 1;
+  k_tilehist<<<nblocks, SORT_THREADS, 0, h->stream>>>((const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p,
+                                                      (const uint32_t*)h->cs[buf].p, n, word, shift,
+                                                      (uint32_t*)h->counts.p, nblocks);
+  NLP_LAUNCHED(h);
+  k_rowscan<<<256, 256, 0, h->stream>>>((uint32_t*)h->counts.p, nblocks, (uint32_t*)h->totals.p);
+  NLP_LAUNCHED(h);
+  k_scatter<<<nblocks, SORT_THREADS, 0, h->stream>>>(
+      (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p,
+      (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p, n, word, shift,
+      (const uint32_t*)h->counts.p, nblocks, (const uint32_t*)h->totals.p, has3);
+  NLP_LAUNCHED(h);
+  buf = o;
+  return NLP_OK;
+}
+
 int radix_sort(nlp_handle* h, int buf, uint64_t n, int* out_buf) {
   *out_buf = buf;
   if (n < 2) return NLP_OK;
@@ -237,20 +261,23 @@ int radix_sort(nlp_handle* h, int buf, uint64_t n, int* out_buf) {
     for (int d = 0; d < 256; ++d)
       if (h->h_hist[pass * 256 + d] == n) { constant = true; break; }
     if (constant) continue;                      // every key has the same digit here
-    const int word = pass / 4, shift = (pass % 4) * 8;
-    const int o = buf ^ 1;
-    k_tilehist<<<nblocks, SORT_THREADS, 0, h->stream>>>((const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p,
-                                                        (const uint32_t*)h->cs[buf].p, n, word, shift,
-                                                        (uint32_t*)h->counts.p, nblocks);
-    NLP_LAUNCHED(h);
-    k_rowscan<<<256, 256, 0, h->stream>>>((uint32_t*)h->counts.p, nblocks, (uint32_t*)h->totals.p);
-    NLP_LAUNCHED(h);
-    k_scatter<<<nblocks, SORT_THREADS, 0, h->stream>>>(
-        (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p,
-        (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p, n, word, shift,
-        (const uint32_t*)h->counts.p, nblocks, (const uint32_t*)h->totals.p);
-    NLP_LAUNCHED(h);
-    buf = o;
+    NLP_TRY(radix_pass(h, buf, n, nblocks, pass, true));
+  }
+  *out_buf = buf;
+  return NLP_OK;
+}
+
+// Stable sort of (u, v[, payload]) records by (u, v) only; ids are < span, so the digits above
+// its bit width are skipped without looking at the data.
+int radix_sort_pairs(nlp_handle* h, int buf, uint64_t n, bool has3, int* out_buf) {
+  *out_buf = buf;
+  if (n < 2) return NLP_OK;
+  const uint32_t nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  NLP_TRY(ensure(h, h->counts, (size_t)nblocks * 256 * 4));
+  const uint32_t top = h->S ? h->S - 1 : 0;
+  for (int pass = 0; pass < 8; ++pass) {
+    if ((top >> ((pass % 4) * 8)) == 0) continue;
+    NLP_TRY(radix_pass(h, buf, n, nblocks, pass, has3));
   }
   *out_buf = buf;
   return NLP_OK;
@@ -355,6 +382,111 @@ int launch_tiny(nlp_handle* h, const Params& p, int bin, const uint32_t* list, u
   return NLP_OK;
 }
 
+// Bytes of GPU scratch a prediction may use: what is free now plus what the handle already holds
+// for candidates and spill tables.
+int scratch_budget(nlp_handle* h, uint64_t* out) {
+  size_t free_b = 0, total_b = 0;
+  NLP_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+  uint64_t budget = (uint64_t)free_b + h->tables.cap + h->touched.cap;
+  for (int b = 0; b < 2; ++b) budget += h->cu[b].cap + h->cv[b].cap + h->cs[b].cap;
+  budget = budget / 10 * 8;
+  if (h->scratch_limit && h->scratch_limit < budget) budget = h->scratch_limit;
+  *out = budget;
+  return NLP_OK;
+}
+
+// LHub pair path (pairs.cuh).  *used stays false when the graph's rows are not symmetric or the
+// wedge records do not fit the scratch budget; the caller then runs the source-centric kernels.
+template <bool FLT>
+int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_buf, uint64_t* out_fill, bool* used) {
+  *used = false;
+  const uint32_t S = h->S;
+  const DevGraph g = dev_graph(h);
+  if (h->sym_state == 0) {
+    NLP_TRY(ensure(h, h->sym_flag, 16));
+    NLP_CUDA(h, cudaMemsetAsync(h->sym_flag.p, 0, 16, h->stream));
+    if (h->M) {
+      k_symmetry<<<grid_for(h->M, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, h->M, (unsigned int*)h->sym_flag.p);
+      NLP_LAUNCHED(h);
+    }
+    unsigned int f = 0;
+    NLP_CUDA(h, cudaMemcpyAsync(&f, h->sym_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->sym_state = f ? 2 : 1;
+    // the check is graph preparation, not part of the prediction: restart the clock
+    NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
+  }
+  if (h->sym_state != 1) return NLP_OK;
+  Counters* hc = h->h_ctr;
+  NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
+  NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
+  k_pair_rows<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, opt->min_degree1, h->rank, h->world,
+                                                                        (uint32_t*)h->work.p, (Counters*)h->ctr.p);
+  NLP_LAUNCHED(h);
+  uint64_t E = 0, P = 0;
+  NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->work.p, S, (unsigned long long*)h->work64.p, &E));
+  PairItems it{nullptr, nullptr, nullptr, nullptr};
+  uint64_t budget = 0;
+  NLP_TRY(scratch_budget(h, &budget));
+  if (E) {
+    if (E * 28 > budget / 2) return NLP_OK;
+    NLP_TRY(ensure(h, h->it_u, E * 4));
+    NLP_TRY(ensure(h, h->it_cnt, E * 4));
+    NLP_TRY(ensure(h, h->it_dw, E * 4));
+    NLP_TRY(ensure(h, h->it_ptr, E * 8));
+    NLP_TRY(ensure(h, h->it_off, E * 8));
+    it.u = (uint32_t*)h->it_u.p; it.cnt = (uint32_t*)h->it_cnt.p; it.dw = (uint32_t*)h->it_dw.p;
+    it.ptr = (unsigned long long*)h->it_ptr.p;
+    k_pair_items<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        g, (const uint32_t*)h->work.p, (const unsigned long long*)h->work64.p, h->rank, h->world, it, (Counters*)h->ctr.p);
+    NLP_LAUNCHED(h);
+    NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->it_cnt.p, E, (unsigned long long*)h->it_off.p, &P));
+  }
+  NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
+  NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
+  NLP_TRY(scratch_budget(h, &budget));
+  if (P >= 0xfffffff0ull || (P + 1024) * 24 > budget) return NLP_OK;
+  NLP_TRY(ensure_candidates(h, P));
+  int cur = 0;
+  h->phases_valid = false;
+  if (P) {
+    k_pair_emit<FLT><<<grid_for(E, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+        g.keys, E, it, (const unsigned long long*)h->it_off.p, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+    NLP_LAUNCHED(h);
+    NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
+    int sb = 0;
+    NLP_TRY(radix_sort_pairs(h, 0, P, FLT, &sb));
+    NLP_CUDA(h, cudaEventRecord(h->ev_phase[2], h->stream));
+    cur = sb ^ 1;
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
+    p.gtable = (const double*)h->gtable.p;
+    p.cap = h->cand_cap; p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
+    p.cu = (uint32_t*)h->cu[cur].p; p.cv = (uint32_t*)h->cv[cur].p; p.cs = (float*)h->cs[cur].p;
+    k_pair_reduce<FLT><<<grid_for(P, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+        p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, P);
+    NLP_LAUNCHED(h);
+    for (int i = 3; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
+    h->phases_valid = true;
+  }
+  NLP_TRY(read_counters(h));
+  if (hc->overflow) return fail(h, NLP_ERR_CAPACITY, "internal: candidate buffer overflow (pair path)");
+  res->first_hop = hc->first_hop;
+  res->eligible_first_hop = hc->eligible_first_hop;
+  res->wedges = hc->wedges;
+  res->candidates = hc->candidates;
+  res->kept = hc->kept;
+  res->emitted = hc->cursor;
+  res->passes = 1;
+  res->path = NLP_PATH_PAIR;
+  res->pair_records = P;
+  *out_buf = cur;
+  *out_fill = hc->cursor;
+  *used = true;
+  return NLP_OK;
+}
+
 template <bool FLT>
 int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_buf, uint64_t* out_fill) {
   const uint32_t S = h->S;
@@ -362,6 +494,12 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   const bool lhub = opt->min_degree1 != 0;
   Counters* hc = h->h_ctr;
 
+  if (lhub && h->path_mode != NLP_PATH_SOURCE) {
+    bool used = false;
+    NLP_TRY(pair_pass<FLT>(h, opt, res, out_buf, out_fill, &used));
+    if (used) return NLP_OK;
+  }
+  res->path = NLP_PATH_SOURCE;
   NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
   NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
   const DevGraph g = dev_graph(h);
@@ -415,12 +553,8 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   for (int b = 0; b < 8; ++b) res->bin_sources[b] = b < NBINS ? nb[b] : 0;
 
   // scratch plan: dense spill tables first, candidate buffer with what is left
-  size_t free_b = 0, total_b = 0;
-  NLP_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
-  uint64_t budget = (uint64_t)free_b + h->tables.cap + h->touched.cap;
-  for (int b = 0; b < 2; ++b) budget += h->cu[b].cap + h->cv[b].cap + h->cs[b].cap;
-  budget = budget / 10 * 8;
-  if (h->scratch_limit && h->scratch_limit < budget) budget = h->scratch_limit;
+  uint64_t budget = 0;
+  NLP_TRY(scratch_budget(h, &budget));
   unsigned dense_slots = 0;
   uint64_t touched_cap = 0;
   if (nb[5]) {
@@ -597,6 +731,7 @@ int nlp_destroy(nlp_handle* h) {
   release(h->own_off); release(h->own_keys); release(h->deg); release(h->work); release(h->work64); release(h->elig); release(h->maxdeg_dev);
   release(h->chunk_base); release(h->chunk_src); release(h->chunk_cnt); release(h->ecount); release(h->ekeys);
   release(h->scan_tiles); release(h->scan_total);
+  release(h->it_u); release(h->it_cnt); release(h->it_dw); release(h->it_ptr); release(h->it_off); release(h->sym_flag);
   for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
@@ -646,6 +781,13 @@ int nlp_set_partition(nlp_handle* h, int rank, int world) {
   if (!h) return NLP_ERR_ARG;
   if (world < 1 || rank < 0 || rank >= world) return fail(h, NLP_ERR_ARG, "nlp_set_partition: need 0 <= rank < world");
   h->rank = rank; h->world = world;
+  return NLP_OK;
+}
+
+int nlp_set_path(nlp_handle* h, int path) {
+  if (!h) return NLP_ERR_ARG;
+  if (path != NLP_PATH_AUTO && path != NLP_PATH_SOURCE && path != NLP_PATH_PAIR) return fail(h, NLP_ERR_ARG, "nlp_set_path: unknown path");
+  h->path_mode = path;
   return NLP_OK;
 }
 

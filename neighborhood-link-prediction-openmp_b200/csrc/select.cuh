@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __rest
                                                            const uint32_t* __restrict__ is, uint32_t* __restrict__ ou,
                                                            uint32_t* __restrict__ ov, uint32_t* __restrict__ os, uint64_t n,
                                                            int word, int shift, const uint32_t* __restrict__ counts,
-                                                           uint32_t nblocks, const uint32_t* __restrict__ totals) {
+                                                           uint32_t nblocks, const uint32_t* __restrict__ totals, bool has3) {
   __shared__ uint32_t s_hist[SORT_WARPS][256];
   __shared__ uint32_t s_tot[256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __rest
   for (int r = 0; r < SORT_ROUNDS; ++r) {
     const uint64_t i = wbase + (uint64_t)r * 32 + lane;
     const bool valid = i < n;
-    ru[r] = valid ? iu[i] : 0u; rv[r] = valid ? iv[i] : 0u; rs[r] = valid ? is[i] : 0u;
+    ru[r] = valid ? iu[i] : 0u; rv[r] = valid ? iv[i] : 0u; rs[r] = (valid && has3) ? is[i] : 0u;
     const uint32_t d = (sort_word(word, ru[r], rv[r], rs[r]) >> shift) & 255u;
     const unsigned m = __match_any_sync(NLP_FULL, valid ? d : (256u + lane));
     const uint32_t before = valid ? s_hist[warp][d] : 0u;
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __rest
     if (i < n) {
       const uint32_t d = (sort_word(word, ru[r], rv[r], rs[r]) >> shift) & 255u;
       const uint32_t pos = s_hist[warp][d] + pre[r];
-      ou[pos] = ru[r]; ov[pos] = rv[r]; os[pos] = rs[r];
+      ou[pos] = ru[r]; ov[pos] = rv[r];
+      if (has3) os[pos] = rs[r];
     }
   }
 }

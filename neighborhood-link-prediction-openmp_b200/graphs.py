@@ -195,6 +195,26 @@ def duplicate_some_entries(offsets, keys, every=7):
     return off2, keys2
 
 
+def duplicate_symmetric(offsets, keys, every=5, copies=2):
+    """Symmetric multiset rows: every ``every``-th undirected edge (by a hash of its endpoints) is
+    stored ``copies`` times in BOTH rows, so entry multiplicities stay symmetric (the shape the
+    LHub pair path accepts) while rows hold duplicates.  Rows stay sorted."""
+    S = offsets.numel() - 1
+    deg = offsets[1:] - offsets[:-1]
+    src = torch.repeat_interleave(torch.arange(S, device=keys.device, dtype=torch.int64), deg)
+    dst = keys.to(torch.int64)
+    lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+    pick = _lsr(hash_u64(lo * (S + 1) + hi, 77), 20) % every == 0
+    rep = torch.ones_like(src)
+    rep[pick] = copies
+    keys2 = torch.repeat_interleave(keys, rep)
+    src2 = torch.repeat_interleave(src, rep)
+    deg2 = torch.bincount(src2, minlength=S)
+    off2 = torch.zeros(S + 1, dtype=torch.int64, device=keys.device)
+    torch.cumsum(deg2, 0, out=off2[1:])
+    return off2, keys2
+
+
 def to_numpy(offsets, keys):
     import numpy as np
     return (offsets.cpu().numpy().astype(np.uint64), keys.cpu().numpy().astype(np.uint32))

@@ -25,6 +25,7 @@ def graphs(quick):
     out.append(("road40", g.to_numpy(*g.road_lattice(40, 0.6, 2))))
     out.append(("pp2k", g.to_numpy(*g.planted_partition(2000, 40, 8, 2, 3))))
     out.append(("pp2k-dup", g.to_numpy(*g.duplicate_some_entries(*g.planted_partition(2000, 40, 8, 2, 3), every=5))))
+    out.append(("pp2k-symdup", g.to_numpy(*g.duplicate_symmetric(*g.planted_partition(2000, 40, 8, 2, 3), every=5, copies=3))))
     out.append(("rmat13", g.to_numpy(*g.rmat(13, 16, 4))))
     if not quick:
         out.append(("web50k", g.to_numpy(*g.web_crawl(50000, 12, seed=5))))
@@ -46,14 +47,16 @@ def main():
                 for K in (N.UNBOUNDED, max(1, M // 20), 3):
                     if name == "rmat16" and D in (0, 1024) and (measure not in ("CN", "JC", "AA") or K == N.UNBOUNDED):
                         continue   # the oracle needs minutes for 1.8e8 unbounded candidates
-                    total += 1
-                    try:
-                        err, r, st = parity.check_case(pred, O, off, keys, measure, D, K, tag=name)
-                    except Exception as e:   # noqa: BLE001
-                        err = "%s %s D=%d: EXCEPTION %r" % (name, measure, D, e)
-                    if err:
-                        fails += 1
-                        print("FAIL", err, flush=True)
+                    for path in ((1, 2) if D else (1,)):   # source-centric kernels; LHub pair path
+                        total += 1
+                        pred.set_path(path)
+                        try:
+                            err, r, st = parity.check_case(pred, O, off, keys, measure, D, K, tag="%s path%d" % (name, path))
+                        except Exception as e:   # noqa: BLE001
+                            err = "%s %s D=%d path%d: EXCEPTION %r" % (name, measure, D, path, e)
+                        if err:
+                            fails += 1
+                            print("FAIL", err, flush=True)
         print("graph %s done (%d entries) t=%.1fs fails=%d" % (name, M, time.time() - t0, fails), flush=True)
     print("SWEEP total=%d fails=%d" % (total, fails))
     return 1 if fails else 0

@@ -24,6 +24,7 @@ def _graph(nlp, name):
         "road60": lambda: g.road_lattice(60, 0.6, 33),
         "pp4k": lambda: g.planted_partition(4000, 50, 10, 2, 34),
         "pp4k_multiset": lambda: g.duplicate_some_entries(*g.planted_partition(4000, 50, 10, 2, 35), every=4),
+        "pp4k_symdup": lambda: g.duplicate_symmetric(*g.planted_partition(4000, 50, 10, 2, 35), every=4, copies=3),
         "web20k": lambda: g.web_crawl(20000, 10, window=500, seed=36),
     }
     return g.to_numpy(*table[name]())
@@ -41,16 +42,28 @@ def test_gpu_matches_reference_golden(pred, name):
             assert err is None, "%s %s" % (name, err)
 
 
-@pytest.mark.parametrize("name", ["rmat12", "rmat14p", "road60", "pp4k", "pp4k_multiset", "web20k"])
+SOURCE_PATH, PAIR_PATH = 1, 2
+
+
+@pytest.mark.parametrize("name", ["rmat12", "rmat14p", "road60", "pp4k", "pp4k_multiset", "pp4k_symdup", "web20k"])
 @pytest.mark.parametrize("D", [0, 2, 4, 32, 1024])
 def test_gpu_matches_oracle(pred, oracle, nlp, name, D):
+    """Both scoring paths (source-centric kernels; LHub pair path) against the oracle."""
     off, keys = _graph(nlp, name)
     pred.set_graph(off, keys)
     K = max(3, len(keys) // 20)
-    for m in nlp.MEASURES:
-        for k in (K, nlp.UNBOUNDED) if (D != 0 or name != "rmat14p") else (K,):
-            err, r, st = parity.check_case(pred, oracle, off, keys, m, D, k, tag=name)
-            assert err is None, err
+    try:
+        for path in (SOURCE_PATH, PAIR_PATH) if D else (SOURCE_PATH,):
+            pred.set_path(path)
+            for m in nlp.MEASURES:
+                for k in (K, nlp.UNBOUNDED) if (D != 0 or name != "rmat14p") else (K,):
+                    err, r, st = parity.check_case(pred, oracle, off, keys, m, D, k, tag="%s path%d" % (name, path))
+                    assert err is None, err
+                    # asymmetric multiset rows are not admissible for the pair path: it must fall back
+                    want = SOURCE_PATH if (path == SOURCE_PATH or name == "pp4k_multiset") else PAIR_PATH
+                    assert r["path"] == want, (name, D, m, r["path"])
+    finally:
+        pred.set_path(0)
 
 
 def test_tie_rule_and_known_answer(pred):
