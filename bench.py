@@ -271,27 +271,45 @@ def run_b200(args):
         return 0
 
     # ---- roofline of the dominant phase --------------------------------------------------------
-    names = ["frontier(k_elig+k_work+k_bin)", "k_dense", "k_hash(16K)", "k_hash(4K)", "k_hash(1K)", "k_tiny<32>", "k_tiny<8>", "select+sort"]
+    path = results[0]["path"]
+    if path == 2:
+        names = ["pair: eligible rows + item descriptors + scans", "pair: k_pair_emit (wedge records)",
+                 "pair: radix sort by (u,v) (k_tilehist+k_rowscan+k_scatter per digit)", "pair: k_pair_reduce (run count + exclusion + score)",
+                 "-", "-", "-", "select+sort (radix top-K)"]
+    else:
+        names = ["frontier(k_elig+k_work+k_bin)", "k_dense", "k_hash(16K)", "k_hash(4K)", "k_hash(1K)", "k_tiny<32>", "k_tiny<8>", "select+sort (radix top-K)"]
     phase = [sum(r["phase_ms"][i] for r in results) for i in range(8)]
     nrun = len(results)
     peak, peak_src = peaks()
     W = sum(r["wedges"] for r in results); C = sum(r["candidates"] for r in results)
     E = sum(r["emitted"] for r in results); Kout = sum(r["count"] for r in results)
-    wedge_ms = sum(phase[1:7])
-    # algorithmic bytes, split by the phase that moves them
-    bytes_frontier = nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world)
-    bytes_wedge = 4 * W + 4 * C + 12 * E
-    bytes_select = 12 * Kout
-    cands = [("frontier: k_work (first-hop scan, hub test, work sums)", phase[0], bytes_frontier),
-             ("wedge kernels (k_dense/k_hash/k_tiny: 2-hop scan + count + score)", wedge_ms, bytes_wedge),
-             ("select+sort (radix top-K)", phase[7], bytes_select)]
+    if path == 2:
+        # per-phase algorithmic bytes of the pair path
+        idbits = max(1, (S - 1).bit_length())
+        digits = 2 * ((idbits + 7) // 8)
+        P = sum(r["pair_records"] for r in results)
+        Pflt = sum(r["pair_records"] for r, m in zip(results, measures * args.steps) if m in ("AA", "RA"))
+        rec_bytes = 8 * P + 4 * Pflt
+        elig = sum(r["eligible_first_hop"] for r in results)
+        cands = [(names[0], phase[0], nrun * 12 * S / max(1, world) + 4 * elig),
+                 (names[1], phase[1], 4 * P + rec_bytes),
+                 (names[2], phase[2], digits * 2 * rec_bytes),
+                 (names[3], phase[3], rec_bytes + 12 * E),
+                 (names[7], phase[7], 12 * E + 12 * Kout)]
+    else:
+        wedge_ms = sum(phase[1:7])
+        # algorithmic bytes, split by the phase that moves them
+        cands = [("frontier: k_work (first-hop scan, hub test, work sums)", phase[0], nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world)),
+                 ("wedge kernels (k_dense/k_hash/k_tiny: 2-hop scan + count + score)", wedge_ms, 4 * W + 4 * C + 12 * E),
+                 (names[7], phase[7], 12 * E + 12 * Kout)]
     dom = max(cands, key=lambda c: c[1])
     achieved = dom[2] / (dom[1] / 1e3) / 1e9 if dom[1] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "share_of_step": dom[1] / max(1e-9, sum(phase)),
                 "algorithmic_bytes_per_step": dom[2] / args.steps}
-    total_alg = bytes_frontier + bytes_wedge + bytes_select
+    # whole step against the reference algorithm's bytes (SURVEY.md section 8d formula)
+    total_alg = nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world) + 4 * W + 4 * C + 12 * Kout
     step_frac = total_alg / (ms / 1e3) / 1e9 / peak
 
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample -------
@@ -339,6 +357,7 @@ def run_b200(args):
         "phase_ms_per_step": {n: p / args.steps for n, p in zip(names, phase)},
         "wall_ms_per_step": wall * 1e3 / args.steps,
         "bins": results[0]["bin_sources"][:6],
+        "path": {1: "source-centric", 2: "pair"}.get(path, path),
     }
     print(json.dumps(line))
     if world > 1:

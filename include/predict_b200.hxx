@@ -1,0 +1,232 @@
+// predict_b200.hxx -- host-side C++ mirror of the reference's link-prediction API
+// (puzzlef/neighborhood-link-prediction-openmp, inc/predict.hxx) on top of the C ABI in
+// nlp_b200.h.  Same names, same template parameter order, same option / result structs:
+//
+//   PredictLinkOptions<W>            inc/predict.hxx:33-55
+//   PredictLinkResult<K, W>          inc/predict.hxx:65-102
+//   predictLinks<Measure>[Omp]<MINDEGREE1=4, MAXFACTOR2=0, FORCEHEAP=false, G, W=float>(x, o={})
+//                                    inc/predict.hxx:502-831 (18 entry points)
+//
+// `G` only needs what the reference templates use: key_type, span(), hasVertex(u), degree(u),
+// forEachEdgeKey(u, f) -- so the reference's DiGraph and DiGraphCsr (inc/Graph.hxx:23-372,
+// 383-639) work unchanged, and so does nlp_b200::DeviceGraph below (a graph that is already
+// resident on the GPU; use it to run many predictions on one upload, as main.cxx:212-220 does).
+//
+// Everything lives in namespace nlp_b200 so the header can sit next to the reference's own
+// predict.hxx in one translation unit (tests do that).  For a drop-in build define
+// NLP_B200_DROP_IN before including: the 20 names are then also visible unqualified.
+//
+// Differences from the reference, all deliberate:
+//   * ties are ordered (score desc, u asc, v asc) instead of by heap accident;
+//   * when fewer than maxEdges candidates exist the shorter list is returned (the sequential
+//     reference's behaviour, inc/predict.hxx:250-255; the OpenMP merge is undefined there);
+//   * errors of the GPU path (no device, out of memory) throw std::runtime_error -- there is no
+//     CPU fallback;
+//   * W must be float (main.cxx:20); FORCEHEAP is accepted and ignored.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "nlp_b200.h"
+
+namespace nlp_b200 {
+
+template <class W>
+struct PredictLinkOptions {
+  int    repeat;     // number of times to repeat the scoring phase [1]
+  size_t maxEdges;   // maximum number of edges to predict [-1]
+  W      minScore;   // minimum score above which to consider a link [0]
+  PredictLinkOptions(int repeat = 1, size_t maxEdges = size_t(-1), W minScore = W()) :
+  repeat(repeat), maxEdges(maxEdges), minScore(minScore) {}
+};
+
+template <class K, class W>
+struct PredictLinkResult {
+  std::vector<std::tuple<K, K, W>> edges;   // predicted links (u < v), score descending
+  float time;                               // total time, milliseconds
+  float scoringTime;                        // scoring phase, milliseconds
+  nlp_result stats;                         // counters of the GPU path (not in the reference)
+  PredictLinkResult() : edges(), time(), scoringTime(), stats() {}
+  PredictLinkResult(std::vector<std::tuple<K, K, W>>&& edges, float time = 0, float scoringTime = 0) :
+  edges(std::move(edges)), time(time), scoringTime(scoringTime), stats() {}
+};
+
+namespace detail {
+
+inline void check(nlp_handle* h, int rc, const char* what) {
+  if (rc == NLP_OK) return;
+  throw std::runtime_error(std::string("nlp_b200: ") + what + ": " + nlp_last_error(h));
+}
+
+// One predictor handle per process (the reference call is blocking and serial as well).
+struct Session {
+  nlp_handle* h = nullptr;
+  std::mutex  mu;
+  const void* resident = nullptr;   // DeviceGraph currently bound to the handle
+  std::vector<uint64_t> offsets;    // staging for pack()
+  std::vector<uint32_t> keys;
+  uint64_t fingerprint = 0;
+  bool     have_fingerprint = false;
+  static Session& get() { static Session s; return s; }
+  nlp_handle* handle() {
+    if (!h) {
+      const char* d = std::getenv("NLP_B200_DEVICE");
+      const int rc = nlp_create(&h, d ? std::atoi(d) : 0);
+      if (rc != NLP_OK) throw std::runtime_error(std::string("nlp_b200: nlp_create: ") + nlp_last_error(nullptr));
+    }
+    return h;
+  }
+  ~Session() { if (h) nlp_destroy(h); }
+};
+
+inline uint64_t mix(uint64_t a, uint64_t x) {
+  a ^= x + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2);
+  return a * 0xBF58476D1CE4E5B9ull;
+}
+
+// G -> CSR (64-bit offsets, 32-bit keys), with a content fingerprint.
+template <class G>
+inline uint64_t pack(const G& x, std::vector<uint64_t>& off, std::vector<uint32_t>& keys) {
+  const size_t S = x.span();
+  off.assign(S + 1, 0);
+  for (size_t u = 0; u < S; ++u)
+    off[u + 1] = off[u] + (x.hasVertex(u) ? (uint64_t)x.degree(u) : 0);
+  keys.resize(off[S]);
+  std::vector<uint64_t> rowhash(S, 0);
+  #pragma omp parallel for schedule(dynamic, 2048)
+  for (size_t u = 0; u < S; ++u) {
+    if (!x.hasVertex(u)) continue;
+    uint64_t i = off[u], hsh = off[u + 1];
+    x.forEachEdgeKey(u, [&](auto v) { keys[i++] = (uint32_t)v; hsh = mix(hsh, (uint64_t)v); });
+    rowhash[u] = hsh;
+  }
+  uint64_t f = mix(S, off[S]);
+  for (size_t u = 0; u < S; ++u) f = mix(f, rowhash[u]);
+  return f;
+}
+
+}  // namespace detail
+
+
+// A graph that already lives on the GPU: upload once, predict many times.
+// Satisfies nothing of the host read API on purpose -- it is only accepted by the entry points.
+class DeviceGraph {
+ public:
+  using key_type = uint32_t;
+  template <class G>
+  explicit DeviceGraph(const G& x) {
+    detail::Session& s = detail::Session::get();
+    std::lock_guard<std::mutex> lock(s.mu);
+    detail::pack(x, s.offsets, s.keys);
+    upload(s, s.offsets.data(), s.keys.data(), (uint32_t)(s.offsets.size() - 1));
+  }
+  // Host CSR arrays directly (offsets[span+1], keys[offsets[span]], rows sorted ascending).
+  DeviceGraph(const uint64_t* offsets, const uint32_t* keys, uint32_t span) {
+    detail::Session& s = detail::Session::get();
+    std::lock_guard<std::mutex> lock(s.mu);
+    upload(s, offsets, keys, span);
+  }
+  ~DeviceGraph() {
+    detail::Session& s = detail::Session::get();
+    if (s.resident == this) s.resident = nullptr;
+  }
+  DeviceGraph(const DeviceGraph&) = delete;
+  DeviceGraph& operator=(const DeviceGraph&) = delete;
+  size_t span() const { return span_; }
+ private:
+  void upload(detail::Session& s, const uint64_t* off, const uint32_t* keys, uint32_t span) {
+    nlp_handle* h = s.handle();
+    detail::check(h, nlp_set_graph(h, off, keys, span), "nlp_set_graph");
+    s.resident = this; s.have_fingerprint = false; span_ = span;
+  }
+  size_t span_ = 0;
+  template <class K, class W, class G> friend PredictLinkResult<K, W> predictLinksB200(const G&, int, unsigned, unsigned, const PredictLinkOptions<W>&);
+};
+
+
+// The one function all 18 entry points forward to.
+template <class K, class W, class G>
+inline PredictLinkResult<K, W> predictLinksB200(const G& x, int measure, unsigned minDegree1, unsigned maxFactor2,
+                                                const PredictLinkOptions<W>& o) {
+  static_assert(std::is_same<W, float>::value, "nlp_b200: the GPU path scores in float (main.cxx:20: TYPE = float)");
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  nlp_handle* h = s.handle();
+  if constexpr (std::is_same<G, DeviceGraph>::value) {
+    if (s.resident != &x) throw std::runtime_error("nlp_b200: this DeviceGraph is no longer resident (another graph was uploaded since)");
+  } else {
+    // content-addressed: the same graph handed over again (main.cxx runs 99 predictions per
+    // batch on one graph) is packed and compared, but not uploaded again
+    const uint64_t f = detail::pack(x, s.offsets, s.keys);
+    if (!(s.have_fingerprint && s.fingerprint == f && s.resident == nullptr)) {
+      detail::check(h, nlp_set_graph(h, s.offsets.data(), s.keys.data(), (uint32_t)(s.offsets.size() - 1)), "nlp_set_graph");
+      s.fingerprint = f; s.have_fingerprint = true; s.resident = nullptr;
+    }
+  }
+  nlp_options opt;
+  opt.measure = measure; opt.min_degree1 = minDegree1; opt.max_factor2 = maxFactor2;
+  opt.repeat = o.repeat; opt.max_edges = o.maxEdges == size_t(-1) ? NLP_UNBOUNDED : (uint64_t)o.maxEdges;
+  opt.min_score = o.minScore;
+  PredictLinkResult<K, W> a;
+  detail::check(h, nlp_predict(h, &opt, &a.stats), "nlp_predict");
+  const size_t n = (size_t)a.stats.count;
+  std::vector<uint32_t> u(n), v(n);
+  std::vector<float> sc(n);
+  detail::check(h, nlp_fetch(h, u.data(), v.data(), sc.data(), n), "nlp_fetch");
+  a.edges.resize(n);   // SoA -> tuples (never memcpy a std::tuple: member order is unspecified)
+  for (size_t i = 0; i < n; ++i) a.edges[i] = std::make_tuple((K)u[i], (K)v[i], (W)sc[i]);
+  a.time = a.stats.time_ms;
+  a.scoringTime = a.stats.scoring_ms;
+  return a;
+}
+
+
+// The 18 entry points (inc/predict.hxx:502-831).  The sequential and the OpenMP names run the
+// same GPU path; measure order as main.cxx:212-220.
+#define NLP_B200_ENTRY(NAME, MEASURE)                                                              \
+  template <int MINDEGREE1 = 4, int MAXFACTOR2 = 0, bool FORCEHEAP = false, class G, class W = float> \
+  inline auto NAME(const G& x, const PredictLinkOptions<W>& o = {}) {                              \
+    using K = typename G::key_type;                                                                \
+    return predictLinksB200<K, W>(x, MEASURE, (unsigned)MINDEGREE1, (unsigned)MAXFACTOR2, o);      \
+  }                                                                                                \
+  template <int MINDEGREE1 = 4, int MAXFACTOR2 = 0, bool FORCEHEAP = false, class G, class W = float> \
+  inline auto NAME##Omp(const G& x, const PredictLinkOptions<W>& o = {}) {                         \
+    using K = typename G::key_type;                                                                \
+    return predictLinksB200<K, W>(x, MEASURE, (unsigned)MINDEGREE1, (unsigned)MAXFACTOR2, o);      \
+  }
+
+NLP_B200_ENTRY(predictLinksCommonNeighbors,        NLP_COMMON_NEIGHBORS)      // inc/predict.hxx:503, 520
+NLP_B200_ENTRY(predictLinksJaccardCoefficient,     NLP_JACCARD_COEFFICIENT)   // inc/predict.hxx:541, 558
+NLP_B200_ENTRY(predictLinksSorensenIndex,          NLP_SORENSEN_INDEX)        // inc/predict.hxx:579, 596
+NLP_B200_ENTRY(predictLinksSaltonCosineSimilarity, NLP_SALTON_COSINE)         // inc/predict.hxx:617, 634
+NLP_B200_ENTRY(predictLinksHubPromoted,            NLP_HUB_PROMOTED)          // inc/predict.hxx:655, 672
+NLP_B200_ENTRY(predictLinksHubDepressed,           NLP_HUB_DEPRESSED)         // inc/predict.hxx:693, 710
+NLP_B200_ENTRY(predictLinksLeichtHolmeNermanScore, NLP_LEICHT_HOLME_NERMAN)   // inc/predict.hxx:731, 748
+NLP_B200_ENTRY(predictLinksAdamicAdarCoefficient,  NLP_ADAMIC_ADAR)           // inc/predict.hxx:769, 787
+NLP_B200_ENTRY(predictLinksResourceAllocationScore, NLP_RESOURCE_ALLOCATION)  // inc/predict.hxx:809, 827
+#undef NLP_B200_ENTRY
+
+}  // namespace nlp_b200
+
+
+#ifdef NLP_B200_DROP_IN
+using nlp_b200::PredictLinkOptions;
+using nlp_b200::PredictLinkResult;
+using nlp_b200::predictLinksCommonNeighbors;         using nlp_b200::predictLinksCommonNeighborsOmp;
+using nlp_b200::predictLinksJaccardCoefficient;      using nlp_b200::predictLinksJaccardCoefficientOmp;
+using nlp_b200::predictLinksSorensenIndex;           using nlp_b200::predictLinksSorensenIndexOmp;
+using nlp_b200::predictLinksSaltonCosineSimilarity;  using nlp_b200::predictLinksSaltonCosineSimilarityOmp;
+using nlp_b200::predictLinksHubPromoted;             using nlp_b200::predictLinksHubPromotedOmp;
+using nlp_b200::predictLinksHubDepressed;            using nlp_b200::predictLinksHubDepressedOmp;
+using nlp_b200::predictLinksLeichtHolmeNermanScore;  using nlp_b200::predictLinksLeichtHolmeNermanScoreOmp;
+using nlp_b200::predictLinksAdamicAdarCoefficient;   using nlp_b200::predictLinksAdamicAdarCoefficientOmp;
+using nlp_b200::predictLinksResourceAllocationScore; using nlp_b200::predictLinksResourceAllocationScoreOmp;
+#endif

@@ -76,6 +76,7 @@ struct nlp_handle {
   // config
   int rank = 0, world = 1;
   uint64_t scratch_limit = 0;
+  uint64_t budget_base = 0;                  // see scratch_budget()
   uint64_t launches = 0;
   std::string err;
 };
@@ -165,6 +166,8 @@ int exclusive_scan(nlp_handle* h, const TIn* in, uint64_t n, unsigned long long*
   return NLP_OK;
 }
 
+int measure_budget(nlp_handle* h);
+
 int finish_graph(nlp_handle* h) {
   const uint32_t S = h->S;
   NLP_TRY(ensure(h, h->deg, (size_t)S * 4));
@@ -204,6 +207,7 @@ int finish_graph(nlp_handle* h) {
   h->maxdeg = md;
   h->gtable_n = 0;
   h->sym_state = 0;
+  NLP_TRY(measure_budget(h));
   h->has_graph = true;
   h->has_result = false;
   return NLP_OK;
@@ -382,16 +386,23 @@ int launch_tiny(nlp_handle* h, const Params& p, int bin, const uint32_t* list, u
   return NLP_OK;
 }
 
-// Bytes of GPU scratch a prediction may use: what is free now plus what the handle already holds
-// for candidates and spill tables.
+// Bytes of GPU scratch a prediction may use: what was free when the graph was set plus what the
+// handle already held for scratch then.  Measured once per graph -- cudaMemGetInfo costs
+// milliseconds when the process holds many allocations, far too much for every prediction.
 int scratch_budget(nlp_handle* h, uint64_t* out) {
+  uint64_t budget = h->budget_base;
+  if (h->scratch_limit && h->scratch_limit < budget) budget = h->scratch_limit;
+  *out = budget;
+  return NLP_OK;
+}
+
+int measure_budget(nlp_handle* h) {
   size_t free_b = 0, total_b = 0;
   NLP_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
   uint64_t budget = (uint64_t)free_b + h->tables.cap + h->touched.cap;
   for (int b = 0; b < 2; ++b) budget += h->cu[b].cap + h->cv[b].cap + h->cs[b].cap;
-  budget = budget / 10 * 8;
-  if (h->scratch_limit && h->scratch_limit < budget) budget = h->scratch_limit;
-  *out = budget;
+  budget += h->it_u.cap + h->it_cnt.cap + h->it_dw.cap + h->it_ptr.cap + h->it_off.cap + h->ecount.cap + h->ekeys.cap;
+  h->budget_base = budget / 10 * 8;
   return NLP_OK;
 }
 

@@ -220,6 +220,24 @@ def to_numpy(offsets, keys):
     return (offsets.cpu().numpy().astype(np.uint64), keys.cpu().numpy().astype(np.uint32))
 
 
+def write_mtx(path, offsets, keys):
+    """MatrixMarket ``pattern symmetric`` file, one line per undirected edge (u > v, 1-based ids as
+    stored), the on-disk format the reference's loader reads (mtx.hxx:39-54, 151-188; run the
+    reference with argv[2] = 1 so it does not symmetrize again)."""
+    import numpy as np
+    off, k = to_numpy(offsets, keys)
+    S = off.shape[0] - 1
+    src = np.repeat(np.arange(S, dtype=np.int64), np.diff(off).astype(np.int64))
+    dst = k.astype(np.int64)
+    keep = src > dst
+    rows, cols = src[keep], dst[keep]
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate pattern symmetric\n")
+        f.write("%d %d %d\n" % (S - 1, S - 1, rows.shape[0]))
+        np.savetxt(f, np.stack([rows, cols], 1), fmt="%d %d")
+    return int(rows.shape[0])
+
+
 def describe(offsets, keys):
     deg = offsets[1:] - offsets[:-1]
     return {"span": int(offsets.numel() - 1), "entries": int(keys.numel()), "max_degree": int(deg.max()),
