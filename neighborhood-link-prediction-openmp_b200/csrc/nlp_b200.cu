@@ -87,7 +87,7 @@ namespace {
   do {                                                                                         \
     cudaError_t e__ = (expr);                                                                  \
     if (e__ != cudaSuccess) {                                                                  \
-      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                          \
+      (h)->err = std::string(#expr) + " (nlp_b200.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e__); \
       return NLP_ERR_CUDA;                                                                     \
     }                                                                                          \
   } while (0)
@@ -118,10 +118,15 @@ void release(DevBuf& b) {
     if (rc__ != NLP_OK) return rc__; \
   } while (0)
 
+// NLP_B200_DEBUG_SYNC=1 in the environment synchronises after every launch, so a faulting
+// kernel is reported at its own launch site.
+static const bool g_debug_sync = [] { const char* e = getenv("NLP_B200_DEBUG_SYNC"); return e && *e == '1'; }();
+
 #define NLP_LAUNCHED(h)                                   \
   do {                                                    \
     (h)->launches++;                                      \
     NLP_CUDA(h, cudaGetLastError());                      \
+    if (g_debug_sync) NLP_CUDA(h, cudaStreamSynchronize((h)->stream)); \
   } while (0)
 
 inline unsigned grid_for(uint64_t items, unsigned per_block, unsigned cap_blocks) {
@@ -239,10 +244,17 @@ int radix_pass(nlp_handle* h, int& buf, uint64_t n, uint32_t nblocks, int pass, 
   NLP_LAUNCHED(h);
   k_rowscan<<<256, 256, 0, h->stream>>>((uint32_t*)h->counts.p, nblocks, (uint32_t*)h->totals.p);
   NLP_LAUNCHED(h);
-  k_scatter<<<nblocks, SORT_THREADS, 0, h->stream>>>(
-      (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p,
-      (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p, n, word, shift,
-      (const uint32_t*)h->counts.p, nblocks, (const uint32_t*)h->totals.p, has3);
+  if (has3) {
+    k_scatter<true><<<nblocks, SORT_THREADS, scatter_smem_bytes(true), h->stream>>>(
+        (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p,
+        (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p, n, word, shift,
+        (const uint32_t*)h->counts.p, nblocks, (const uint32_t*)h->totals.p);
+  } else {
+    k_scatter<false><<<nblocks, SORT_THREADS, scatter_smem_bytes(false), h->stream>>>(
+        (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p,
+        (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p, n, word, shift,
+        (const uint32_t*)h->counts.p, nblocks, (const uint32_t*)h->totals.p);
+  }
   NLP_LAUNCHED(h);
   buf = o;
   return NLP_OK;
@@ -326,10 +338,12 @@ int top_k(nlp_handle* h, int buf, uint64_t n, uint64_t K, int* out_buf, uint64_t
 int ensure_candidates(nlp_handle* h, uint64_t cap) {
   if (cap < 1024) cap = 1024;
   if (cap <= h->cand_cap) return NLP_OK;
+  // padded to whole sort tiles: k_scatter reads full tiles with TMA bulk copies
+  const uint64_t padded = (cap + SORT_TILE - 1) / SORT_TILE * SORT_TILE + SORT_TILE;
   for (int b = 0; b < 2; ++b) {
-    NLP_TRY(ensure(h, h->cu[b], cap * 4));
-    NLP_TRY(ensure(h, h->cv[b], cap * 4));
-    NLP_TRY(ensure(h, h->cs[b], cap * 4));
+    NLP_TRY(ensure(h, h->cu[b], padded * 4));
+    NLP_TRY(ensure(h, h->cv[b], padded * 4));
+    NLP_TRY(ensure(h, h->cs[b], padded * 4));
   }
   h->cand_cap = cap;
   h->has_result = false;
@@ -731,6 +745,9 @@ int nlp_create(nlp_handle** out, int device) {
     delete h;
     return rc;
   }
+  if ((e = cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes(true))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes(false))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(k_scatter)", e);
   *out = h;
   return NLP_OK;
 }

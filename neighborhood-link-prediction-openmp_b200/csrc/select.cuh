@@ -83,52 +83,135 @@ __global__ void __launch_bounds__(256) k_rowscan(uint32_t* __restrict__ counts, 
   if (threadIdx.x == 255) totals[blockIdx.x] = part[255];
 }
 
-// Stable scatter of one tile: ranks inside a warp come from match.any, warps are ordered by
-// a shared-memory scan, tiles by the scanned count matrix.
-__global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __restrict__ iu, const uint32_t* __restrict__ iv,
-                                                           const uint32_t* __restrict__ is, uint32_t* __restrict__ ou,
-                                                           uint32_t* __restrict__ ov, uint32_t* __restrict__ os, uint64_t n,
-                                                           int word, int shift, const uint32_t* __restrict__ counts,
-                                                           uint32_t nblocks, const uint32_t* __restrict__ totals, bool has3) {
-  __shared__ uint32_t s_hist[SORT_WARPS][256];
-  __shared__ uint32_t s_tot[256];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
-  s_tot[tid] = totals[tid];
+// Exclusive scan of one u32 per thread over the SORT_THREADS threads of the block.
+__device__ __forceinline__ uint32_t sort_block_exclusive(uint32_t x, uint32_t* s_warp /*[SORT_WARPS]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = x;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  uint32_t ru[SORT_ROUNDS], rv[SORT_ROUNDS], rs[SORT_ROUNDS], pre[SORT_ROUNDS];
-  const uint64_t wbase = (uint64_t)blockIdx.x * SORT_TILE + (uint64_t)warp * (32 * SORT_ROUNDS);
+  uint32_t before = 0;
+  #pragma unroll
+  for (int w = 0; w < SORT_WARPS; ++w) before += w < warp ? s_warp[w] : 0u;
+  __syncthreads();
+  return before + inc - x;
+}
+
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) --------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // make the init visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Shared-memory plan of k_scatter (all dynamic): the raw tile (2 or 3 arrays of SORT_TILE words,
+// filled by TMA bulk copies), the tile permutation, warp-private digit counters, per-digit bases.
+__host__ __device__ constexpr uint32_t scatter_smem_bytes(bool has3) {
+  return SORT_TILE * 4u * (has3 ? 3u : 2u) + SORT_TILE * 2u + SORT_WARPS * 256u * 4u + 256u * 4u + SORT_WARPS * 4u + 16u;
+}
+
+// Stable scatter of one tile.  The tile's arrays arrive in shared memory by TMA bulk copies (no
+// registers, whole tile in flight at once; the buffers are padded to a multiple of SORT_TILE so a
+// full tile can always be read).  Ranks inside a warp come from match.any, warps are ordered by a
+// shared-memory scan, tiles by the scanned count matrix.  A tile-local permutation sorts the tile
+// by digit, so records leave in tile order and every digit's records form one contiguous run: a
+// warp store touches the 2-3 runs it straddles instead of 32 different lines.
+template <bool HAS3>
+__global__ void __launch_bounds__(SORT_THREADS, HAS3 ? 3 : 4)
+k_scatter(const uint32_t* __restrict__ iu, const uint32_t* __restrict__ iv, const uint32_t* __restrict__ is,
+          uint32_t* __restrict__ ou, uint32_t* __restrict__ ov, uint32_t* __restrict__ os, uint64_t n,
+          int word, int shift, const uint32_t* __restrict__ counts, uint32_t nblocks, const uint32_t* __restrict__ totals) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  constexpr int NW = HAS3 ? 3 : 2;
+  uint32_t* raw = smem;                                            // [NW][SORT_TILE]
+  uint16_t* s_perm = reinterpret_cast<uint16_t*>(raw + NW * SORT_TILE);   // [SORT_TILE]
+  uint32_t (*s_hist)[256] = reinterpret_cast<uint32_t (*)[256]>(raw + NW * SORT_TILE + SORT_TILE / 2);
+  uint32_t* s_gbase = &s_hist[0][0] + SORT_WARPS * 256;
+  uint32_t* s_warp = s_gbase + 256;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_warp + SORT_WARPS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t tbase = (uint64_t)blockIdx.x * SORT_TILE;
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    mbar_expect_tx(s_bar, NW * SORT_TILE * 4);
+    bulk_g2s(raw, iu + tbase, SORT_TILE * 4, s_bar);
+    bulk_g2s(raw + SORT_TILE, iv + tbase, SORT_TILE * 4, s_bar);
+    if (HAS3) bulk_g2s(raw + 2 * SORT_TILE, is + tbase, SORT_TILE * 4, s_bar);
+  }
+  for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  mbar_wait(s_bar, 0);
+  const uint32_t tile_n = (uint32_t)(n - tbase < (uint64_t)SORT_TILE ? n - tbase : (uint64_t)SORT_TILE);
+  // the word this pass sorts on (sort_word: 0 = v, 1 = u, 2 = score)
+  const uint32_t* kw = word == 0 ? raw + SORT_TILE : word == 1 ? raw : raw + 2 * SORT_TILE;
+  uint32_t pre[SORT_ROUNDS];
   const unsigned lt = (1u << lane) - 1u;
   #pragma unroll
   for (int r = 0; r < SORT_ROUNDS; ++r) {
-    const uint64_t i = wbase + (uint64_t)r * 32 + lane;
-    const bool valid = i < n;
-    ru[r] = valid ? iu[i] : 0u; rv[r] = valid ? iv[i] : 0u; rs[r] = (valid && has3) ? is[i] : 0u;
-    const uint32_t d = (sort_word(word, ru[r], rv[r], rs[r]) >> shift) & 255u;
+    const uint32_t idx = (uint32_t)warp * (32 * SORT_ROUNDS) + r * 32 + lane;
+    const bool valid = idx < tile_n;
+    uint32_t x = kw[idx];
+    if (word == 2) x = desc_key(x);
+    const uint32_t d = (x >> shift) & 255u;
     const unsigned m = __match_any_sync(NLP_FULL, valid ? d : (256u + lane));
     const uint32_t before = valid ? s_hist[warp][d] : 0u;
-    pre[r] = before + __popc(m & lt);
+    pre[r] = (d << 16) | (before + __popc(m & lt));                // digit and rank inside (warp, digit)
     __syncwarp();
     if (valid && (__ffs(m) - 1) == lane) s_hist[warp][d] = before + __popc(m);
     __syncwarp();
   }
   __syncthreads();
-  {   // thread t owns digit t: global base + tile prefix + warps before
-    uint32_t run = 0;
-    for (int d = 0; d < tid; ++d) run += s_tot[d];
-    run += counts[(uint64_t)tid * nblocks + blockIdx.x];
+  {   // thread t owns digit t
+    uint32_t c[SORT_WARPS], tile_count = 0;
     #pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t c = s_hist[w][tid]; s_hist[w][tid] = run; run += c; }
+    for (int w = 0; w < SORT_WARPS; ++w) { c[w] = s_hist[w][tid]; tile_count += c[w]; }
+    const uint32_t tile_start = sort_block_exclusive(tile_count, s_warp);       // records of smaller digits in this tile
+    const uint32_t digit_start = sort_block_exclusive(totals[tid], s_warp);     // ... in the whole buffer
+    uint32_t run = tile_start;
+    #pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) { s_hist[w][tid] = run; run += c[w]; }
+    s_gbase[tid] = digit_start + counts[(uint64_t)tid * nblocks + blockIdx.x] - tile_start;
   }
   __syncthreads();
   #pragma unroll
   for (int r = 0; r < SORT_ROUNDS; ++r) {
-    const uint64_t i = wbase + (uint64_t)r * 32 + lane;
-    if (i < n) {
-      const uint32_t d = (sort_word(word, ru[r], rv[r], rs[r]) >> shift) & 255u;
-      const uint32_t pos = s_hist[warp][d] + pre[r];
-      ou[pos] = ru[r]; ov[pos] = rv[r];
-      if (has3) os[pos] = rs[r];
+    const uint32_t idx = (uint32_t)warp * (32 * SORT_ROUNDS) + r * 32 + lane;
+    if (idx < tile_n) s_perm[s_hist[warp][pre[r] >> 16] + (pre[r] & 0xffffu)] = (uint16_t)idx;
+  }
+  __syncthreads();
+  #pragma unroll 4
+  for (int k = 0; k < SORT_ROUNDS; ++k) {
+    const uint32_t lp = (uint32_t)k * SORT_THREADS + tid;
+    if (lp < tile_n) {
+      const uint32_t src = s_perm[lp];
+      uint32_t x = kw[src];
+      if (word == 2) x = desc_key(x);
+      const uint32_t gp = s_gbase[(x >> shift) & 255u] + lp;
+      ou[gp] = raw[src]; ov[gp] = raw[SORT_TILE + src];
+      if (HAS3) os[gp] = raw[2 * SORT_TILE + src];
     }
   }
 }
