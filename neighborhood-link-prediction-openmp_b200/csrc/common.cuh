@@ -6,6 +6,8 @@
 
 #define NLP_FULL 0xffffffffu
 #define NLP_EMPTY 0xffffffffu     // hash-slot sentinel (vertex ids are < span <= 2^32-1)
+#define NLP_NO_SCORE 0xffffffffu  // "no pair here" in a record-aligned score array (a NaN pattern no kept
+                                  // score can have; desc_key maps it to the worst key 0xffffffff)
 
 namespace nlp {
 
@@ -133,11 +135,11 @@ struct Tally {
   }
 };
 
-// Score one touched pair and append it to the candidate buffer (kernel (d) fused epilogue).
-// Must be called by all 32 lanes of a warp (`has` = this lane holds a touched pair).
-// Returns the number of pairs the warp appended.
-__device__ __forceinline__ uint32_t score_and_emit(const Params& p, bool has, uint32_t u, uint64_t du,
-                                                   uint32_t v, uint32_t n, float nf, Tally& t) {
+// Score one touched pair (kernel (d), fused epilogue): returns true when the pair is kept
+// (score > min_score, inc/predict.hxx:311) and passes the pruning threshold; tallies candidates
+// and kept pairs.
+__device__ __forceinline__ bool score_pair(const Params& p, bool has, uint32_t u, uint64_t du, uint32_t v, uint32_t n,
+                                           float nf, Tally& t, float* score_out) {
   float score = 0.0f;
   bool keep = false;
   if (has) {
@@ -158,6 +160,17 @@ __device__ __forceinline__ uint32_t score_and_emit(const Params& p, bool has, ui
     const Threshold T = *p.thr;
     keep = (k < T.key) || (k == T.key && (u < T.u || (u == T.u && v < T.v)));
   }
+  *score_out = score;
+  return keep;
+}
+
+// Score one touched pair and append it to the candidate buffer.
+// Must be called by all 32 lanes of a warp (`has` = this lane holds a touched pair).
+// Returns the number of pairs the warp appended.
+__device__ __forceinline__ uint32_t score_and_emit(const Params& p, bool has, uint32_t u, uint64_t du,
+                                                   uint32_t v, uint32_t n, float nf, Tally& t) {
+  float score;
+  const bool keep = score_pair(p, has, u, du, v, n, nf, t, &score);
   const unsigned m = __ballot_sync(NLP_FULL, keep);
   if (m == 0) return 0;
   const int lane = threadIdx.x & 31;

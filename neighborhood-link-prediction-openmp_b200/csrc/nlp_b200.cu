@@ -69,6 +69,11 @@ struct nlp_handle {
   DevBuf tables, touched;
   // select / sort scratch
   DevBuf counts, totals, hist, sel, cursor2;
+  DevBuf oc_counts, oc_off;                  // ordered compaction (pair path top-K)
+  // pair path: records sorted by (u, v) in buffer pair_sorted, aligned scores in cs[pair_sorted ^ 1]
+  bool pair_pending = false;
+  int pair_sorted = 0;
+  uint64_t pair_n = 0, pair_kept = 0;
   // result
   int res_buf = 0;
   uint64_t res_count = 0;
@@ -260,7 +265,7 @@ int radix_pass(nlp_handle* h, int& buf, uint64_t n, uint32_t nblocks, int pass, 
   return NLP_OK;
 }
 
-int radix_sort(nlp_handle* h, int buf, uint64_t n, int* out_buf) {
+int radix_sort(nlp_handle* h, int buf, uint64_t n, int* out_buf, int first_pass = 0) {
   *out_buf = buf;
   if (n < 2) return NLP_OK;
   NLP_CUDA(h, cudaMemsetAsync(h->hist.p, 0, 12 * 256 * 8, h->stream));
@@ -272,7 +277,7 @@ int radix_sort(nlp_handle* h, int buf, uint64_t n, int* out_buf) {
   NLP_CUDA(h, cudaStreamSynchronize(h->stream));
   const uint32_t nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
   NLP_TRY(ensure(h, h->counts, (size_t)nblocks * 256 * 4));
-  for (int pass = 0; pass < 12; ++pass) {
+  for (int pass = first_pass; pass < 12; ++pass) {
     bool constant = false;
     for (int d = 0; d < 256; ++d)
       if (h->h_hist[pass * 256 + d] == n) { constant = true; break; }
@@ -332,6 +337,50 @@ int top_k(nlp_handle* h, int buf, uint64_t n, uint64_t K, int* out_buf, uint64_t
   }
   NLP_TRY(radix_sort(h, buf, n, out_buf));
   *out_n = std::min(n, K);
+  return NLP_OK;
+}
+
+// Pair path: the records in buffer `sb` are sorted by (u, v), cs[sb ^ 1] holds the aligned score
+// bits (NLP_NO_SCORE = nothing).  Select on the score alone, copy the survivors out in order,
+// stable-sort them by score: ties stay in ascending (u, v) order = canonical order.
+int top_k_ordered(nlp_handle* h, int sb, uint64_t n, uint64_t kept, uint64_t K, int* out_buf, uint64_t* out_n) {
+  const int cur = sb ^ 1;
+  *out_buf = cur; *out_n = 0;
+  if (!n || !kept) return NLP_OK;
+  const uint32_t* sbits = (const uint32_t*)h->cs[cur].p;
+  int mode = 0;
+  if (K < kept) {
+    NLP_CUDA(h, cudaMemsetAsync(h->sel.p, 0, sizeof(SelectState), h->stream));
+    const uint64_t slack = std::max<uint64_t>(K / 8, 65536);
+    uint64_t above = 0, bucket = n;
+    uint32_t bits = 0;
+    while (bits < 32 && above + bucket > K + slack) {
+      k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
+          (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, sbits, n, (SelectState*)h->sel.p);
+      NLP_LAUNCHED(h);
+      k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K);
+      NLP_LAUNCHED(h);
+      NLP_CUDA(h, cudaMemcpyAsync(h->h_sel, h->sel.p, offsetof(SelectState, hist), cudaMemcpyDeviceToHost, h->stream));
+      NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+      above = h->h_sel->above; bucket = h->h_sel->bucket; bits = h->h_sel->bits;
+    }
+    mode = bits > 0 ? 1 : 0;
+  }
+  const uint32_t ntiles = (uint32_t)((n + OC_TILE - 1) / OC_TILE);
+  NLP_TRY(ensure(h, h->oc_counts, (size_t)ntiles * 4));
+  NLP_TRY(ensure(h, h->oc_off, (size_t)ntiles * 8));
+  k_ordered_count<<<ntiles, OC_THREADS, 0, h->stream>>>(sbits, n, (const SelectState*)h->sel.p, mode, (uint32_t*)h->oc_counts.p);
+  NLP_LAUNCHED(h);
+  uint64_t m = 0;
+  NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &m));
+  // survivors go to (cu[cur], cv[cur], cs[sb]); swapping the two score arrays makes that buffer `cur`
+  k_ordered_write<<<ntiles, OC_THREADS, 0, h->stream>>>(
+      (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, sbits, n, (const SelectState*)h->sel.p, mode,
+      (const unsigned long long*)h->oc_off.p, (uint32_t*)h->cu[cur].p, (uint32_t*)h->cv[cur].p, (uint32_t*)h->cs[sb].p);
+  NLP_LAUNCHED(h);
+  std::swap(h->cs[0], h->cs[1]);
+  NLP_TRY(radix_sort(h, cur, m, out_buf, 8));      // score digits only
+  *out_n = std::min(m, K);
   return NLP_OK;
 }
 
@@ -488,10 +537,10 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
     p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
     p.gtable = (const double*)h->gtable.p;
     p.cap = h->cand_cap; p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
-    p.cu = (uint32_t*)h->cu[cur].p; p.cv = (uint32_t*)h->cv[cur].p; p.cs = (float*)h->cs[cur].p;
     k_pair_reduce<FLT><<<grid_for(P, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-        p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, P);
+        p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, P, (uint32_t*)h->cs[cur].p);
     NLP_LAUNCHED(h);
+    h->pair_sorted = sb;
     for (int i = 3; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
     h->phases_valid = true;
   }
@@ -502,12 +551,14 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   res->wedges = hc->wedges;
   res->candidates = hc->candidates;
   res->kept = hc->kept;
-  res->emitted = hc->cursor;
+  res->emitted = hc->kept;
   res->passes = 1;
   res->path = NLP_PATH_PAIR;
   res->pair_records = P;
+  h->pair_pending = true; h->pair_n = P; h->pair_kept = hc->kept;
+  if (!P) h->pair_sorted = 0;
   *out_buf = cur;
-  *out_fill = hc->cursor;
+  *out_fill = hc->kept;
   *used = true;
   return NLP_OK;
 }
@@ -525,6 +576,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
     if (used) return NLP_OK;
   }
   res->path = NLP_PATH_SOURCE;
+  h->pair_pending = false;
   NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
   NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
   const DevGraph g = dev_graph(h);
@@ -764,7 +816,7 @@ int nlp_destroy(nlp_handle* h) {
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
   release(h->tables); release(h->touched); release(h->counts); release(h->totals); release(h->hist);
-  release(h->sel); release(h->cursor2);
+  release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->h_hist) cudaFreeHost(h->h_hist);
   if (h->h_sel) cudaFreeHost(h->h_sel);
@@ -857,7 +909,8 @@ int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res) {
   }
   int ob = buf;
   uint64_t on = 0;
-  NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
+  if (h->pair_pending) NLP_TRY(top_k_ordered(h, h->pair_sorted, h->pair_n, h->pair_kept, opt->max_edges, &ob, &on));
+  else                 NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
   NLP_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
   NLP_CUDA(h, cudaEventSynchronize(h->ev_done));
   float sel = 0.f;

@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(256) k_pair_emit(const uint32_t* __restrict__ 
 }
 
 // Records sorted by (u, v): one thread per record, the first record of every run reduces the run.
+// Output stays ALIGNED with the records: score_bits[i] = score of the pair whose run starts at
+// record i, NLP_NO_SCORE everywhere else (inside runs, dropped pairs).  The kept pairs are thus
+// still in ascending (u, v) order, which the ordered top-K (select.cuh) exploits: it only has
+// to sort by score.
 template <bool FLT>
 __global__ void __launch_bounds__(256) k_pair_reduce(Params p, const uint32_t* __restrict__ pu, const uint32_t* __restrict__ pv,
-                                                     const uint32_t* __restrict__ pw, uint64_t n) {
+                                                     const uint32_t* __restrict__ pw, uint64_t n, uint32_t* __restrict__ score_bits) {
   Tally tally;
   const uint64_t n32 = (n + 31u) & ~31ull;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n32; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -200,7 +204,9 @@ __global__ void __launch_bounds__(256) k_pair_reduce(Params p, const uint32_t* _
       // existing edges keep their candidate slot with value 0 (inc/predict.hxx:306-307)
       if (row_contains(p.g.keys, ub, (uint32_t)du, v)) { cnt = 0; acc = 0.0f; }
     }
-    score_and_emit(p, head, u, du, v, cnt, acc, tally);
+    float score;
+    const bool keep = score_pair(p, head, u, du, v, cnt, acc, tally, &score);
+    if (i < n) score_bits[i] = keep ? __float_as_uint(score) : NLP_NO_SCORE;
   }
   tally.flush(p.ctr);
 }

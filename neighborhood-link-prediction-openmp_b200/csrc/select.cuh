@@ -324,4 +324,73 @@ __global__ void __launch_bounds__(256) k_select_compact(const uint32_t* __restri
   }
 }
 
+// ---- ordered top-K (pair path) ----------------------------------------------------------------
+// Input: n records (u, v) sorted by (u, v) and an aligned array of score bits (NLP_NO_SCORE =
+// nothing there).  The best K are found by an MSD radix select on the score alone, copied out IN
+// ORDER (tile counts -> scan -> write), and then only need a stable sort by score: ties keep the
+// ascending (u, v) order, which is the canonical order.
+enum { OC_THREADS = 256, OC_PER_THREAD = 8, OC_TILE = OC_THREADS * OC_PER_THREAD };
+
+// mode 0: every valid score; mode 1: score key prefix <= selected prefix (st->bits in [8, 32])
+__device__ __forceinline__ bool ordered_keep(const SelectState* st, uint32_t sbits, int mode) {
+  if (sbits == NLP_NO_SCORE) return false;
+  if (mode == 0) return true;
+  const uint32_t b = st->bits;
+  return (desc_key(sbits) >> (32 - b)) <= (st->pre_hi >> (32 - b));
+}
+
+__global__ void __launch_bounds__(OC_THREADS) k_ordered_count(const uint32_t* __restrict__ sbits, uint64_t n,
+                                                              const SelectState* __restrict__ st, int mode,
+                                                              uint32_t* __restrict__ tile_counts) {
+  __shared__ uint32_t s_warp[OC_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * OC_TILE + (uint64_t)threadIdx.x * OC_PER_THREAD;
+  uint32_t c = 0;
+  #pragma unroll
+  for (int k = 0; k < OC_PER_THREAD; ++k)
+    if (base + k < n && ordered_keep(st, sbits[base + k], mode)) ++c;
+  c = __reduce_add_sync(NLP_FULL, c);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    #pragma unroll
+    for (int w = 0; w < OC_THREADS / 32; ++w) t += s_warp[w];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(OC_THREADS) k_ordered_write(const uint32_t* __restrict__ pu, const uint32_t* __restrict__ pv,
+                                                              const uint32_t* __restrict__ sbits, uint64_t n,
+                                                              const SelectState* __restrict__ st, int mode,
+                                                              const unsigned long long* __restrict__ tile_off,
+                                                              uint32_t* __restrict__ ou, uint32_t* __restrict__ ov,
+                                                              uint32_t* __restrict__ os) {
+  __shared__ uint32_t s_warp[OC_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t base = (uint64_t)blockIdx.x * OC_TILE + (uint64_t)threadIdx.x * OC_PER_THREAD;
+  uint32_t sb[OC_PER_THREAD];
+  uint32_t c = 0, keepmask = 0;
+  #pragma unroll
+  for (int k = 0; k < OC_PER_THREAD; ++k) {
+    sb[k] = base + k < n ? sbits[base + k] : NLP_NO_SCORE;
+    if (ordered_keep(st, sb[k], mode)) { keepmask |= 1u << k; ++c; }
+  }
+  uint32_t inc = c;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t before = 0;
+  #pragma unroll
+  for (int w = 0; w < OC_THREADS / 32; ++w) before += w < warp ? s_warp[w] : 0u;
+  unsigned long long pos = tile_off[blockIdx.x] + before + inc - c;
+  #pragma unroll
+  for (int k = 0; k < OC_PER_THREAD; ++k) {
+    if ((keepmask >> k) & 1u) { ou[pos] = pu[base + k]; ov[pos] = pv[base + k]; os[pos] = sb[k]; ++pos; }
+  }
+}
+
 }  // namespace nlp
