@@ -54,6 +54,7 @@ struct nlp_handle {
   DevBuf it_u, it_cnt, it_dw, it_ptr, it_off, sym_flag;
   int sym_state = 0;                         // 0 unknown, 1 symmetric rows, 2 not symmetric
   int path_mode = NLP_PATH_AUTO;
+  int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
   uint32_t gtable_n = 0;
@@ -437,6 +438,20 @@ int launch_dense(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
   return NLP_OK;
 }
 
+// Count measures: hub-heavy sources on windowed shared-memory counters (k_range).
+constexpr uint32_t RANGE_COUNTERS = 48 * 1024;      // 192 KB of u32 counters per block
+
+template <bool ADMIT>
+int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t n, uint32_t* deferred) {
+  if (!n) return NLP_OK;
+  const size_t smem = (size_t)RANGE_COUNTERS * 4;
+  NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
+  k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 5, deferred, RANGE_COUNTERS);
+  NLP_LAUNCHED(h);
+  return NLP_OK;
+}
+
 template <bool FLT>
 int launch_tiny(nlp_handle* h, const Params& p, int bin, const uint32_t* list, uint32_t n) {
   if (!n) return NLP_OK;
@@ -634,7 +649,10 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   NLP_TRY(scratch_budget(h, &budget));
   unsigned dense_slots = 0;
   uint64_t touched_cap = 0;
-  if (nb[5]) {
+  // count measures take the windowed shared-memory counters; the float measures need the ordered
+  // single-warp accumulation of k_dense
+  const bool use_range = !FLT && h->maxdeg < (1u << 26) && h->range_mode != 0;
+  if (nb[5] && !use_range) {
     touched_cap = std::min<uint64_t>(hc->max_bound, S);
     const uint64_t per_slot = (uint64_t)S * 4 + touched_cap * 4;
     uint64_t want = FLT ? (uint64_t)h->num_sms * 16 : (uint64_t)h->num_sms * 2;
@@ -680,7 +698,8 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   if (!admit) {
     // everything fits: one pass, no admission control, no host round trip until the end
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
-    NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
+    if (use_range) NLP_TRY((launch_range<false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr)));
+    else NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
     for (int b = 4; b >= 2; --b) {
       NLP_TRY((launch_hash<FLT, false>(h, p, b, (const uint32_t*)h->list[b].p, (uint32_t)nb[b], nullptr)));
@@ -705,7 +724,8 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
       // reset queues / deferred counts, seed the reservation with the current fill
       NLP_CUDA(h, cudaMemsetAsync((char*)h->ctr.p + offsetof(Counters, deferred), 0, 16 * 8, h->stream));
       NLP_CUDA(h, cudaMemcpyAsync((char*)h->ctr.p + offsetof(Counters, reserved), &fill, 8, cudaMemcpyHostToDevice, h->stream));
-      NLP_TRY((launch_dense<FLT, true>(h, p, lists[5], (uint32_t)remaining[5], defers[5], dense_slots, touched_cap)));
+      if (use_range) NLP_TRY((launch_range<true>(h, p, lists[5], (uint32_t)remaining[5], defers[5])));
+      else NLP_TRY((launch_dense<FLT, true>(h, p, lists[5], (uint32_t)remaining[5], defers[5], dense_slots, touched_cap)));
       for (int b = 4; b >= 2; --b) NLP_TRY((launch_hash<FLT, true>(h, p, b, lists[b], (uint32_t)remaining[b], defers[b])));
       NLP_TRY(read_counters(h));
       fill = hc->cursor;

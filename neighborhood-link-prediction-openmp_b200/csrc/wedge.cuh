@@ -518,4 +518,155 @@ __global__ void k_dense(Params p, const uint32_t* __restrict__ list, uint32_t n,
   tally.flush(p.ctr);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Range path (count measures, hub-heavy sources): the candidate set of such a source is a large
+// fraction of the vertex set (1.6e5 of 2.6e5 vertices at R-MAT 18), so instead of hashing, the
+// block keeps DIRECT-ADDRESSED u32 counters in shared memory for a window [lo, lo + C) of v and
+// walks the windows lo = u+1, u+1+C, ...  Rows are sorted, so every pass reads only the part of
+// each second-hop row that falls in the window (two binary searches per row and pass); counting is
+// one shared-memory atomic per wedge, nothing leaves the SM until scoring.  Replaces the
+// reference's per-thread dense |V| array (inc/predict.hxx:117-122, 157-158), which the global
+// spill tables of k_dense emulate in HBM at the price of one 32-byte sector RMW per wedge.
+// Counter value 0 = untouched; RANGE_ZEROED = touched, then zeroed because v is in N(u)
+// (inc/predict.hxx:306-307: such pairs stay candidates with value 0).
+constexpr uint32_t RANGE_ZEROED = 0x80000000u;
+enum { RANGE_THREADS = 1024 };
+
+__device__ __forceinline__ uint32_t lower_bound_row(const uint32_t* __restrict__ keys, uint64_t b, uint32_t d, uint32_t x) {
+  uint32_t lo = 0, hi = d;                            // first position with key >= x
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(keys + b + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Wedges behind 32 first-hop entries whose v lies in [vlo, vhi): cnt[v - vlo] += 1.
+__device__ __forceinline__ void range_chunk(const Params& p, bool has, uint32_t w, uint32_t vlo, uint32_t vhi, uint32_t* cnt) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t* __restrict__ keys = p.g.keys;
+  uint64_t wb = 0;
+  uint32_t dw = 0;
+  if (has) {
+    wb = __ldg(p.g.off + w);
+    dw = (uint32_t)(__ldg(p.g.off + w + 1) - wb);
+    if (dw > 16u) {                                   // sorted row: cut to the window
+      const uint32_t a = lower_bound_row(keys, wb, dw, vlo);
+      const uint32_t b = vhi > vlo ? a + lower_bound_row(keys, wb + a, dw - a, vhi) : a;
+      wb += a; dw = b - a;
+    }
+  }
+  uint32_t inc = dw;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  // a chunk of 32 rows holds < 2^32 entries in a window of < 2^32 vertices unless rows carry
+  // astronomically many duplicates; the scan is exact for every graph the ABI accepts (M < 2^64
+  // is not the limit here, 32 * maxdeg < 2^32 is, and k_range is only used when that holds)
+  const uint32_t tot = __shfl_sync(NLP_FULL, inc, 31);
+  for (uint32_t sb = 0; sb < tot; sb += 32u) {
+    const uint32_t idx = sb + lane;
+    int j = 0;                                        // smallest j with inc[j] > idx
+    #pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
+      if (x <= idx) j += step;
+    }
+    const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
+    const uint32_t dwj  = __shfl_sync(NLP_FULL, dw, j);
+    const uint64_t wbj  = __shfl_sync(NLP_FULL, wb, j);
+    if (idx < tot) {
+      const uint32_t v = __ldg(keys + wbj + (idx - (incj - dwj)));
+      if (v >= vlo && v < vhi) atomicAdd(cnt + (v - vlo), 1u);      // inc/predict.hxx:156-158
+    }
+  }
+}
+
+template <bool ADMIT>
+__global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
+                                                             uint32_t* __restrict__ deferred, uint32_t C) {
+  extern __shared__ uint32_t cnt[];                   // C counters
+  __shared__ int s_go;
+  __shared__ uint32_t s_qi;
+  __shared__ unsigned int s_emitted;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const uint32_t* __restrict__ keys = p.g.keys;
+  Tally tally;
+  for (uint32_t i = tid; i < C; i += blockDim.x) cnt[i] = 0u;
+  if (tid == 0) s_emitted = 0;
+  __syncthreads();
+  for (;;) {
+    if (tid == 0) s_qi = (uint32_t)atomicAdd(&p.ctr->queue[bin], 1ull);     // dynamic: sources differ by 1000x in work
+    __syncthreads();
+    const uint32_t qi = s_qi;
+    __syncthreads();
+    if (qi >= n) break;
+    const uint32_t u = __ldg(list + qi);
+    uint32_t need = 0;
+    if (ADMIT) {
+      if (tid == 0) s_go = admit_source(p, u, bin, deferred, &need) ? 1 : 0;
+      __syncthreads();
+      const int go = s_go;
+      __syncthreads();
+      if (!go) continue;
+    }
+    const uint64_t ub = __ldg(p.g.off + u);
+    const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
+    const FirstHop f = first_hop(p, u, ub, du);
+    uint32_t emitted = 0;
+    for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += C) {
+      const uint32_t vlo = (uint32_t)lo64;
+      const uint32_t vhi = (uint32_t)(lo64 + C < p.g.S ? lo64 + C : p.g.S);
+      if (f.npieces == 1) {
+        for (uint32_t base = (uint32_t)warp * 32u; base < f.single_count; base += (uint32_t)nw * 32u) {
+          const uint32_t i = base + lane;
+          const bool has = i < f.single_count;
+          range_chunk(p, has, has ? __ldg(f.base + i) : 0u, vlo, vhi, cnt);
+        }
+      } else {
+        for (uint32_t c = warp; c < f.npieces; c += nw) {
+          const uint32_t pc = __ldg(f.piece_cnt + c);
+          const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
+          for (uint32_t base = 0; base < pc; base += 32u) {
+            const uint32_t i = base + lane;
+            const bool has = i < pc;
+            range_chunk(p, has, has ? __ldg(pb + i) : 0u, vlo, vhi, cnt);
+          }
+        }
+      }
+      __syncthreads();
+      {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
+        const uint32_t a = lower_bound_row(keys, ub, du, vlo);
+        const uint32_t b = a + lower_bound_row(keys, ub + a, du - a, vhi);
+        for (uint32_t i = a + tid; i < b; i += blockDim.x) {
+          const uint32_t x = __ldg(keys + ub + i) - vlo;
+          if (cnt[x] != 0u) cnt[x] = RANGE_ZEROED;
+        }
+      }
+      __syncthreads();
+      const uint32_t len = vhi - vlo;
+      for (uint32_t sb = (uint32_t)warp * 32u; sb < len; sb += (uint32_t)nw * 32u) {
+        const uint32_t i = sb + lane;
+        uint32_t c = 0;
+        if (i < len) { c = cnt[i]; if (c) cnt[i] = 0u; }
+        if (__any_sync(NLP_FULL, c != 0u))
+          emitted += score_and_emit(p, c != 0u, u, du, vlo + i, c & ~RANGE_ZEROED, 0.0f, tally);
+      }
+      __syncthreads();
+    }
+    if (ADMIT) {
+      if (lane == 0 && emitted) atomicAdd(&s_emitted, emitted);
+      __syncthreads();
+      if (tid == 0) {
+        atomicAdd(&p.ctr->reserved, (unsigned long long)s_emitted - (unsigned long long)need);
+        s_emitted = 0;
+      }
+      __syncthreads();
+    }
+  }
+  tally.flush(p.ctr);
+}
+
 }  // namespace nlp
