@@ -439,7 +439,7 @@ int launch_dense(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
 }
 
 // Count measures: hub-heavy sources on windowed shared-memory counters (k_range).
-constexpr uint32_t RANGE_COUNTERS = 48 * 1024;      // 192 KB of u32 counters per block
+constexpr uint32_t RANGE_COUNTERS = 52 * 1024;      // 208 KB of u32 counters per block (+13 KB static)
 
 template <bool ADMIT>
 int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t n, uint32_t* deferred) {
@@ -651,7 +651,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   uint64_t touched_cap = 0;
   // count measures take the windowed shared-memory counters; the float measures need the ordered
   // single-warp accumulation of k_dense
-  const bool use_range = !FLT && h->maxdeg < (1u << 26) && h->range_mode != 0;
+  const bool use_range = !FLT && h->maxdeg < (1u << 22) && h->range_mode != 0;
   if (nb[5] && !use_range) {
     touched_cap = std::min<uint64_t>(hc->max_bound, S);
     const uint64_t per_slot = (uint64_t)S * 4 + touched_cap * 4;

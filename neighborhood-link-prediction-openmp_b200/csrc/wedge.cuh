@@ -541,9 +541,39 @@ __device__ __forceinline__ uint32_t lower_bound_row(const uint32_t* __restrict__
   return lo;
 }
 
-// Wedges behind 32 first-hop entries whose v lies in [vlo, vhi): cnt[v - vlo] += 1.
-__device__ __forceinline__ void range_chunk(const Params& p, bool has, uint32_t w, uint32_t vlo, uint32_t vhi, uint32_t* cnt) {
-  const int lane = threadIdx.x & 31;
+// Block-wide inclusive scan of one u32 per thread (RANGE_THREADS threads) into s_inc[].
+__device__ __forceinline__ void range_block_scan(uint32_t x, uint32_t* s_inc, uint32_t* s_wsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = x;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_wsum[lane];                        // RANGE_THREADS / 32 == 32 warps
+    uint32_t winc = w;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(NLP_FULL, winc, d);
+      if (lane >= d) winc += t;
+    }
+    s_wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  s_inc[threadIdx.x] = inc + s_wsum[warp];
+  __syncthreads();
+}
+
+// Wedges behind up to RANGE_THREADS first-hop entries (thread t holds entry t) whose v lies in
+// [vlo, vhi): cnt[v - vlo] += 1.  The window parts of all rows are laid end to end and dealt to
+// the threads of the WHOLE block, so one hub row among the entries is shared by 1024 threads
+// instead of stalling the one warp that drew it (ncu: 54 % of the first version's stall samples
+// sat at the barrier behind such warps).
+__device__ __forceinline__ void range_batch(const Params& p, bool has, uint32_t w, uint32_t vlo, uint32_t vhi, uint32_t* cnt,
+                                            uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
   const uint32_t* __restrict__ keys = p.g.keys;
   uint64_t wb = 0;
   uint32_t dw = 0;
@@ -552,42 +582,33 @@ __device__ __forceinline__ void range_chunk(const Params& p, bool has, uint32_t 
     dw = (uint32_t)(__ldg(p.g.off + w + 1) - wb);
     if (dw > 16u) {                                   // sorted row: cut to the window
       const uint32_t a = lower_bound_row(keys, wb, dw, vlo);
-      const uint32_t b = vhi > vlo ? a + lower_bound_row(keys, wb + a, dw - a, vhi) : a;
+      const uint32_t b = a + lower_bound_row(keys, wb + a, dw - a, vhi);
       wb += a; dw = b - a;
     }
   }
-  uint32_t inc = dw;
-  #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
-    if (lane >= d) inc += t;
-  }
-  // a chunk of 32 rows holds < 2^32 entries in a window of < 2^32 vertices unless rows carry
-  // astronomically many duplicates; the scan is exact for every graph the ABI accepts (M < 2^64
-  // is not the limit here, 32 * maxdeg < 2^32 is, and k_range is only used when that holds)
-  const uint32_t tot = __shfl_sync(NLP_FULL, inc, 31);
-  for (uint32_t sb = 0; sb < tot; sb += 32u) {
-    const uint32_t idx = sb + lane;
-    int j = 0;                                        // smallest j with inc[j] > idx
-    #pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-      const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
-      if (x <= idx) j += step;
+  s_wb[threadIdx.x] = wb;
+  range_block_scan(dw, s_inc, s_wsum);                // k_range is only used when 1024 * maxdeg < 2^32
+  const uint32_t tot = s_inc[RANGE_THREADS - 1];
+  for (uint32_t idx = threadIdx.x; idx < tot; idx += RANGE_THREADS) {
+    uint32_t lo = 0, hi = RANGE_THREADS - 1;          // smallest j with s_inc[j] > idx
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_inc[mid] <= idx) lo = mid + 1; else hi = mid;
     }
-    const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
-    const uint32_t dwj  = __shfl_sync(NLP_FULL, dw, j);
-    const uint64_t wbj  = __shfl_sync(NLP_FULL, wb, j);
-    if (idx < tot) {
-      const uint32_t v = __ldg(keys + wbj + (idx - (incj - dwj)));
-      if (v >= vlo && v < vhi) atomicAdd(cnt + (v - vlo), 1u);      // inc/predict.hxx:156-158
-    }
+    const uint32_t before = lo ? s_inc[lo - 1] : 0u;
+    const uint32_t v = __ldg(keys + s_wb[lo] + (idx - before));
+    if (v >= vlo && v < vhi) atomicAdd(cnt + (v - vlo), 1u);        // inc/predict.hxx:156-158
   }
+  __syncthreads();
 }
 
 template <bool ADMIT>
 __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
                                                              uint32_t* __restrict__ deferred, uint32_t C) {
   extern __shared__ uint32_t cnt[];                   // C counters
+  __shared__ unsigned long long s_wb[RANGE_THREADS];
+  __shared__ uint32_t s_inc[RANGE_THREADS];
+  __shared__ uint32_t s_wsum[32];
   __shared__ int s_go;
   __shared__ uint32_t s_qi;
   __shared__ unsigned int s_emitted;
@@ -619,24 +640,15 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
     for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += C) {
       const uint32_t vlo = (uint32_t)lo64;
       const uint32_t vhi = (uint32_t)(lo64 + C < p.g.S ? lo64 + C : p.g.S);
-      if (f.npieces == 1) {
-        for (uint32_t base = (uint32_t)warp * 32u; base < f.single_count; base += (uint32_t)nw * 32u) {
-          const uint32_t i = base + lane;
-          const bool has = i < f.single_count;
-          range_chunk(p, has, has ? __ldg(f.base + i) : 0u, vlo, vhi, cnt);
-        }
-      } else {
-        for (uint32_t c = warp; c < f.npieces; c += nw) {
-          const uint32_t pc = __ldg(f.piece_cnt + c);
-          const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
-          for (uint32_t base = 0; base < pc; base += 32u) {
-            const uint32_t i = base + lane;
-            const bool has = i < pc;
-            range_chunk(p, has, has ? __ldg(pb + i) : 0u, vlo, vhi, cnt);
-          }
+      for (uint32_t c = 0; c < f.npieces; ++c) {
+        const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
+        const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
+        for (uint32_t base = 0; base < pc; base += RANGE_THREADS) {
+          const uint32_t i = base + tid;
+          const bool has = i < pc;
+          range_batch(p, has, has ? __ldg(pb + i) : 0u, vlo, vhi, cnt, s_inc, s_wb, s_wsum);
         }
       }
-      __syncthreads();
       {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
         const uint32_t a = lower_bound_row(keys, ub, du, vlo);
         const uint32_t b = a + lower_bound_row(keys, ub + a, du - a, vhi);

@@ -30,6 +30,9 @@ def graphs(quick):
     if not quick:
         out.append(("web50k", g.to_numpy(*g.web_crawl(50000, 12, seed=5))))
         out.append(("rmat16", g.to_numpy(*g.rmat(16, 16, 6))))
+    only = os.environ.get("SWEEP_GRAPHS")
+    if only:
+        out = [g for g in out if g[0] in only.split(",")]
     return out
 
 
