@@ -81,12 +81,13 @@ typedef struct {
   uint64_t emitted;             /* pairs written to the candidate buffer (after threshold prune) */
   uint64_t frontier_sources;    /* sources with non-zero work                                    */
   uint64_t bin_sources[8];      /* sources per path: [0]=8-lane [1]=32-lane [2..4]=hash 1K/4K/16K
-                                   [5]=global dense spill, [6..7] reserved                       */
+                                   [5]=global dense spill [6]=windowed shared-memory counters
+                                   (hub-heavy sources of the count measures), [7] reserved       */
   uint32_t passes;              /* candidate-buffer passes (1 unless the buffer had to be pruned)*/
   uint32_t path;                /* nlp_path the prediction ran on (NLP_PATH_SOURCE or NLP_PATH_PAIR) */
   float    phase_ms[8];         /* device time per phase of the LAST scoring repeat (CUDA events on
                                    the handle's stream).  NLP_PATH_SOURCE: [0] frontier
-                                   (eligibility+work+binning) [1] dense spill [2] hash 16K
+                                   (eligibility+work+binning) [1] hub-heavy sources (windowed counters + dense spill) [2] hash 16K
                                    [3] hash 4K [4] hash 1K [5] 32-lane [6] 8-lane; [1..6] are 0 when
                                    the buffer had to be pruned (passes > 1).  NLP_PATH_PAIR:
                                    [0] eligible rows + item descriptors + scans [1] wedge-record

@@ -13,7 +13,7 @@ namespace nlp {
 
 enum Measure { M_CN = 0, M_JC, M_SI, M_SC, M_HP, M_HD, M_LHN, M_AA, M_RA };
 
-enum { NBINS = 6 };
+enum { NBINS = 7 };
 // Rows longer than LONG_ROW first-hop entries are cut into CHUNK-entry pieces by the frontier
 // pass (one block per piece), so that a hub's row never serialises a single warp.
 constexpr uint32_t LONG_ROW = 2048;
@@ -22,6 +22,8 @@ constexpr uint32_t CHUNK = 2048;
 //   0: 8-lane sub-warp groups   (work <= 8)        1: 32-lane warp (work <= 32)
 //   2: smem hash, 1K slots      (bound <= 768)     3: smem hash, 4K slots (bound <= 3072)
 //   4: smem hash, 16K slots     (bound <= 12288)   5: global dense spill table
+//   6: windowed shared-memory counters (k_range): hub-heavy sources of the count measures whose
+//      work pays for walking the vertex range in windows of C counters
 // work(u)  = sum of deg(w) over eligible first-hop entries w of u   (wedges the reference scans)
 // bound(u) = min(work(u), S-1-u) >= number of distinct v > u the source can touch
 __host__ __device__ inline uint32_t bin_slots(int bin) { return bin == 2 ? 1024u : bin == 3 ? 4096u : 16384u; }
@@ -64,6 +66,7 @@ struct Params {
   DevGraph g;
   uint32_t D;          // MINDEGREE1 (0 = IHub)
   uint32_t F2;         // MAXFACTOR2
+  uint32_t coop;       // count measures: block-cooperative wedge streaming (maxdeg small enough)
   int      measure;
   float    min_score;
   const uint32_t* elig;     // LHub eligibility bitmask (bit w = deg(w) <= D), null for IHub

@@ -54,6 +54,7 @@ struct nlp_handle {
   DevBuf it_u, it_cnt, it_dw, it_ptr, it_off, sym_flag;
   int sym_state = 0;                         // 0 unknown, 1 symmetric rows, 2 not symmetric
   int path_mode = NLP_PATH_AUTO;
+  int coop_mode = 1;                         // 0: per-warp wedge streaming in k_hash / k_dense (count measures)
   int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
@@ -447,7 +448,7 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
   const size_t smem = (size_t)RANGE_COUNTERS * 4;
   NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
-  k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 5, deferred, RANGE_COUNTERS);
+  k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS);
   NLP_LAUNCHED(h);
   return NLP_OK;
 }
@@ -630,8 +631,11 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   }
   BinLists bl;
   for (int b = 0; b < NBINS; ++b) bl.list[b] = (uint32_t*)h->list[b].p;
+  // count measures may send hub-heavy sources to the windowed shared-memory counters (k_range);
+  // the float measures need the ordered single-warp accumulation of k_dense
+  const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS : 0u;
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
-                                                                  false, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
+                                                                  false, range_c, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -649,10 +653,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   NLP_TRY(scratch_budget(h, &budget));
   unsigned dense_slots = 0;
   uint64_t touched_cap = 0;
-  // count measures take the windowed shared-memory counters; the float measures need the ordered
-  // single-warp accumulation of k_dense
-  const bool use_range = !FLT && h->maxdeg < (1u << 22) && h->range_mode != 0;
-  if (nb[5] && !use_range) {
+  if (nb[5]) {
     touched_cap = std::min<uint64_t>(hc->max_bound, S);
     const uint64_t per_slot = (uint64_t)S * 4 + touched_cap * 4;
     uint64_t want = FLT ? (uint64_t)h->num_sms * 16 : (uint64_t)h->num_sms * 2;
@@ -682,6 +683,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   int cur = 0;
   Params p;
   p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
+  p.coop = (h->maxdeg < (1u << 22) && h->coop_mode != 0) ? 1u : 0u;
   p.elig = lhub ? (const uint32_t*)h->elig.p : nullptr;
   p.ekeys = lhub ? (const uint32_t*)h->ekeys.p : nullptr;
   p.ecount = lhub ? (const uint32_t*)h->ecount.p : nullptr;
@@ -698,8 +700,8 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   if (!admit) {
     // everything fits: one pass, no admission control, no host round trip until the end
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
-    if (use_range) NLP_TRY((launch_range<false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr)));
-    else NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
+    NLP_TRY((launch_range<false>(h, p, (const uint32_t*)h->list[6].p, (uint32_t)nb[6], nullptr)));
+    NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
     for (int b = 4; b >= 2; --b) {
       NLP_TRY((launch_hash<FLT, false>(h, p, b, (const uint32_t*)h->list[b].p, (uint32_t)nb[b], nullptr)));
@@ -724,8 +726,8 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
       // reset queues / deferred counts, seed the reservation with the current fill
       NLP_CUDA(h, cudaMemsetAsync((char*)h->ctr.p + offsetof(Counters, deferred), 0, 16 * 8, h->stream));
       NLP_CUDA(h, cudaMemcpyAsync((char*)h->ctr.p + offsetof(Counters, reserved), &fill, 8, cudaMemcpyHostToDevice, h->stream));
-      if (use_range) NLP_TRY((launch_range<true>(h, p, lists[5], (uint32_t)remaining[5], defers[5])));
-      else NLP_TRY((launch_dense<FLT, true>(h, p, lists[5], (uint32_t)remaining[5], defers[5], dense_slots, touched_cap)));
+      NLP_TRY((launch_range<true>(h, p, lists[6], (uint32_t)remaining[6], defers[6])));
+      NLP_TRY((launch_dense<FLT, true>(h, p, lists[5], (uint32_t)remaining[5], defers[5], dense_slots, touched_cap)));
       for (int b = 4; b >= 2; --b) NLP_TRY((launch_hash<FLT, true>(h, p, b, lists[b], (uint32_t)remaining[b], defers[b])));
       NLP_TRY(read_counters(h));
       fill = hc->cursor;
@@ -789,6 +791,8 @@ int nlp_create(nlp_handle** out, int device) {
   if (device < 0 || device >= ndev) { g_create_error = "nlp_create: bad device index"; return NLP_ERR_ARG; }
   nlp_handle* h = new nlp_handle();
   h->device = device;
+  if (const char* e = getenv("NLP_B200_RANGE")) h->range_mode = atoi(e);   // experiment knobs
+  if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string("nlp_create: ") + what + ": " + cudaGetErrorString(err);
     delete h;

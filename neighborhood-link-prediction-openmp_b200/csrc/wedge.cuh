@@ -154,6 +154,83 @@ __device__ __forceinline__ void stream_wedges(const Params& p, uint32_t u, uint6
   }
 }
 
+// Block-wide inclusive scan of one u32 per thread into s_inc[0 .. blockDim.x) (blockDim.x a
+// multiple of 32, at most 1024; s_wsum holds 32 words).
+__device__ __forceinline__ void block_scan_u32(uint32_t x, uint32_t* s_inc, uint32_t* s_wsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t inc = x;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < nw ? s_wsum[lane] : 0u;
+    uint32_t winc = w;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(NLP_FULL, winc, d);
+      if (lane >= d) winc += t;
+    }
+    s_wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  s_inc[threadIdx.x] = inc + s_wsum[warp];
+  __syncthreads();
+}
+
+// Count measures, block-cooperative: thread t of the team takes first-hop entry t of a batch, the
+// second-hop rows of the whole batch are laid end to end (block scan) and dealt to ALL threads, so
+// a hub row inside the batch is shared by the team instead of stalling the one warp that drew it.
+// Order does not matter for integer counts.  Requires blockDim.x * maxdeg < 2^32 (host checks).
+template <class Sink>
+__device__ __forceinline__ void stream_wedges_block(const Params& p, uint32_t u, uint64_t ub, uint32_t du, Sink& sink,
+                                                    uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
+  const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+  const uint32_t* __restrict__ keys = p.g.keys;
+  const FirstHop f = first_hop(p, u, ub, du);
+  for (uint32_t c = 0; c < f.npieces; ++c) {
+    const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
+    const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
+    for (uint32_t base = 0; base < pc; base += nt) {
+      const uint32_t i = base + tid;
+      uint64_t wb = 0;
+      uint32_t dw = 0;
+      if (i < pc) {
+        const uint32_t w = __ldg(pb + i);
+        wb = __ldg(p.g.off + w);
+        dw = (uint32_t)(__ldg(p.g.off + w + 1) - wb);
+        if (dw > 32u) {                                 // sorted row: jump over v <= u
+          const uint32_t sk = skip_le(keys, wb, dw, u);
+          wb += sk; dw -= sk;
+        }
+      }
+      s_wb[tid] = wb;
+      block_scan_u32(dw, s_inc, s_wsum);
+      const uint32_t tot = s_inc[nt - 1];
+      for (uint32_t b2 = (uint32_t)(tid & ~31); b2 < tot; b2 += nt) {      // warp-uniform trip count
+        const uint32_t idx = b2 + lane;
+        bool ok = idx < tot;
+        uint32_t v = 0;
+        if (ok) {
+          uint32_t lo = 0, hi = nt - 1;                 // smallest j with s_inc[j] > idx
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_inc[mid] <= idx) lo = mid + 1; else hi = mid;
+          }
+          const uint32_t before = lo ? s_inc[lo - 1] : 0u;
+          v = __ldg(keys + s_wb[lo] + (idx - before));
+          ok = v > u;                                   // inc/predict.hxx:292-296
+        }
+        sink.wedge(ok, v, 0.0);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // Ordered fold of the FLT measures inside one warp: lanes hold wedges in reference order;
 // `m` is the match.any group of this lane's v, `mine` marks its lowest lane, `dups` the lanes
 // that sit in a group of two or more.  Returns, in the leader lane, acc after adding the group's
@@ -342,6 +419,9 @@ template <bool FLT, bool ADMIT>
 __global__ void k_hash(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
                        uint32_t* __restrict__ deferred, int log2_slots) {
   extern __shared__ uint2 slots[];
+  __shared__ unsigned long long s_wb[FLT ? 32 : 512];
+  __shared__ uint32_t s_inc[FLT ? 32 : 512];
+  __shared__ uint32_t s_wsum[32];
   __shared__ int s_go;
   __shared__ unsigned int s_emitted, s_count;
   const uint32_t nslots = 1u << log2_slots, mask = nslots - 1u;
@@ -367,6 +447,7 @@ __global__ void k_hash(Params p, const uint32_t* __restrict__ list, uint32_t n, 
     const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
     const HashTable table{slots, slist, &s_count, mask, shift};
     if (FLT) { HashSinkFlt sink{table};   stream_wedges<true>(p, u, ub, du, warp, nw, sink); }
+    else if (p.coop) { HashSinkCount sink{table}; stream_wedges_block(p, u, ub, du, sink, s_inc, s_wb, s_wsum); }
     else     { HashSinkCount sink{table}; stream_wedges<false>(p, u, ub, du, warp, nw, sink); }
     __syncthreads();
     const uint32_t nt = s_count;
@@ -467,6 +548,9 @@ template <bool FLT, bool ADMIT>
 __global__ void k_dense(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
                         uint32_t* __restrict__ deferred, uint32_t* __restrict__ tables,
                         uint32_t* __restrict__ touched_all, uint64_t touched_cap) {
+  __shared__ unsigned long long s_wb[FLT ? 32 : 512];
+  __shared__ uint32_t s_inc[FLT ? 32 : 512];
+  __shared__ uint32_t s_wsum[32];
   __shared__ int s_go;
   __shared__ unsigned int s_cnt, s_emitted;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -489,6 +573,7 @@ __global__ void k_dense(Params p, const uint32_t* __restrict__ list, uint32_t n,
     const uint64_t ub = __ldg(p.g.off + u);
     const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
     if (FLT) { DenseSinkFlt sink{table, touched, &s_cnt};   stream_wedges<true>(p, u, ub, du, warp, nw, sink); }
+    else if (p.coop) { DenseSinkCount sink{table, touched, &s_cnt}; stream_wedges_block(p, u, ub, du, sink, s_inc, s_wb, s_wsum); }
     else     { DenseSinkCount sink{table, touched, &s_cnt}; stream_wedges<false>(p, u, ub, du, warp, nw, sink); }
     __syncthreads();
     for (uint32_t i = tid; i < du; i += blockDim.x)                 // inc/predict.hxx:307
@@ -541,32 +626,6 @@ __device__ __forceinline__ uint32_t lower_bound_row(const uint32_t* __restrict__
   return lo;
 }
 
-// Block-wide inclusive scan of one u32 per thread (RANGE_THREADS threads) into s_inc[].
-__device__ __forceinline__ void range_block_scan(uint32_t x, uint32_t* s_inc, uint32_t* s_wsum) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t inc = x;
-  #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
-    if (lane >= d) inc += t;
-  }
-  if (lane == 31) s_wsum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = s_wsum[lane];                        // RANGE_THREADS / 32 == 32 warps
-    uint32_t winc = w;
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(NLP_FULL, winc, d);
-      if (lane >= d) winc += t;
-    }
-    s_wsum[lane] = winc - w;
-  }
-  __syncthreads();
-  s_inc[threadIdx.x] = inc + s_wsum[warp];
-  __syncthreads();
-}
-
 // Wedges behind up to RANGE_THREADS first-hop entries (thread t holds entry t) whose v lies in
 // [vlo, vhi): cnt[v - vlo] += 1.  The window parts of all rows are laid end to end and dealt to
 // the threads of the WHOLE block, so one hub row among the entries is shared by 1024 threads
@@ -587,7 +646,7 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, uint32_t 
     }
   }
   s_wb[threadIdx.x] = wb;
-  range_block_scan(dw, s_inc, s_wsum);                // k_range is only used when 1024 * maxdeg < 2^32
+  block_scan_u32(dw, s_inc, s_wsum);                  // k_range is only used when 1024 * maxdeg < 2^32
   const uint32_t tot = s_inc[RANGE_THREADS - 1];
   for (uint32_t idx = threadIdx.x; idx < tot; idx += RANGE_THREADS) {
     uint32_t lo = 0, hi = RANGE_THREADS - 1;          // smallest j with s_inc[j] > idx
