@@ -36,6 +36,15 @@ WORKLOADS = {
     "rmat20": dict(kind="rmat", scale=20, ef=16, seed=43, frac=0.1, desc="R-MAT scale-20 (smoke size)"),
     "rmat18": dict(kind="rmat", scale=18, ef=16, seed=42, frac=0.01, desc="R-MAT scale-18, 1e-2|E| removed (configs[0])"),
     "rmat16": dict(kind="rmat", scale=16, ef=16, seed=42, frac=0.1, desc="R-MAT scale-16 (tiny)"),
+    # BASELINE configs[2..4]: parity/scale cases, run with --workload (not the default bench line)
+    "road24m": dict(kind="road", side=4900, keep=0.6, seed=44, frac=0.1,
+                    desc="road/mesh-shaped 4900x4900 lattice, edges kept with p=0.6 (~24M vertices, avg degree ~2.4), 0.1|E| removed (configs[2])"),
+    "web50m": dict(kind="web", n=50_000_000, avg_out=19, seed=45, frac=0.1,
+                   desc="web-crawl-shaped, 50M vertices, power-law out-degree, host locality (configs[3], sk-2005 scale)"),
+    "web25m": dict(kind="web", n=25_000_000, avg_out=19, seed=45, frac=0.1, desc="web-crawl-shaped, 25M vertices (configs[3] at half scale)"),
+    "web6m": dict(kind="web", n=6_250_000, avg_out=19, seed=45, frac=0.1, desc="web-crawl-shaped, 6.25M vertices (configs[3] at 1/8 scale)"),
+    "rmat24": dict(kind="rmat", scale=24, ef=16, seed=46, frac=0.01, desc="R-MAT scale-24, 1e-2|E| removed (configs[4]; use --degree 0)"),
+    "rmat21": dict(kind="rmat", scale=21, ef=16, seed=46, frac=0.01, desc="R-MAT scale-21, 1e-2|E| removed (configs[4] at 1/8 scale; use --degree 0)"),
 }
 MEASURES = ["CN", "JC", "SI", "SC", "HP", "HD", "LHN", "AA", "RA"]
 METRIC = "lhub_predicted_edges_per_s"
@@ -45,7 +54,12 @@ def build_workload(name, device):
     import nlp_b200 as N
     w = WORKLOADS[name]
     t0 = time.time()
-    off, keys = N.graphs.rmat(w["scale"], w["ef"], w["seed"], permute=True, device=device)
+    if w["kind"] == "rmat":
+        off, keys = N.graphs.rmat(w["scale"], w["ef"], w["seed"], permute=True, device=device)
+    elif w["kind"] == "road":
+        off, keys = N.graphs.road_lattice(w["side"], w["keep"], w["seed"], device=device)
+    else:
+        off, keys = N.graphs.web_crawl(w["n"], w["avg_out"], seed=w["seed"], device=device)
     off, keys, rl, rh = N.graphs.remove_edges(off, keys, w["frac"], w["seed"] + 1000)
     K = int(rl.numel())
     del rl, rh
@@ -149,6 +163,8 @@ def run_reference(args):
     nm = int(max(1, min(len(MEASURES), 150.0 / (per_measure * total_steps))))
     order = ["JC", "AA", "CN", "SC", "RA", "SI", "HP", "HD", "LHN"]
     sample = [m for m in MEASURES if m in order[:nm]]
+    if args.measures:
+        sample = [m for m in args.measures.split(",") if m]
     for _ in range(args.warmup):
         reference_step(R, K, args.degree, sample, threads)
     edges = 0; ref_ms = 0.0; wall = 0.0
@@ -187,13 +203,16 @@ def run_b200(args):
     off, keys, K, info = build_workload(args.workload, dev)
     S = int(off.numel() - 1); M = int(keys.numel())
     # host copies in pinned memory (e2e leg) -- int64/int32 tensors carry the uint64/uint32 bits
-    h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
+    do_e2e = not args.no_e2e
+    if do_e2e:
+        h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
     pred = N.Predictor(local)
     pred.set_partition(rank, world)
     stream = torch.cuda.ExternalStream(pred.lib.nlp_stream(pred.h), device=dev)
-    measures = MEASURES
+    measures = [m for m in args.measures.split(",") if m] if args.measures else MEASURES
     D = args.degree
-    h_out = [torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()]
+    if do_e2e:
+        h_out = [torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()]
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,24 +265,26 @@ def run_b200(args):
 
     # ---- value: graph resident in HBM ---------------------------------------------------------
     pred.set_graph_pointers(off.data_ptr(), keys.data_ptr(), S, device=True, keep=(off, keys))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~0.1 s to come up: start it before the warm-up
     for _ in range(args.warmup):
         one_step()
     launches0 = pred.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     edges, ms, wall, results = timed(one_step, args.steps, collect=True)
-    clocks = sampler.stop() if rank == 0 else None
     launches = pred.launch_count() - launches0
     value = edges / (ms / 1e3)
 
     # ---- e2e: host buffers in, host results out ----------------------------------------------
-    for _ in range(max(1, min(args.warmup, 2))):
-        one_step_e2e()
-    e_edges, e_ms, e_wall, _ = timed(one_step_e2e, args.steps)
-    e2e_value = e_edges / (e_ms / 1e3)
-    h2d = (S + 1) * 8 + M * 4
-    d2h = int(e_edges / args.steps) * 12
+    if do_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            one_step_e2e()
+        e_edges, e_ms, e_wall, _ = timed(one_step_e2e, args.steps)
+        e2e = {"value": e_edges / (e_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": (S + 1) * 8 + M * 4,
+               "d2h_bytes_per_step": int(e_edges / args.steps) * 12, "ms_per_step": e_ms / args.steps}
+    else:
+        e2e = None
+    clocks = sampler.stop() if rank == 0 else None     # sampled over warm-up + both timed regions
 
     if rank != 0:
         if world > 1:
@@ -298,14 +319,20 @@ def run_b200(args):
                  (names[7], phase[7], 12 * E + 12 * Kout)]
     else:
         wedge_ms = sum(phase[1:7])
+        if wedge_ms == 0:   # pruned candidate buffer (passes > 1, e.g. IHub): per-phase events are off
+            wedge_ms = sum(r["scoring_ms"] - r["frontier_ms"] for r in results)
         # algorithmic bytes, split by the phase that moves them
         cands = [("frontier: k_work (first-hop scan, hub test, work sums)", phase[0], nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world)),
                  ("wedge kernels (k_dense/k_hash/k_tiny: 2-hop scan + count + score)", wedge_ms, 4 * W + 4 * C + 12 * E),
                  (names[7], phase[7], 12 * E + 12 * Kout)]
     dom = max(cands, key=lambda c: c[1])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from `ncu --set full` (see profiles/README.md)
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload + ":" + str(D), {}).get(dom[0])
     achieved = dom[2] / (dom[1] / 1e3) / 1e9 if dom[1] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": dom[1] / max(1e-9, sum(phase)),
                 "algorithmic_bytes_per_step": dom[2] / args.steps}
     # whole step against the reference algorithm's bytes (SURVEY.md section 8d formula)
@@ -316,16 +343,18 @@ def run_b200(args):
     cpu = None
     try:
         from oracle import oracle_py as O
-        if O.ref_available():
+        if args.no_cpu_baseline:
+            cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "reference", "sample": "skipped (--no-cpu-baseline)"}
+        elif O.ref_available():
             offn, keysn = N.graphs.to_numpy(off, keys)
             R = O.RefGraph(offn, keysn)
             threads = os.cpu_count() or 1
-            sample = ["JC", "AA"]
+            sample = [m for m in ("JC", "AA") if m in measures] or measures[:1]
             e, rms, w = reference_step(R, K, D, sample, threads)
             if e == K * len(sample):
                 cpu = {"value": e / (rms / 1e3), "unit": "edges/s", "cores": threads, "kind": "reference",
-                       "sample": "one pass of %s (2 of 9 measures) on the full graph, reference OpenMP templates, "
-                                 "reference's own `time` field (%.0f ms wall)" % ("+".join(sample), w * 1e3)}
+                       "sample": "one pass of %s (%d of %d measures) on the full graph, reference OpenMP templates, "
+                                 "reference's own `time` field (%.0f ms wall)" % ("+".join(sample), len(sample), len(measures), w * 1e3)}
             else:
                 cpu = {"value": None, "unit": "edges/s", "cores": threads, "kind": "reference",
                        "sample": "reference returned fewer than K edges (UB regime)"}
@@ -347,8 +376,7 @@ def run_b200(args):
         "config": dict(info, min_degree1=D, measures=measures, l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6),
                        parallelism="sources partitioned over %d GPU(s), CSR replicated" % world),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e_ms / args.steps},
+        "e2e": e2e,
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -356,7 +384,7 @@ def run_b200(args):
         "step_hbm_frac": step_frac,
         "phase_ms_per_step": {n: p / args.steps for n, p in zip(names, phase)},
         "wall_ms_per_step": wall * 1e3 / args.steps,
-        "bins": results[0]["bin_sources"][:6],
+        "bins": results[0]["bin_sources"][:7],
         "path": {1: "source-centric", 2: "pair"}.get(path, path),
     }
     print(json.dumps(line))
@@ -368,11 +396,14 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rmat22", choices=sorted(WORKLOADS))
-    ap.add_argument("--degree", type=int, default=16, help="MINDEGREE1 of the LHub runs")
+    ap.add_argument("--degree", type=int, default=16, help="MINDEGREE1 of the LHub runs (0 = IHub)")
+    ap.add_argument("--measures", default="", help="comma list (default: all nine)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large workloads)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run on the host cores")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

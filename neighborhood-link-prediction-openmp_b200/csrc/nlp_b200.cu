@@ -55,6 +55,9 @@ struct nlp_handle {
   int sym_state = 0;                         // 0 unknown, 1 symmetric rows, 2 not symmetric
   int path_mode = NLP_PATH_AUTO;
   int coop_mode = 1;                         // 0: per-warp wedge streaming in k_hash / k_dense (count measures)
+  int cluster_mode = 0;                      // 0: single-CTA k_range only (default: remote shared-memory atomics
+                                             // measured 1.3x/2x/3.3x slower at cluster size 2/4/8, R-MAT 20 IHub),
+                                             // 1: auto, n > 1: force clusters of n CTAs
   int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
@@ -442,13 +445,44 @@ int launch_dense(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
 // Count measures: hub-heavy sources on windowed shared-memory counters (k_range).
 constexpr uint32_t RANGE_COUNTERS = 52 * 1024;      // 208 KB of u32 counters per block (+13 KB static)
 
+// CTAs per cluster for the range path: 1 while a source needs few windows anyway, else 8
+// (portable cluster size; windows 8x wider, passes 8x fewer).
+inline uint32_t range_cluster_size(const nlp_handle* h) {
+  if (h->cluster_mode == 0) return 1;
+  if (h->cluster_mode > 1) return (uint32_t)h->cluster_mode;
+  return ((uint64_t)h->S + RANGE_COUNTERS - 1) / RANGE_COUNTERS > 8 ? 8u : 1u;
+}
+
 template <bool ADMIT>
 int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t n, uint32_t* deferred) {
   if (!n) return NLP_OK;
   const size_t smem = (size_t)RANGE_COUNTERS * 4;
-  NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
-  k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS);
+  const uint32_t cs = range_cluster_size(h);
+  if (cs <= 1) {
+    NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
+    k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS);
+    NLP_LAUNCHED(h);
+    return NLP_OK;
+  }
+  auto kern = k_range_cluster<ADMIT>;
+  NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cs > 8) NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(RANGE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(cs);
+  int max_clusters = 0;
+  NLP_CUDA(h, cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+  if (max_clusters < 1) return fail(h, NLP_ERR_CUDA, "k_range_cluster: no cluster of this size fits the device");
+  const unsigned nclusters = (unsigned)std::min<uint64_t>(n, (uint64_t)max_clusters);
+  cfg.gridDim = dim3(nclusters * cs);
+  uint32_t C = RANGE_COUNTERS;
+  int bin = 6;
+  NLP_CUDA(h, cudaLaunchKernelEx(&cfg, kern, p, list, n, bin, deferred, C));
   NLP_LAUNCHED(h);
   return NLP_OK;
 }
@@ -633,7 +667,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   for (int b = 0; b < NBINS; ++b) bl.list[b] = (uint32_t*)h->list[b].p;
   // count measures may send hub-heavy sources to the windowed shared-memory counters (k_range);
   // the float measures need the ordered single-warp accumulation of k_dense
-  const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS : 0u;
+  const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS * range_cluster_size(h) : 0u;
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
                                                                   false, range_c, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
@@ -793,6 +827,7 @@ int nlp_create(nlp_handle** out, int device) {
   h->device = device;
   if (const char* e = getenv("NLP_B200_RANGE")) h->range_mode = atoi(e);   // experiment knobs
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
+  if (const char* e = getenv("NLP_B200_CLUSTER")) h->cluster_mode = atoi(e);
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string("nlp_create: ") + what + ": " + cudaGetErrorString(err);
     delete h;
