@@ -71,7 +71,7 @@ struct nlp_handle {
   DevBuf cu[2], cv[2], cs[2];
   uint64_t cand_cap = 0;
   // dense spill tables
-  DevBuf tables, touched;
+  DevBuf tables, touched, range_cursors;
   // select / sort scratch
   DevBuf counts, totals, hist, sel, cursor2;
   DevBuf oc_counts, oc_off;                  // ordered compaction (pair path top-K)
@@ -461,7 +461,11 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
   if (cs <= 1) {
     NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
-    k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS);
+    // per block: row cursor + row end for every first-hop entry of its current source
+    const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
+    NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * 2 * stride * 8));
+    k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS,
+                                                             (unsigned long long*)h->range_cursors.p, stride);
     NLP_LAUNCHED(h);
     return NLP_OK;
   }
@@ -874,7 +878,7 @@ int nlp_destroy(nlp_handle* h) {
   for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
-  release(h->tables); release(h->touched); release(h->counts); release(h->totals); release(h->hist);
+  release(h->tables); release(h->touched); release(h->range_cursors); release(h->counts); release(h->totals); release(h->hist);
   release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->h_hist) cudaFreeHost(h->h_hist);

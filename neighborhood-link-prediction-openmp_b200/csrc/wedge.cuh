@@ -627,26 +627,51 @@ __device__ __forceinline__ uint32_t lower_bound_row(const uint32_t* __restrict__
   return lo;
 }
 
+// First position in [a, e) (absolute indices into keys, sorted row) whose key is >= x: gallop from
+// a, then bisect.  Window after window the cursor only moves forward, so a step costs O(log of
+// the segment it skips) dependent loads instead of O(log of the row).
+__device__ __forceinline__ unsigned long long gallop_to(const uint32_t* __restrict__ keys, unsigned long long a,
+                                                        unsigned long long e, uint32_t x) {
+  if (a >= e || __ldg(keys + a) >= x) return a;
+  unsigned long long lo = a, step = 1;                 // keys[lo] < x
+  while (lo + step < e && __ldg(keys + lo + step) < x) { lo += step; step <<= 1; }
+  unsigned long long hi = lo + step < e ? lo + step : e;   // keys[hi] >= x, or hi == e
+  while (lo + 1 < hi) {
+    const unsigned long long mid = lo + ((hi - lo) >> 1);
+    if (__ldg(keys + mid) < x) lo = mid; else hi = mid;
+  }
+  return hi;
+}
+
 // Wedges behind up to RANGE_THREADS first-hop entries (thread t holds entry t) whose v lies in
 // [vlo, vhi): cnt[v - vlo] += 1.  The window parts of all rows are laid end to end and dealt to
 // the threads of the WHOLE block, so one hub row among the entries is shared by 1024 threads
 // instead of stalling the one warp that drew it (ncu: 54 % of the first version's stall samples
-// sat at the barrier behind such warps).
-__device__ __forceinline__ void range_batch(const Params& p, bool has, uint32_t w, uint32_t vlo, uint32_t vhi, uint32_t* cnt,
+// sat at the barrier behind such warps).  cur[] / end[] (global scratch of this block, one slot
+// per first-hop entry) carry every row's position from window to window: the first window finds
+// the first key > u by bisection and stores the row end, later windows only read the two words
+// (coalesced) and gallop forward.
+__device__ __forceinline__ void range_batch(const Params& p, bool has, bool first, uint32_t w, uint32_t vlo, uint32_t vhi,
+                                            unsigned long long* cur, unsigned long long* end, uint32_t* cnt,
                                             uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
   const uint32_t* __restrict__ keys = p.g.keys;
-  uint64_t wb = 0;
+  unsigned long long a = 0;
   uint32_t dw = 0;
   if (has) {
-    wb = __ldg(p.g.off + w);
-    dw = (uint32_t)(__ldg(p.g.off + w + 1) - wb);
-    if (dw > 16u) {                                   // sorted row: cut to the window
-      const uint32_t a = lower_bound_row(keys, wb, dw, vlo);
-      const uint32_t b = a + lower_bound_row(keys, wb + a, dw - a, vhi);
-      wb += a; dw = b - a;
+    unsigned long long e;
+    if (first) {
+      const unsigned long long wb = __ldg(p.g.off + w);
+      e = __ldg(p.g.off + w + 1);
+      a = wb + lower_bound_row(keys, wb, (uint32_t)(e - wb), vlo);
+      *end = e;
+    } else {
+      a = *cur; e = *end;
     }
+    const unsigned long long b = vhi >= p.g.S ? e : gallop_to(keys, a, e, vhi);
+    *cur = b;
+    dw = (uint32_t)(b - a);
   }
-  s_wb[threadIdx.x] = wb;
+  s_wb[threadIdx.x] = a;
   block_scan_u32(dw, s_inc, s_wsum);                  // k_range is only used when 1024 * maxdeg < 2^32
   const uint32_t tot = s_inc[RANGE_THREADS - 1];
   for (uint32_t idx = threadIdx.x; idx < tot; idx += RANGE_THREADS) {
@@ -657,15 +682,18 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, uint32_t 
     }
     const uint32_t before = lo ? s_inc[lo - 1] : 0u;
     const uint32_t v = __ldg(keys + s_wb[lo] + (idx - before));
-    if (v >= vlo && v < vhi) atomicAdd(cnt + (v - vlo), 1u);        // inc/predict.hxx:156-158
+    atomicAdd(cnt + (v - vlo), 1u);                                  // inc/predict.hxx:156-158
   }
   __syncthreads();
 }
 
 template <bool ADMIT>
 __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
-                                                             uint32_t* __restrict__ deferred, uint32_t C) {
+                                                             uint32_t* __restrict__ deferred, uint32_t C,
+                                                             unsigned long long* __restrict__ cursors, uint64_t cursor_stride) {
   extern __shared__ uint32_t cnt[];                   // C counters
+  unsigned long long* cur = cursors + (uint64_t)blockIdx.x * 2 * cursor_stride;   // [cursor_stride] positions
+  unsigned long long* end = cur + cursor_stride;                                  // [cursor_stride] row ends
   __shared__ unsigned long long s_wb[RANGE_THREADS];
   __shared__ uint32_t s_inc[RANGE_THREADS];
   __shared__ uint32_t s_wsum[32];
@@ -700,13 +728,15 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
     for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += C) {
       const uint32_t vlo = (uint32_t)lo64;
       const uint32_t vhi = (uint32_t)(lo64 + C < p.g.S ? lo64 + C : p.g.S);
+      const bool first = lo64 == (uint64_t)u + 1;
       for (uint32_t c = 0; c < f.npieces; ++c) {
         const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
         const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
         for (uint32_t base = 0; base < pc; base += RANGE_THREADS) {
           const uint32_t i = base + tid;
           const bool has = i < pc;
-          range_batch(p, has, has ? __ldg(pb + i) : 0u, vlo, vhi, cnt, s_inc, s_wb, s_wsum);
+          const uint64_t ci = (uint64_t)c * CHUNK + i;
+          range_batch(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, cur + ci, end + ci, cnt, s_inc, s_wb, s_wsum);
         }
       }
       {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
