@@ -88,8 +88,9 @@ typedef struct {
   float    phase_ms[8];         /* device time per phase of the LAST scoring repeat (CUDA events on
                                    the handle's stream).  NLP_PATH_SOURCE: [0] frontier
                                    (eligibility+work+binning) [1] hub-heavy sources (windowed counters + dense spill) [2] hash 16K
-                                   [3] hash 4K [4] hash 1K [5] 32-lane [6] 8-lane; [1..6] are 0 when
-                                   the buffer had to be pruned (passes > 1).  NLP_PATH_PAIR:
+                                   [3] hash 4K [4] hash 1K [5] 32-lane [6] 8-lane; summed over the
+                                   passes when the buffer had to be pruned (passes > 1; the top-K
+                                   cuts between passes are not included).  NLP_PATH_PAIR:
                                    [0] eligible rows + item descriptors + scans [1] wedge-record
                                    emission [2] radix sort by (u, v) [3] run reduce + scoring.
                                    Both: [7] final select+sort.                                  */

@@ -82,6 +82,7 @@ struct Params {
   const uint32_t* chunk_cnt;
   uint32_t* cu; uint32_t* cv; float* cs;   // candidate buffer (SoA)
   unsigned long long cap;
+  unsigned long long soft_cap;   // admission of a pass stops once this many candidates are written
   Counters* ctr;
   const Threshold* thr;
 };

@@ -37,6 +37,7 @@ struct nlp_handle {
   cudaEvent_t ev_start = nullptr, ev_frontier = nullptr, ev_scored = nullptr, ev_done = nullptr;
   cudaEvent_t ev_phase[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool phases_valid = false;
+  float phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // pruned-buffer mode: per-phase time summed over passes
   // graph
   const uint64_t* d_off = nullptr;
   const uint32_t* d_keys = nullptr;
@@ -705,9 +706,11 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   const uint64_t cap_limit = std::min<uint64_t>(budget / 24, 0xfffffff0ull);
   uint64_t want_cap = total_need;
   if (K != NLP_UNBOUNDED) {
-    // room for every candidate when that is cheap; otherwise 16 K (at least 2^27 entries = 3 GB)
+    // room for every candidate when that is cheap; otherwise 16 K, at least 2^27 entries (3 GB)
+    // and up to a quarter of the scratch budget: a source reserves its BOUND while it runs, so
+    // the buffer also limits how many hub-heavy sources can be in flight at once
     const uint64_t k16 = K > (1ull << 58) ? (1ull << 62) : 16 * K;
-    want_cap = std::min<uint64_t>(total_need, std::max<uint64_t>(k16, 1ull << 27) + S + (1ull << 20));
+    want_cap = std::min<uint64_t>(total_need, std::max<uint64_t>(std::max<uint64_t>(k16, 1ull << 27), cap_limit / 4) + S + (1ull << 20));
   }
   const uint64_t cap = std::min<uint64_t>(want_cap, cap_limit);
   const bool admit = cap < total_need;
@@ -730,11 +733,14 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   p.gtable = (const double*)h->gtable.p;
   p.work = (const uint32_t*)h->work.p;
   p.cap = cap; p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
+  p.soft_cap = cap;
+  const uint64_t pass_quota = std::max<uint64_t>(K > (1ull << 58) ? cap : 16 * K, 1ull << 22);   // writes per pass before a cut
   auto bind = [&](int b) { p.cu = (uint32_t*)h->cu[b].p; p.cv = (uint32_t*)h->cv[b].p; p.cs = (float*)h->cs[b].p; };
   bind(cur);
 
   res->passes = 1;
   h->phases_valid = false;
+  for (int i = 0; i < 8; ++i) h->phase_acc[i] = 0.f;
   if (!admit) {
     // everything fits: one pass, no admission control, no host round trip until the end
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
@@ -764,9 +770,15 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
       // reset queues / deferred counts, seed the reservation with the current fill
       NLP_CUDA(h, cudaMemsetAsync((char*)h->ctr.p + offsetof(Counters, deferred), 0, 16 * 8, h->stream));
       NLP_CUDA(h, cudaMemcpyAsync((char*)h->ctr.p + offsetof(Counters, reserved), &fill, 8, cudaMemcpyHostToDevice, h->stream));
+      p.soft_cap = std::min<uint64_t>(cap, fill + pass_quota);
+      NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
       NLP_TRY((launch_range<true>(h, p, lists[6], (uint32_t)remaining[6], defers[6])));
       NLP_TRY((launch_dense<FLT, true>(h, p, lists[5], (uint32_t)remaining[5], defers[5], dense_slots, touched_cap)));
-      for (int b = 4; b >= 2; --b) NLP_TRY((launch_hash<FLT, true>(h, p, b, lists[b], (uint32_t)remaining[b], defers[b])));
+      NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
+      for (int b = 4; b >= 2; --b) {
+        NLP_TRY((launch_hash<FLT, true>(h, p, b, lists[b], (uint32_t)remaining[b], defers[b])));
+        NLP_CUDA(h, cudaEventRecord(h->ev_phase[6 - b], h->stream));
+      }
       NLP_TRY(read_counters(h));
       fill = hc->cursor;
       uint64_t fill_ub = fill;
@@ -778,8 +790,14 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
           NLP_TRY((launch_tiny<FLT>(h, p, b, (const uint32_t*)h->list[b].p + tiny_pos[b], (uint32_t)take)));
           tiny_pos[b] += take; fill_ub += take * G;
         }
+        NLP_CUDA(h, cudaEventRecord(h->ev_phase[b ? 5 : 6], h->stream));
       }
       NLP_TRY(read_counters(h));
+      for (int i = 1; i <= 6; ++i) {   // per-phase device time, summed over the passes
+        float ms = 0.f;
+        NLP_CUDA(h, cudaEventElapsedTime(&ms, h->ev_phase[i - 1], h->ev_phase[i]));
+        h->phase_acc[i] += ms;
+      }
       fill = hc->cursor;
       bool done = tiny_pos[0] == nb[0] && tiny_pos[1] == nb[1];
       for (int b = 2; b < NBINS; ++b) { remaining[b] = hc->deferred[b]; done = done && remaining[b] == 0; std::swap(lists[b], defers[b]); }
@@ -987,6 +1005,8 @@ int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res) {
   NLP_CUDA(h, cudaEventElapsedTime(&res->phase_ms[0], h->ev_start, h->ev_frontier));
   if (h->phases_valid)
     for (int i = 1; i <= 6; ++i) NLP_CUDA(h, cudaEventElapsedTime(&res->phase_ms[i], h->ev_phase[i - 1], h->ev_phase[i]));
+  else if (res->path == NLP_PATH_SOURCE)
+    for (int i = 1; i <= 6; ++i) res->phase_ms[i] = h->phase_acc[i];
   res->phase_ms[7] = sel;
   return NLP_OK;
 }

@@ -405,13 +405,30 @@ __device__ __forceinline__ bool admit_source(const Params& p, uint32_t u, int bi
   const uint32_t w = p.work[u], room = p.g.S - 1u - u;
   const uint32_t need = w < room ? w : room;
   *need_out = need;
-  const unsigned long long r = atomicAdd(&p.ctr->reserved, (unsigned long long)need);
-  if (r + need > p.cap) {
+  for (;;) {
+    // Stop admitting once this pass has written enough: the host then cuts the buffer to the
+    // best K, which tightens the pruning threshold for everything that follows.  (The buffer
+    // itself is much larger: its size bounds the reservations of the sources in flight.)
+    if (*reinterpret_cast<volatile unsigned long long*>(&p.ctr->cursor) >= p.soft_cap) break;
+    // optimistic reservation: one atomic in the common case
+    const unsigned long long r = atomicAdd(&p.ctr->reserved, (unsigned long long)need);
+    if (r + need <= p.cap) return true;
     atomicAdd(&p.ctr->reserved, 0ull - (unsigned long long)need);
-    deferred[atomicAdd(&p.ctr->deferred[bin], 1ull)] = u;
-    return false;
+    // No room because of what is already WRITTEN -> next pass.  No room only because of the
+    // (pessimistic: bound, not count) reservations of sources still in flight -> wait for them;
+    // every in-flight source belongs to a resident block that never waits itself, so this ends.
+    // Waiting blocks only READ the counter (a transient reservation of every waiter would keep
+    // all of them out for ever) and retry when it shows room.
+    for (;;) {
+      const unsigned long long written = *reinterpret_cast<volatile unsigned long long*>(&p.ctr->cursor);
+      if (written + need > p.cap) goto defer;
+      if (*reinterpret_cast<volatile unsigned long long*>(&p.ctr->reserved) + need <= p.cap) break;
+      __nanosleep(2000);
+    }
   }
-  return true;
+defer:
+  deferred[atomicAdd(&p.ctr->deferred[bin], 1ull)] = u;
+  return false;
 }
 
 // One team (= block) per source; blockDim = 32 * team_warps (team_warps = 1 for FLT).
