@@ -207,9 +207,20 @@ def run_b200(args):
     if do_e2e:
         h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
     pred = N.Predictor(local)
-    pred.set_partition(rank, world)
+    all_measures = [m for m in args.measures.split(",") if m] if args.measures else MEASURES
+    # N > 1: the nine predictions of a step are independent units (main.cxx:212-220 runs them one
+    # after the other), so they are dealt to the ranks and no data-path collective is needed;
+    # when a step has fewer predictions than ranks (e.g. one IHub measure) the SOURCES of each
+    # prediction are partitioned instead and the local top-K lists merged with one all-gather.
+    shard = args.shard
+    if shard == "auto":
+        shard = "measures" if len(all_measures) >= world else "sources"
+    if world == 1:
+        shard = "none"
+    if shard == "sources":
+        pred.set_partition(rank, world)
     stream = torch.cuda.ExternalStream(pred.lib.nlp_stream(pred.h), device=dev)
-    measures = [m for m in args.measures.split(",") if m] if args.measures else MEASURES
+    measures = all_measures[rank::world] if shard == "measures" else all_measures
     D = args.degree
     if do_e2e:
         h_out = [torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()]
@@ -223,7 +234,7 @@ def run_b200(args):
     def one_step(collect=None):
         edges = 0
         for m in measures:
-            if world > 1:
+            if shard == "sources":
                 r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
             else:
                 r = pred.predict(m, D, max_edges=K); n = r["count"]
@@ -236,7 +247,7 @@ def run_b200(args):
         pred.set_graph_pointers(h_off.data_ptr(), h_keys.data_ptr(), S, device=False, keep=(h_off, h_keys))
         edges = 0
         for m in measures:
-            if world > 1:
+            if shard == "sources":
                 r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
             else:
                 r = pred.predict(m, D, max_edges=K); n = r["count"]
@@ -261,6 +272,10 @@ def run_b200(args):
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
+            if shard == "measures":          # every rank predicted different measures: whole-job edge count
+                e = torch.tensor([edges], device=dev, dtype=torch.int64)
+                dist.all_reduce(e, op=dist.ReduceOp.SUM)
+                edges = int(e[0])
         return edges, ms, wall, results
 
     # ---- value: graph resident in HBM ---------------------------------------------------------
@@ -374,8 +389,10 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32 counts, f32 scores (f64 terms for AA/RA/Salton)", "data": "synthetic",
-        "config": dict(info, min_degree1=D, measures=measures, l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6),
-                       parallelism="sources partitioned over %d GPU(s), CSR replicated" % world),
+        "config": dict(info, min_degree1=D, l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6),
+                       measures=all_measures,
+                       parallelism={"none": "1 GPU", "measures": "the %d predictions of a step dealt to %d GPUs (independent units, no collective), CSR replicated" % (len(all_measures), world),
+                                    "sources": "sources of every prediction partitioned over %d GPUs, CSR replicated, one all-gather + on-device merge" % world}[shard]),
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
@@ -403,6 +420,8 @@ def main():
     ap.add_argument("--workload", default="rmat22", choices=sorted(WORKLOADS))
     ap.add_argument("--degree", type=int, default=16, help="MINDEGREE1 of the LHub runs (0 = IHub)")
     ap.add_argument("--measures", default="", help="comma list (default: all nine)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "measures", "sources"],
+                    help="N > 1: deal the predictions of a step to the ranks, or partition the sources of each prediction")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run on the host cores")
     args = ap.parse_args()

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,9 @@ struct nlp_handle {
   // pair path (LHub on symmetric graphs)
   DevBuf it_u, it_cnt, it_dw, it_ptr, it_off, sym_flag;
   int sym_state = 0;                         // 0 unknown, 1 symmetric rows, 2 not symmetric
+  // item / record counts of the pair path per (D, rank, world): a pure function of the resident
+  // graph, so only the first prediction at a threshold pays the two host round trips for them
+  std::map<uint64_t, std::pair<uint64_t, uint64_t>> pair_sizes;
   int path_mode = NLP_PATH_AUTO;
   int coop_mode = 1;                         // 0: per-warp wedge streaming in k_hash / k_dense (count measures)
   int cluster_mode = 0;                      // 0: single-CTA k_range only (default: remote shared-memory atomics
@@ -163,7 +167,7 @@ DevGraph dev_graph(const nlp_handle* h) {
 // out[i] = sum of in[0..i); returns the grand total in *total (host).  in/out may alias for u64.
 template <class TIn>
 int exclusive_scan(nlp_handle* h, const TIn* in, uint64_t n, unsigned long long* out, uint64_t* total) {
-  *total = 0;
+  if (total) *total = 0;
   if (!n) return NLP_OK;
   const uint32_t ntiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
   NLP_TRY(ensure(h, h->scan_tiles, (size_t)ntiles * 8));
@@ -175,6 +179,7 @@ int exclusive_scan(nlp_handle* h, const TIn* in, uint64_t n, unsigned long long*
   NLP_LAUNCHED(h);
   k_scan_apply<TIn><<<ntiles, SCAN_THREADS, 0, h->stream>>>(in, n, (const unsigned long long*)h->scan_tiles.p, out);
   NLP_LAUNCHED(h);
+  if (!total) return NLP_OK;                 // the caller knows the total already: no host round trip
   unsigned long long t = 0;
   NLP_CUDA(h, cudaMemcpyAsync(&t, h->scan_total.p, 8, cudaMemcpyDeviceToHost, h->stream));
   NLP_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -223,6 +228,7 @@ int finish_graph(nlp_handle* h) {
   h->maxdeg = md;
   h->gtable_n = 0;
   h->sym_state = 0;
+  h->pair_sizes.clear();
   NLP_TRY(measure_budget(h));
   h->has_graph = true;
   h->has_result = false;
@@ -318,16 +324,19 @@ int top_k(nlp_handle* h, int buf, uint64_t n, uint64_t K, int* out_buf, uint64_t
     const uint64_t slack = std::max<uint64_t>(K / 8, 65536);
     uint64_t above = 0, bucket = n;
     uint32_t bits = 0;
-    while (bits < 96 && above + bucket > K + slack) {
-      k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
-          (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, n,
-          (SelectState*)h->sel.p);
-      NLP_LAUNCHED(h);
-      k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K);
-      NLP_LAUNCHED(h);
+    bool done = false;
+    while (!done) {
+      for (int lvl = 0; lvl < 4; ++lvl) {        // four levels queued back to back, one read of the state
+        k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
+            (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, n,
+            (SelectState*)h->sel.p);
+        NLP_LAUNCHED(h);
+        k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K, (unsigned long long)slack, 96u);
+        NLP_LAUNCHED(h);
+      }
       NLP_CUDA(h, cudaMemcpyAsync(h->h_sel, h->sel.p, offsetof(SelectState, hist), cudaMemcpyDeviceToHost, h->stream));
       NLP_CUDA(h, cudaStreamSynchronize(h->stream));
-      above = h->h_sel->above; bucket = h->h_sel->bucket; bits = h->h_sel->bits;
+      above = h->h_sel->above; bucket = h->h_sel->bucket; bits = h->h_sel->bits; done = h->h_sel->done != 0;
     }
     if (bits > 0 && above + bucket < n) {
       const int o = buf ^ 1;
@@ -358,18 +367,15 @@ int top_k_ordered(nlp_handle* h, int sb, uint64_t n, uint64_t kept, uint64_t K, 
   if (K < kept) {
     NLP_CUDA(h, cudaMemsetAsync(h->sel.p, 0, sizeof(SelectState), h->stream));
     const uint64_t slack = std::max<uint64_t>(K / 8, 65536);
-    uint64_t above = 0, bucket = n;
     uint32_t bits = 0;
-    while (bits < 32 && above + bucket > K + slack) {
+    for (int lvl = 0; lvl < 4; ++lvl) {            // at most 32 score bits: all levels queued, one read
       k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
           (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, sbits, n, (SelectState*)h->sel.p);
       NLP_LAUNCHED(h);
-      k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K);
+      k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K, (unsigned long long)slack, 32u);
       NLP_LAUNCHED(h);
-      NLP_CUDA(h, cudaMemcpyAsync(h->h_sel, h->sel.p, offsetof(SelectState, hist), cudaMemcpyDeviceToHost, h->stream));
-      NLP_CUDA(h, cudaStreamSynchronize(h->stream));
-      above = h->h_sel->above; bucket = h->h_sel->bucket; bits = h->h_sel->bits;
     }
+    bits = 8;   // K < kept <= n: at least one level ran; k_ordered_* read the exact state on the device
     mode = bits > 0 ? 1 : 0;
   }
   const uint32_t ntiles = (uint32_t)((n + OC_TILE - 1) / OC_TILE);
@@ -553,7 +559,11 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
                                                                         (uint32_t*)h->work.p, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   uint64_t E = 0, P = 0;
-  NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->work.p, S, (unsigned long long*)h->work64.p, &E));
+  const uint64_t size_key = ((uint64_t)opt->min_degree1 << 32) | ((uint64_t)h->rank << 16) | (uint64_t)h->world;
+  const auto known = h->pair_sizes.find(size_key);
+  const bool cached = known != h->pair_sizes.end();
+  if (cached) { E = known->second.first; P = known->second.second; }
+  NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->work.p, S, (unsigned long long*)h->work64.p, cached ? nullptr : &E));
   PairItems it{nullptr, nullptr, nullptr, nullptr};
   uint64_t budget = 0;
   NLP_TRY(scratch_budget(h, &budget));
@@ -569,8 +579,9 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
     k_pair_items<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(
         g, (const uint32_t*)h->work.p, (const unsigned long long*)h->work64.p, h->rank, h->world, it, (Counters*)h->ctr.p);
     NLP_LAUNCHED(h);
-    NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->it_cnt.p, E, (unsigned long long*)h->it_off.p, &P));
+    NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->it_cnt.p, E, (unsigned long long*)h->it_off.p, cached ? nullptr : &P));
   }
+  if (!cached) h->pair_sizes[size_key] = std::make_pair(E, P);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
   NLP_TRY(scratch_budget(h, &budget));

@@ -249,6 +249,8 @@ struct SelectState {
   uint32_t bits;                      // resolved leading bits (multiple of 8)
   unsigned long long above;           // items strictly before the undecided bucket
   unsigned long long bucket;          // items in the undecided bucket
+  uint32_t done;                      // narrowing finished: later hist/step launches are no-ops
+  uint32_t pad;
   unsigned long long hist[256];
 };
 
@@ -272,6 +274,7 @@ __device__ __forceinline__ uint32_t select_digit(uint32_t bits, uint32_t w2, uin
 __global__ void __launch_bounds__(256) k_select_hist(const uint32_t* __restrict__ cu, const uint32_t* __restrict__ cv,
                                                      const uint32_t* __restrict__ cs, uint64_t n, SelectState* st) {
   __shared__ uint32_t sh[256];
+  if (st->done) return;
   sh[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t bits = st->bits;
@@ -287,7 +290,10 @@ __global__ void __launch_bounds__(256) k_select_hist(const uint32_t* __restrict_
 }
 
 // Single thread: pick the digit bucket that holds the K-th item, extend the prefix by 8 bits.
-__global__ void k_select_step(SelectState* st, unsigned long long K) {
+// The narrowing is finished (st->done) once the survivors (above + bucket) fit K + slack or
+// max_bits are resolved; the host queues several levels back to back and reads the state once.
+__global__ void k_select_step(SelectState* st, unsigned long long K, unsigned long long slack, uint32_t max_bits) {
+  if (st->done) return;
   unsigned long long above = st->above;
   int d = 0;
   for (; d < 255; ++d) {
@@ -302,6 +308,7 @@ __global__ void k_select_step(SelectState* st, unsigned long long K) {
   st->above = above;
   st->bucket = st->hist[d];
   st->bits = bits + 8;
+  if (above + st->hist[d] <= K + slack || bits + 8 >= max_bits) st->done = 1;
   for (int i = 0; i < 256; ++i) st->hist[i] = 0;
 }
 
