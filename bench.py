@@ -222,8 +222,9 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(pred.lib.nlp_stream(pred.h), device=dev)
     measures = all_measures[rank::world] if shard == "measures" else all_measures
     D = args.degree
-    if do_e2e:
-        h_out = [torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()]
+    if do_e2e:   # two sets of pinned result buffers: transfers are double buffered (nlp_fetch_async)
+        h_out = [[torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()]
+                 for _ in range(2)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,13 +247,18 @@ def run_b200(args):
     def one_step_e2e():
         pred.set_graph_pointers(h_off.data_ptr(), h_keys.data_ptr(), S, device=False, keep=(h_off, h_keys))
         edges = 0
-        for m in measures:
+        for i, m in enumerate(measures):
             if shard == "sources":
                 r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
             else:
                 r = pred.predict(m, D, max_edges=K); n = r["count"]
-            pred.fetch_into(h_out[0].data_ptr(), h_out[1].data_ptr(), h_out[2].data_ptr(), n)
+            if shard == "sources":
+                pred.fetch_into(h_out[0][0].data_ptr(), h_out[0][1].data_ptr(), h_out[0][2].data_ptr(), n)
+            else:    # the device -> host transfer of this result overlaps the next prediction
+                o = h_out[i % 2]
+                pred.fetch_async(o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n)
             edges += n
+        pred.fetch_wait()
         return edges
 
     def timed(fn, steps, collect=False):

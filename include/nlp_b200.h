@@ -146,6 +146,14 @@ int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res);
  * Copies min(capacity, count) edges.                                                           */
 int nlp_fetch(nlp_handle* h, uint32_t* u, uint32_t* v, float* score, uint64_t capacity);
 
+/* Same, without blocking: the result is first copied to a staging buffer on the GPU (so the next
+ * nlp_predict may start at once), then transferred to the caller's arrays on a second stream.
+ * The arrays (pinned host memory for a truly asynchronous transfer) must stay untouched until
+ * nlp_fetch_wait() returns.  At most two transfers are in flight; a third call waits for the
+ * oldest.  Use: predict, fetch_async, predict, fetch_async, ..., fetch_wait.                    */
+int nlp_fetch_async(nlp_handle* h, uint32_t* u, uint32_t* v, float* score, uint64_t capacity);
+int nlp_fetch_wait(nlp_handle* h);
+
 /* Device pointers of the last result (count elements each), for on-device consumers and for
  * the multi-GPU all-gather.                                                                    */
 int nlp_result_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d_v,

@@ -16,7 +16,7 @@ STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH
           4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT"}
 
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
-           "nlp_set_scratch_limit", "nlp_set_path", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
+           "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
            "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
@@ -71,6 +71,8 @@ def load_library(build_if_missing=True):
     lib.nlp_set_path.argtypes = [vp, C.c_int]
     lib.nlp_predict.argtypes = [vp, C.POINTER(Options), C.POINTER(Result)]
     lib.nlp_fetch.argtypes = [vp, vp, vp, vp, u64]
+    lib.nlp_fetch_async.argtypes = [vp, vp, vp, vp, u64]
+    lib.nlp_fetch_wait.argtypes = [vp]
     lib.nlp_result_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     lib.nlp_merge.argtypes = [vp, vp, vp, vp, u64, u64, C.POINTER(C.c_float)]
     lib.nlp_launch_count.argtypes = [vp]
@@ -141,6 +143,13 @@ class Predictor:
     def fetch_into(self, u_ptr, v_ptr, s_ptr, capacity):
         """Copy the result into caller memory (host or device pointers)."""
         self._check(self.lib.nlp_fetch(self.h, u_ptr, v_ptr, s_ptr, capacity))
+
+    def fetch_async(self, u_ptr, v_ptr, s_ptr, capacity):
+        """Non-blocking fetch (see nlp_fetch_async); finish with fetch_wait()."""
+        self._check(self.lib.nlp_fetch_async(self.h, u_ptr, v_ptr, s_ptr, capacity))
+
+    def fetch_wait(self):
+        self._check(self.lib.nlp_fetch_wait(self.h))
 
     def result_device(self):
         pu, pv, ps, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()

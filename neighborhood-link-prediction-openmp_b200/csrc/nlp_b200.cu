@@ -84,6 +84,13 @@ struct nlp_handle {
   bool pair_pending = false;
   int pair_sorted = 0;
   uint64_t pair_n = 0, pair_kept = 0;
+  // asynchronous fetch: result -> staging (device copy on the compute stream) -> caller memory
+  // (copy stream), double buffered, so the next prediction overlaps the transfer
+  cudaStream_t copy_stream = nullptr;
+  DevBuf stg_u[2], stg_v[2], stg_s[2];
+  cudaEvent_t ev_stg_ready[2] = {nullptr, nullptr}, ev_stg_done[2] = {nullptr, nullptr};
+  bool stg_busy[2] = {false, false};
+  int stg_next = 0;
   // result
   int res_buf = 0;
   uint64_t res_count = 0;
@@ -876,6 +883,11 @@ int nlp_create(nlp_handle** out, int device) {
   }
   h->num_sms = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_stg_ready[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_stg_done[i], cudaEventDisableTiming);
+  }
   cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_frontier); cudaEventCreate(&h->ev_scored); cudaEventCreate(&h->ev_done);
   for (int i = 0; i < 7; ++i) cudaEventCreate(&h->ev_phase[i]);
   if ((e = cudaMallocHost((void**)&h->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -900,6 +912,12 @@ int nlp_destroy(nlp_handle* h) {
   if (!h) return NLP_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (int i = 0; i < 2; ++i) {
+    release(h->stg_u[i]); release(h->stg_v[i]); release(h->stg_s[i]);
+    if (h->ev_stg_ready[i]) cudaEventDestroy(h->ev_stg_ready[i]);
+    if (h->ev_stg_done[i]) cudaEventDestroy(h->ev_stg_done[i]);
+  }
   release(h->own_off); release(h->own_keys); release(h->deg); release(h->work); release(h->work64); release(h->elig); release(h->maxdeg_dev);
   release(h->chunk_base); release(h->chunk_src); release(h->chunk_cnt); release(h->ecount); release(h->ekeys);
   release(h->scan_tiles); release(h->scan_total);
@@ -1034,6 +1052,41 @@ int nlp_fetch(nlp_handle* h, uint32_t* u, uint32_t* v, float* score, uint64_t ca
   NLP_CUDA(h, cudaMemcpyAsync(v, h->cv[b].p, n * 4, cudaMemcpyDefault, h->stream));
   NLP_CUDA(h, cudaMemcpyAsync(score, h->cs[b].p, n * 4, cudaMemcpyDefault, h->stream));
   NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLP_OK;
+}
+
+int nlp_fetch_async(nlp_handle* h, uint32_t* u, uint32_t* v, float* score, uint64_t capacity) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_result) return fail(h, NLP_ERR_NO_RESULT, "nlp_fetch_async: no result");
+  const uint64_t n = std::min<uint64_t>(capacity, h->res_count);
+  if (!n) return NLP_OK;
+  if (!u || !v || !score) return fail(h, NLP_ERR_ARG, "nlp_fetch_async: null output");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  const int s = h->stg_next;
+  h->stg_next ^= 1;
+  if (h->stg_busy[s]) NLP_CUDA(h, cudaEventSynchronize(h->ev_stg_done[s]));   // slot still feeding an older transfer
+  NLP_TRY(ensure(h, h->stg_u[s], n * 4));
+  NLP_TRY(ensure(h, h->stg_v[s], n * 4));
+  NLP_TRY(ensure(h, h->stg_s[s], n * 4));
+  const int b = h->res_buf;
+  NLP_CUDA(h, cudaMemcpyAsync(h->stg_u[s].p, h->cu[b].p, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(h->stg_v[s].p, h->cv[b].p, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(h->stg_s[s].p, h->cs[b].p, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+  NLP_CUDA(h, cudaEventRecord(h->ev_stg_ready[s], h->stream));
+  NLP_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_stg_ready[s], 0));
+  NLP_CUDA(h, cudaMemcpyAsync(u, h->stg_u[s].p, n * 4, cudaMemcpyDefault, h->copy_stream));
+  NLP_CUDA(h, cudaMemcpyAsync(v, h->stg_v[s].p, n * 4, cudaMemcpyDefault, h->copy_stream));
+  NLP_CUDA(h, cudaMemcpyAsync(score, h->stg_s[s].p, n * 4, cudaMemcpyDefault, h->copy_stream));
+  NLP_CUDA(h, cudaEventRecord(h->ev_stg_done[s], h->copy_stream));
+  h->stg_busy[s] = true;
+  return NLP_OK;
+}
+
+int nlp_fetch_wait(nlp_handle* h) {
+  if (!h) return NLP_ERR_ARG;
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  NLP_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  h->stg_busy[0] = h->stg_busy[1] = false;
   return NLP_OK;
 }
 

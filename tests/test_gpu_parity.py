@@ -173,3 +173,27 @@ def test_properties_at_scale(pred, nlp):
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_fetch_async_double_buffered(pred, nlp):
+    """nlp_fetch_async: results staged on the GPU and transferred on a second stream while the
+    next predictions run; three transfers in a row (more than the two staging slots)."""
+    import torch
+    off, keys = _graph(nlp, "rmat12")
+    pred.set_graph(off, keys)
+    cases = [("JC", 4, 4000), ("AA", 0, 3000), ("CN", 16, 5000)]
+    want, bufs = [], []
+    for m, D, K in cases:
+        r = pred.predict(m, D, max_edges=K)
+        want.append(pred.fetch(r["count"]))
+    for m, D, K in cases:
+        r = pred.predict(m, D, max_edges=K)
+        n = r["count"]
+        b = (torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(),
+             torch.empty(n, dtype=torch.float32).pin_memory())
+        pred.fetch_async(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), n)
+        bufs.append(b)
+    pred.fetch_wait()
+    for (m, D, K), w, b in zip(cases, want, bufs):
+        got = (b[0].numpy().view(np.uint32), b[1].numpy().view(np.uint32), b[2].numpy())
+        assert parity.compare(got, w, "fetch_async %s D=%d" % (m, D)) is None
