@@ -26,14 +26,22 @@ namespace nlp {
 // asym != 0 afterwards <=> some entry (u, w) has a different multiplicity than (w, u).
 __global__ void __launch_bounds__(256) k_symmetry(DevGraph g, uint64_t M, unsigned int* __restrict__ asym) {
   const uint32_t* __restrict__ keys = g.keys;
-  for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < M; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t w = __ldg(keys + e);
-    uint32_t lo = 0, hi = g.S;                       // off[lo] <= e < off[hi]
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t base = warp0 * 32u; base < M; base += nwarps * 32u) {
+    // row of the warp's first entry by bisection (same loads in every lane: broadcast), then
+    // every lane walks forward to its own row -- 32 consecutive entries span few rows
+    uint32_t lo = 0, hi = g.S;                       // off[lo] <= base < off[hi]
     while (lo + 1 < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (__ldg(g.off + mid) <= e) lo = mid; else hi = mid;
+      if (__ldg(g.off + mid) <= base) lo = mid; else hi = mid;
     }
-    const uint32_t u = lo;
+    const uint64_t e = base + lane;
+    if (e >= M) continue;
+    uint32_t u = lo;
+    while (__ldg(g.off + u + 1) <= e) ++u;
+    const uint32_t w = __ldg(keys + e);
     const uint64_t ub = __ldg(g.off + u), ue = __ldg(g.off + u + 1);
     if (e > ub && __ldg(keys + e - 1) == w) continue;          // counted at the first entry of the run
     uint32_t mult = 1;
