@@ -130,6 +130,15 @@ int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_
  * split of inc/predict.hxx:287.                                                                */
 int nlp_set_partition(nlp_handle* h, int rank, int world);
 
+/* Reuse across predictions on the same graph ("sweep fusion"; default off).
+ * The nine measures share their common-neighbour counts, and main.cxx:212-220 asks for all of
+ * them at the same thresholds: with reuse on, the pair path keeps the sorted wedge records of a
+ * threshold (per D and partition, least-recently-used thresholds dropped beyond a quarter of the
+ * scratch budget), and a later prediction at that threshold only runs the reduce / score / select
+ * kernels.  Results are identical.  Every call (on or off) empties the store; nlp_set_graph* does
+ * too.  Note that `repeat` > 1 then times one cold and repeat-1 warm scoring passes.             */
+int nlp_set_reuse(nlp_handle* h, int on);
+
 /* Force a scoring path (testing / measurement); default NLP_PATH_AUTO. */
 int nlp_set_path(nlp_handle* h, int path);
 

@@ -16,7 +16,7 @@ STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH
           4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT"}
 
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
-           "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
+           "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_set_reuse", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
            "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
@@ -69,6 +69,7 @@ def load_library(build_if_missing=True):
     lib.nlp_set_partition.argtypes = [vp, C.c_int, C.c_int]
     lib.nlp_set_scratch_limit.argtypes = [vp, u64]
     lib.nlp_set_path.argtypes = [vp, C.c_int]
+    lib.nlp_set_reuse.argtypes = [vp, C.c_int]
     lib.nlp_predict.argtypes = [vp, C.POINTER(Options), C.POINTER(Result)]
     lib.nlp_fetch.argtypes = [vp, vp, vp, vp, u64]
     lib.nlp_fetch_async.argtypes = [vp, vp, vp, vp, u64]
@@ -122,6 +123,10 @@ class Predictor:
     def set_path(self, path):
         """0 = auto, 1 = source-centric kernels, 2 = LHub pair path (when admissible)."""
         self._check(self.lib.nlp_set_path(self.h, path))
+
+    def set_reuse(self, on):
+        """Keep sorted wedge records per threshold for later measures (empties the store)."""
+        self._check(self.lib.nlp_set_reuse(self.h, 1 if on else 0))
 
     def set_scratch_limit(self, nbytes):
         self._check(self.lib.nlp_set_scratch_limit(self.h, nbytes))

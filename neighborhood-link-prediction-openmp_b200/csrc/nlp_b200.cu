@@ -80,10 +80,19 @@ struct nlp_handle {
   // select / sort scratch
   DevBuf counts, totals, hist, sel, cursor2;
   DevBuf oc_counts, oc_off;                  // ordered compaction (pair path top-K)
-  // pair path: records sorted by (u, v) in buffer pair_sorted, aligned scores in cs[pair_sorted ^ 1]
+  // pair path: records sorted by (u, v) at (pair_pu, pair_pv), aligned scores in cs[pair_score_buf]
   bool pair_pending = false;
-  int pair_sorted = 0;
+  const uint32_t* pair_pu = nullptr;
+  const uint32_t* pair_pv = nullptr;
+  int pair_score_buf = 0;
+  bool pair_from_cache = false;
   uint64_t pair_n = 0, pair_kept = 0;
+  // nlp_set_reuse: sorted wedge records kept per (D, rank, world) so that further measures at the
+  // same threshold only reduce + score + select (the nine measures share their counts)
+  struct PairCache { DevBuf u, v, w; uint64_t P = 0, first_hop = 0, elig = 0, wedges = 0, stamp = 0; };
+  std::map<uint64_t, PairCache> pair_cache;
+  int reuse = 0;
+  uint64_t cache_bytes = 0, cache_stamp = 0;
   // asynchronous fetch: result -> staging (device copy on the compute stream) -> caller memory
   // (copy stream), double buffered, so the next prediction overlaps the transfer
   cudaStream_t copy_stream = nullptr;
@@ -196,6 +205,12 @@ int exclusive_scan(nlp_handle* h, const TIn* in, uint64_t n, unsigned long long*
 
 int measure_budget(nlp_handle* h);
 
+void clear_pair_cache(nlp_handle* h) {
+  for (auto& kv : h->pair_cache) { release(kv.second.u); release(kv.second.v); release(kv.second.w); }
+  h->pair_cache.clear();
+  h->cache_bytes = 0;
+}
+
 int finish_graph(nlp_handle* h) {
   const uint32_t S = h->S;
   NLP_TRY(ensure(h, h->deg, (size_t)S * 4));
@@ -236,6 +251,7 @@ int finish_graph(nlp_handle* h) {
   h->gtable_n = 0;
   h->sym_state = 0;
   h->pair_sizes.clear();
+  clear_pair_cache(h);
   NLP_TRY(measure_budget(h));
   h->has_graph = true;
   h->has_result = false;
@@ -365,25 +381,25 @@ int top_k(nlp_handle* h, int buf, uint64_t n, uint64_t K, int* out_buf, uint64_t
 // Pair path: the records in buffer `sb` are sorted by (u, v), cs[sb ^ 1] holds the aligned score
 // bits (NLP_NO_SCORE = nothing).  Select on the score alone, copy the survivors out in order,
 // stable-sort them by score: ties stay in ascending (u, v) order = canonical order.
-int top_k_ordered(nlp_handle* h, int sb, uint64_t n, uint64_t kept, uint64_t K, int* out_buf, uint64_t* out_n) {
-  const int cur = sb ^ 1;
-  *out_buf = cur; *out_n = 0;
+int top_k_ordered(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
+  const uint32_t* pu = h->pair_pu;
+  const uint32_t* pv = h->pair_pv;
+  const uint64_t n = h->pair_n, kept = h->pair_kept;
+  const int sbuf = h->pair_score_buf, ob = sbuf ^ 1;
+  *out_buf = ob; *out_n = 0;
   if (!n || !kept) return NLP_OK;
-  const uint32_t* sbits = (const uint32_t*)h->cs[cur].p;
+  const uint32_t* sbits = (const uint32_t*)h->cs[sbuf].p;
   int mode = 0;
   if (K < kept) {
     NLP_CUDA(h, cudaMemsetAsync(h->sel.p, 0, sizeof(SelectState), h->stream));
     const uint64_t slack = std::max<uint64_t>(K / 8, 65536);
-    uint32_t bits = 0;
-    for (int lvl = 0; lvl < 4; ++lvl) {            // at most 32 score bits: all levels queued, one read
-      k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
-          (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, sbits, n, (SelectState*)h->sel.p);
+    for (int lvl = 0; lvl < 4; ++lvl) {            // at most 32 score bits: all levels queued, the state stays on the device
+      k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(pu, pv, sbits, n, (SelectState*)h->sel.p);
       NLP_LAUNCHED(h);
       k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K, (unsigned long long)slack, 32u);
       NLP_LAUNCHED(h);
     }
-    bits = 8;   // K < kept <= n: at least one level ran; k_ordered_* read the exact state on the device
-    mode = bits > 0 ? 1 : 0;
+    mode = 1;   // K < kept <= n: at least one level ran; k_ordered_* read the exact state on the device
   }
   const uint32_t ntiles = (uint32_t)((n + OC_TILE - 1) / OC_TILE);
   NLP_TRY(ensure(h, h->oc_counts, (size_t)ntiles * 4));
@@ -392,13 +408,17 @@ int top_k_ordered(nlp_handle* h, int sb, uint64_t n, uint64_t kept, uint64_t K, 
   NLP_LAUNCHED(h);
   uint64_t m = 0;
   NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &m));
-  // survivors go to (cu[cur], cv[cur], cs[sb]); swapping the two score arrays makes that buffer `cur`
-  k_ordered_write<<<ntiles, OC_THREADS, 0, h->stream>>>(
-      (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, sbits, n, (const SelectState*)h->sel.p, mode,
-      (const unsigned long long*)h->oc_off.p, (uint32_t*)h->cu[cur].p, (uint32_t*)h->cv[cur].p, (uint32_t*)h->cs[sb].p);
+  // Survivors go to buffer `ob`.  When the records live in candidate buffer `ob` themselves (no
+  // cache), its u/v arrays are still being read: write to (cu[sbuf], cv[sbuf], cs[ob]) instead and
+  // swap the two score arrays afterwards, which makes that triple buffer `sbuf`.
+  int res = ob;
+  uint32_t *ou = (uint32_t*)h->cu[ob].p, *ov = (uint32_t*)h->cv[ob].p, *os = (uint32_t*)h->cs[ob].p;
+  if (!h->pair_from_cache) { ou = (uint32_t*)h->cu[sbuf].p; ov = (uint32_t*)h->cv[sbuf].p; res = sbuf; }
+  k_ordered_write<<<ntiles, OC_THREADS, 0, h->stream>>>(pu, pv, sbits, n, (const SelectState*)h->sel.p, mode,
+                                                        (const unsigned long long*)h->oc_off.p, ou, ov, os);
   NLP_LAUNCHED(h);
-  std::swap(h->cs[0], h->cs[1]);
-  NLP_TRY(radix_sort(h, cur, m, out_buf, 8));      // score digits only
+  if (!h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
+  NLP_TRY(radix_sort(h, res, m, out_buf, 8));      // score digits only
   *out_n = std::min(m, K);
   return NLP_OK;
 }
@@ -562,11 +582,47 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   Counters* hc = h->h_ctr;
   NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
   NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
+  const uint64_t size_key = ((uint64_t)opt->min_degree1 << 32) | ((uint64_t)h->rank << 16) | (uint64_t)h->world;
+  Params p;
+  memset(&p, 0, sizeof p);
+  p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
+  p.gtable = (const double*)h->gtable.p;
+  p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
+  h->phases_valid = false;
+
+  // ---- sorted records of this threshold already resident (nlp_set_reuse)? -----------------------
+  if (h->reuse) {
+    auto hit = h->pair_cache.find(size_key);
+    if (hit != h->pair_cache.end()) {
+      nlp_handle::PairCache& c = hit->second;
+      c.stamp = ++h->cache_stamp;
+      const uint64_t P = c.P;
+      NLP_TRY(ensure_candidates(h, P));
+      for (int i = 0; i < 3; ++i) NLP_CUDA(h, cudaEventRecord(i == 0 ? h->ev_frontier : h->ev_phase[i - 1], h->stream));
+      NLP_CUDA(h, cudaEventRecord(h->ev_phase[2], h->stream));
+      if (P) {
+        p.cap = h->cand_cap;
+        k_pair_reduce<FLT><<<grid_for(P, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+            p, (const uint32_t*)c.u.p, (const uint32_t*)c.v.p, (const uint32_t*)c.w.p, P, (uint32_t*)h->cs[0].p);
+        NLP_LAUNCHED(h);
+      }
+      for (int i = 3; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
+      h->phases_valid = true;
+      NLP_TRY(read_counters(h));
+      res->first_hop = c.first_hop; res->eligible_first_hop = c.elig; res->wedges = c.wedges;
+      res->candidates = hc->candidates; res->kept = hc->kept; res->emitted = hc->kept;
+      res->passes = 1; res->path = NLP_PATH_PAIR; res->pair_records = P;
+      h->pair_pending = true; h->pair_from_cache = true; h->pair_n = P; h->pair_kept = hc->kept;
+      h->pair_pu = (const uint32_t*)c.u.p; h->pair_pv = (const uint32_t*)c.v.p; h->pair_score_buf = 0;
+      *out_buf = 1; *out_fill = hc->kept; *used = true;
+      return NLP_OK;
+    }
+  }
+
   k_pair_rows<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, opt->min_degree1, h->rank, h->world,
                                                                         (uint32_t*)h->work.p, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   uint64_t E = 0, P = 0;
-  const uint64_t size_key = ((uint64_t)opt->min_degree1 << 32) | ((uint64_t)h->rank << 16) | (uint64_t)h->world;
   const auto known = h->pair_sizes.find(size_key);
   const bool cached = known != h->pair_sizes.end();
   if (cached) { E = known->second.first; P = known->second.second; }
@@ -594,26 +650,25 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   NLP_TRY(scratch_budget(h, &budget));
   if (P >= 0xfffffff0ull || (P + 1024) * 24 > budget) return NLP_OK;
   NLP_TRY(ensure_candidates(h, P));
-  int cur = 0;
-  h->phases_valid = false;
+  p.cap = h->cand_cap;
+  // with reuse on, the records always carry deg(w) so that they serve the float measures too
+  const bool payload = FLT || h->reuse;
+  int cur = 0, sb = 0;
   if (P) {
-    k_pair_emit<FLT><<<grid_for(E, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-        g.keys, E, it, (const unsigned long long*)h->it_off.p, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+    if (payload)
+      k_pair_emit<true><<<grid_for(E, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+          g.keys, E, it, (const unsigned long long*)h->it_off.p, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+    else
+      k_pair_emit<false><<<grid_for(E, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+          g.keys, E, it, (const unsigned long long*)h->it_off.p, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
     NLP_LAUNCHED(h);
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
-    int sb = 0;
-    NLP_TRY(radix_sort_pairs(h, 0, P, FLT, &sb));
+    NLP_TRY(radix_sort_pairs(h, 0, P, payload, &sb));
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[2], h->stream));
     cur = sb ^ 1;
-    Params p;
-    memset(&p, 0, sizeof p);
-    p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
-    p.gtable = (const double*)h->gtable.p;
-    p.cap = h->cand_cap; p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
     k_pair_reduce<FLT><<<grid_for(P, 256, h->num_sms * 16), 256, 0, h->stream>>>(
         p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, P, (uint32_t*)h->cs[cur].p);
     NLP_LAUNCHED(h);
-    h->pair_sorted = sb;
     for (int i = 3; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
     h->phases_valid = true;
   }
@@ -628,8 +683,30 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   res->passes = 1;
   res->path = NLP_PATH_PAIR;
   res->pair_records = P;
-  h->pair_pending = true; h->pair_n = P; h->pair_kept = hc->kept;
-  if (!P) h->pair_sorted = 0;
+  h->pair_pending = true; h->pair_from_cache = false; h->pair_n = P; h->pair_kept = hc->kept;
+  h->pair_pu = (const uint32_t*)h->cu[sb].p; h->pair_pv = (const uint32_t*)h->cv[sb].p; h->pair_score_buf = cur;
+  if (h->reuse && P) {
+    // keep a copy of the sorted records (after the reduce kernel is queued: same stream, so the
+    // copy simply follows it); evict least-recently-used thresholds beyond a quarter of the budget
+    const uint64_t bytes = P * 12;
+    const uint64_t limit = budget / 4;
+    while (h->cache_bytes + bytes > limit && !h->pair_cache.empty()) {
+      auto lru = h->pair_cache.begin();
+      for (auto i = h->pair_cache.begin(); i != h->pair_cache.end(); ++i) if (i->second.stamp < lru->second.stamp) lru = i;
+      h->cache_bytes -= lru->second.P * 12;
+      release(lru->second.u); release(lru->second.v); release(lru->second.w);
+      h->pair_cache.erase(lru);
+    }
+    if (h->cache_bytes + bytes <= limit) {
+      nlp_handle::PairCache& c = h->pair_cache[size_key];
+      NLP_TRY(ensure(h, c.u, P * 4)); NLP_TRY(ensure(h, c.v, P * 4)); NLP_TRY(ensure(h, c.w, P * 4));
+      NLP_CUDA(h, cudaMemcpyAsync(c.u.p, h->cu[sb].p, P * 4, cudaMemcpyDeviceToDevice, h->stream));
+      NLP_CUDA(h, cudaMemcpyAsync(c.v.p, h->cv[sb].p, P * 4, cudaMemcpyDeviceToDevice, h->stream));
+      NLP_CUDA(h, cudaMemcpyAsync(c.w.p, h->cs[sb].p, P * 4, cudaMemcpyDeviceToDevice, h->stream));
+      c.P = P; c.first_hop = hc->first_hop; c.elig = hc->eligible_first_hop; c.wedges = hc->wedges; c.stamp = ++h->cache_stamp;
+      h->cache_bytes += bytes;
+    }
+  }
   *out_buf = cur;
   *out_fill = hc->kept;
   *used = true;
@@ -912,6 +989,7 @@ int nlp_destroy(nlp_handle* h) {
   if (!h) return NLP_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  clear_pair_cache(h);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (int i = 0; i < 2; ++i) {
     release(h->stg_u[i]); release(h->stg_v[i]); release(h->stg_s[i]);
@@ -974,6 +1052,15 @@ int nlp_set_partition(nlp_handle* h, int rank, int world) {
   return NLP_OK;
 }
 
+int nlp_set_reuse(nlp_handle* h, int on) {
+  if (!h) return NLP_ERR_ARG;
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  clear_pair_cache(h);
+  h->reuse = on ? 1 : 0;
+  return NLP_OK;
+}
+
 int nlp_set_path(nlp_handle* h, int path) {
   if (!h) return NLP_ERR_ARG;
   if (path != NLP_PATH_AUTO && path != NLP_PATH_SOURCE && path != NLP_PATH_PAIR) return fail(h, NLP_ERR_ARG, "nlp_set_path: unknown path");
@@ -1019,7 +1106,7 @@ int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res) {
   }
   int ob = buf;
   uint64_t on = 0;
-  if (h->pair_pending) NLP_TRY(top_k_ordered(h, h->pair_sorted, h->pair_n, h->pair_kept, opt->max_edges, &ob, &on));
+  if (h->pair_pending) NLP_TRY(top_k_ordered(h, opt->max_edges, &ob, &on));
   else                 NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
   NLP_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
   NLP_CUDA(h, cudaEventSynchronize(h->ev_done));

@@ -197,3 +197,33 @@ def test_fetch_async_double_buffered(pred, nlp):
     for (m, D, K), w, b in zip(cases, want, bufs):
         got = (b[0].numpy().view(np.uint32), b[1].numpy().view(np.uint32), b[2].numpy())
         assert parity.compare(got, w, "fetch_async %s D=%d" % (m, D)) is None
+
+
+def test_reuse_across_measures(pred, oracle, nlp):
+    """nlp_set_reuse: the sorted wedge records of a threshold feed every later measure at that
+    threshold (main.cxx:212-220 order: measure-major, thresholds inside); results stay bit-exact
+    and the later predictions skip emission and sort."""
+    off, keys = _graph(nlp, "pp4k_symdup")
+    pred.set_graph(off, keys)
+    K = len(keys) // 10
+    try:
+        pred.set_reuse(True)
+        seen = set()
+        for m in nlp.MEASURES:
+            for D in (2, 16):
+                err, r, st = parity.check_case(pred, oracle, off, keys, m, D, K, tag="reuse")
+                assert err is None, err
+                assert r["path"] == PAIR_PATH
+                if D in seen:     # no emission, no sort: only back-to-back event records (a few microseconds)
+                    assert r["phase_ms"][1] < 0.02 and r["phase_ms"][2] < 0.02, r["phase_ms"]
+                else:
+                    assert r["phase_ms"][2] > 0.02, r["phase_ms"]
+                seen.add(D)
+        # a new graph empties the store
+        off2, keys2 = _graph(nlp, "rmat12")
+        pred.set_graph(off2, keys2)
+        err, r, st = parity.check_case(pred, oracle, off2, keys2, "AA", 16, 3000, tag="reuse-newgraph")
+        assert err is None, err
+        assert r["phase_ms"][2] > 0.02
+    finally:
+        pred.set_reuse(False)
