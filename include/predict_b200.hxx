@@ -81,6 +81,10 @@ struct Session {
       const char* d = std::getenv("NLP_B200_DEVICE");
       const int rc = nlp_create(&h, d ? std::atoi(d) : 0);
       if (rc != NLP_OK) throw std::runtime_error(std::string("nlp_b200: nlp_create: ") + nlp_last_error(nullptr));
+      // NLP_B200_REUSE=1: share the sorted wedge records of a threshold between the measures
+      // (main.cxx:212-220 runs all nine at every threshold on one graph); see nlp_set_reuse
+      const char* r = std::getenv("NLP_B200_REUSE");
+      if (r && *r == '1') nlp_set_reuse(h, 1);
     }
     return h;
   }
