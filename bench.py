@@ -50,7 +50,9 @@ MEASURES = ["CN", "JC", "SI", "SC", "HP", "HD", "LHN", "AA", "RA"]
 METRIC = "lhub_predicted_edges_per_s"
 
 
-def build_workload(name, device):
+def build_workload(name, device, batch=0):
+    """The graph of workload `name` with its edges removed.  `batch` picks the random removal:
+    the reference draws REPEAT_BATCH = 5 independent removals per fraction (main.cxx:26-28,163)."""
     import nlp_b200 as N
     w = WORKLOADS[name]
     t0 = time.time()
@@ -60,7 +62,7 @@ def build_workload(name, device):
         off, keys = N.graphs.road_lattice(w["side"], w["keep"], w["seed"], device=device)
     else:
         off, keys = N.graphs.web_crawl(w["n"], w["avg_out"], seed=w["seed"], device=device)
-    off, keys, rl, rh = N.graphs.remove_edges(off, keys, w["frac"], w["seed"] + 1000)
+    off, keys, rl, rh = N.graphs.remove_edges(off, keys, w["frac"], w["seed"] + 1000 + batch)
     K = int(rl.numel())
     del rl, rh
     if device != "cpu":
@@ -222,23 +224,27 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = "cuda:%d" % local
-    off, keys, K, info = build_workload(args.workload, dev)
+    all_measures = [m for m in args.measures.split(",") if m] if args.measures else MEASURES
+    # N > 1, three ways to use the GPUs (CSR replicated in all of them):
+    #  batches  (default)  every rank runs a whole step on ITS OWN batch -- the reference draws
+    #           REPEAT_BATCH independent random removals per fraction (main.cxx:163) and predicts on
+    #           each; independent units, no data-path collective, per-GPU work fixed: weak scaling
+    #  measures the nine predictions of ONE batch dealt to the ranks (strong scaling, no collective)
+    #  sources  the source vertices of each prediction partitioned (nlp_set_partition), local top-K
+    #           lists merged with one all-gather + on-device select (strong scaling; what a single
+    #           heavy prediction, e.g. IHub, needs)
+    shard = args.shard
+    if shard == "auto":
+        shard = "batches" if len(all_measures) > 1 else "sources"
+    if world == 1:
+        shard = "none"
+    off, keys, K, info = build_workload(args.workload, dev, batch=rank if shard == "batches" else 0)
     S = int(off.numel() - 1); M = int(keys.numel())
     # host copies in pinned memory (e2e leg) -- int64/int32 tensors carry the uint64/uint32 bits
     do_e2e = not args.no_e2e
     if do_e2e:
         h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
     pred = N.Predictor(local)
-    all_measures = [m for m in args.measures.split(",") if m] if args.measures else MEASURES
-    # N > 1: the nine predictions of a step are independent units (main.cxx:212-220 runs them one
-    # after the other), so they are dealt to the ranks and no data-path collective is needed;
-    # when a step has fewer predictions than ranks (e.g. one IHub measure) the SOURCES of each
-    # prediction are partitioned instead and the local top-K lists merged with one all-gather.
-    shard = args.shard
-    if shard == "auto":
-        shard = "measures" if len(all_measures) >= world else "sources"
-    if world == 1:
-        shard = "none"
     if shard == "sources":
         pred.set_partition(rank, world)
     stream = torch.cuda.ExternalStream(pred.lib.nlp_stream(pred.h), device=dev)
@@ -300,7 +306,7 @@ def run_b200(args):
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
-            if shard == "measures":          # every rank predicted different measures: whole-job edge count
+            if shard in ("measures", "batches"):     # every rank predicted something different: whole-job edge count
                 e = torch.tensor([edges], device=dev, dtype=torch.int64)
                 dist.all_reduce(e, op=dist.ReduceOp.SUM)
                 edges = int(e[0])
@@ -323,7 +329,14 @@ def run_b200(args):
         for _ in range(max(1, min(args.warmup, 2))):
             one_step_e2e()
         e_edges, e_ms, e_wall, _ = timed(one_step_e2e, args.steps)
-        e2e = {"value": e_edges / (e_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": (S + 1) * 8 + M * 4,
+        h2d = (S + 1) * 8 + M * 4
+        if shard == "batches":             # every rank moves its own graph: whole-job bytes
+            t = torch.tensor([h2d], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            h2d = int(t[0])
+        elif shard in ("measures", "sources"):
+            h2d *= world
+        e2e = {"value": e_edges / (e_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(e_edges / args.steps) * 12, "ms_per_step": e_ms / args.steps}
     else:
         e2e = None
@@ -434,11 +447,14 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak" if shard in ("none", "batches") else "strong",
         "vs_baseline": None, "dtype": "u32 counts, f32 scores (f64 terms for AA/RA/Salton)", "data": "synthetic",
         "config": dict(info, min_degree1=D, l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6),
                        measures=all_measures,
-                       parallelism={"none": "1 GPU", "measures": "the %d predictions of a step dealt to %d GPUs (independent units, no collective), CSR replicated" % (len(all_measures), world),
+                       parallelism={"none": "1 GPU",
+                                    "batches": "%d batches (independent random removals of the same graph, main.cxx:163), one whole step per GPU, CSR replicated, no collective" % world,
+                                    "measures": "the %d predictions of a step dealt to %d GPUs (independent units, no collective), CSR replicated" % (len(all_measures), world),
                                     "sources": "sources of every prediction partitioned over %d GPUs, CSR replicated, one all-gather + on-device merge" % world}[shard]),
         "clocks": clocks,
         "e2e": e2e,
@@ -468,8 +484,9 @@ def main():
     ap.add_argument("--workload", default="rmat22", choices=sorted(WORKLOADS))
     ap.add_argument("--degree", type=int, default=16, help="MINDEGREE1 of the LHub runs (0 = IHub)")
     ap.add_argument("--measures", default="", help="comma list (default: all nine)")
-    ap.add_argument("--shard", default="auto", choices=["auto", "measures", "sources"],
-                    help="N > 1: deal the predictions of a step to the ranks, or partition the sources of each prediction")
+    ap.add_argument("--shard", default="auto", choices=["auto", "batches", "measures", "sources"],
+                    help="N > 1: one batch per rank (weak scaling, default), the predictions of one batch dealt to the ranks, "
+                         "or the sources of each prediction partitioned (all-gather merge)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run on the host cores")
     args = ap.parse_args()

@@ -31,7 +31,8 @@ typedef enum {
   NLP_ERR_CUDA      = 2,   /* CUDA runtime error, or no usable device                           */
   NLP_ERR_NO_GRAPH  = 3,   /* nlp_predict before nlp_set_graph                                  */
   NLP_ERR_CAPACITY  = 4,   /* candidate buffer cannot hold an unbounded (max_edges = -1) result  */
-  NLP_ERR_NO_RESULT = 5    /* nlp_fetch before nlp_predict                                      */
+  NLP_ERR_NO_RESULT = 5,   /* nlp_fetch before nlp_predict                                      */
+  NLP_ERR_NO_TRUTH  = 6    /* nlp_evaluate before nlp_set_truth                                 */
 } nlp_status;
 
 /* Similarity measures, in the order main.cxx:212-220 runs them.
@@ -174,6 +175,32 @@ int nlp_result_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d_v,
  * select_ms (optional) receives the device time.                                               */
 int nlp_merge(nlp_handle* h, const uint32_t* d_u, const uint32_t* d_v, const float* d_score,
               uint64_t n, uint64_t max_edges, float* select_ms);
+
+/* ---- evaluation on the device ---------------------------------------
+ * main.cxx scores every prediction against the edges the batch removed (PREDICT_LINKS,
+ * main.cxx:48-57): both directions of the predicted edges are sorted and made unique
+ * (main.cxx:51-54, directedInsertions main.cxx:97-104), intersected with the sorted directed list
+ * of removed edges (commonEdges, main.cxx:126-133), and precision / recall are the size of the
+ * intersection over the two list sizes (main.cxx:201-202).  With the result already in GPU
+ * memory this is one kernel, and the K x 12 bytes of a prediction need not cross PCIe at all.   */
+
+/* The held-back edges: n directed (u, v) pairs sorted ascending by (u, v) -- main.cxx's
+ * `deletions0` (main.cxx:206-207; both directions of every removed undirected edge).  HOST (or
+ * this GPU's) pointers; copied.  Independent of the graph; stays until the next nlp_set_truth.
+ * NLP_ERR_ARG when the list is not sorted.                                                      */
+int nlp_set_truth(nlp_handle* h, const uint32_t* u, const uint32_t* v, uint64_t n);
+
+typedef struct {
+  uint64_t predicted;   /* |insertions1| = 2 x predicted edges (main.cxx:51-54)                  */
+  uint64_t truth;       /* |insertions0| = n of nlp_set_truth                                    */
+  uint64_t common;      /* |commonEdges(insertions0, insertions1)| (main.cxx:55)                 */
+  double   precision;   /* common / max(predicted, 1) (main.cxx:201)                             */
+  double   recall;      /* common / max(truth, 1)     (main.cxx:202)                             */
+  float    ms;          /* device time of the evaluation                                         */
+} nlp_evaluation;
+
+/* Evaluate the handle's last result (nlp_predict or nlp_merge) against the held-back edges.    */
+int nlp_evaluate(nlp_handle* h, nlp_evaluation* out);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t nlp_launch_count(const nlp_handle* h);

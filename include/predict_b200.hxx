@@ -75,6 +75,7 @@ struct Session {
   std::vector<uint32_t> keys;
   uint64_t fingerprint = 0;
   bool     have_fingerprint = false;
+  bool     fetch_edges = true;      // setFetchEdges(false): results stay on the GPU (evaluateLastPrediction)
   static Session& get() { static Session s; return s; }
   nlp_handle* handle() {
     if (!h) {
@@ -181,15 +182,61 @@ inline PredictLinkResult<K, W> predictLinksB200(const G& x, int measure, unsigne
   opt.min_score = o.minScore;
   PredictLinkResult<K, W> a;
   detail::check(h, nlp_predict(h, &opt, &a.stats), "nlp_predict");
+  a.time = a.stats.time_ms;
+  a.scoringTime = a.stats.scoring_ms;
+  if (!s.fetch_edges) return a;      // the edges stay in GPU memory (evaluateLastPrediction)
   const size_t n = (size_t)a.stats.count;
   std::vector<uint32_t> u(n), v(n);
   std::vector<float> sc(n);
   detail::check(h, nlp_fetch(h, u.data(), v.data(), sc.data(), n), "nlp_fetch");
   a.edges.resize(n);   // SoA -> tuples (never memcpy a std::tuple: member order is unspecified)
   for (size_t i = 0; i < n; ++i) a.edges[i] = std::make_tuple((K)u[i], (K)v[i], (W)sc[i]);
-  a.time = a.stats.time_ms;
-  a.scoringTime = a.stats.scoring_ms;
   return a;
+}
+
+
+// ---- evaluation on the GPU (main.cxx:48-57, 94-133, 199-206) ------------------------------------
+// main.cxx turns every prediction into both directions, sorts, uniques and intersects it with the
+// sorted directed list of removed edges on the host.  These three calls do the same where the
+// prediction already lies:
+//
+//   setHeldBackEdges(deletions0);        // once per batch: main.cxx:206-207's sorted directed list
+//   setFetchEdges(false);                // optional: leave PredictLinkResult::edges empty (no D2H copy)
+//   auto p1 = fn<deg>(y, {repeat, deletions0.size()/2});
+//   auto ev = evaluateLastPrediction();  // ev.precision, ev.recall as glog prints them (main.cxx:201-202)
+struct LinkEvaluation {
+  size_t predicted;   // |insertions1|: directed predicted edges (main.cxx:51-54)
+  size_t truth;       // |insertions0|
+  size_t common;      // |common1| (main.cxx:55)
+  double precision;   // main.cxx:201
+  double recall;      // main.cxx:202
+  float  time;        // device time, milliseconds
+};
+
+// `edges` = sorted directed (u, v[, w]) tuples, e.g. main.cxx's deletions0.
+template <class Tuple>
+inline void setHeldBackEdges(const std::vector<Tuple>& edges) {
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  nlp_handle* h = s.handle();
+  std::vector<uint32_t> u(edges.size()), v(edges.size());
+  for (size_t i = 0; i < edges.size(); ++i) { u[i] = (uint32_t)std::get<0>(edges[i]); v[i] = (uint32_t)std::get<1>(edges[i]); }
+  detail::check(h, nlp_set_truth(h, u.data(), v.data(), (uint64_t)edges.size()), "nlp_set_truth");
+}
+
+inline void setFetchEdges(bool on) {
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  s.fetch_edges = on;
+}
+
+inline LinkEvaluation evaluateLastPrediction() {
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  nlp_handle* h = s.handle();
+  nlp_evaluation e;
+  detail::check(h, nlp_evaluate(h, &e), "nlp_evaluate");
+  return LinkEvaluation{(size_t)e.predicted, (size_t)e.truth, (size_t)e.common, e.precision, e.recall, e.ms};
 }
 
 

@@ -13,11 +13,11 @@ from . import build as _build
 MEASURES = ["CN", "JC", "SI", "SC", "HP", "HD", "LHN", "AA", "RA"]   # main.cxx:212-220 order
 UNBOUNDED = (1 << 64) - 1
 STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH",
-          4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT"}
+          4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT", 6: "NLP_ERR_NO_TRUTH"}
 
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
            "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_set_reuse", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
-           "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
+           "nlp_set_truth", "nlp_evaluate", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
 class Options(C.Structure):
@@ -39,6 +39,15 @@ class Result(C.Structure):
             x = getattr(self, n)
             d[n] = list(x) if n in ("bin_sources", "phase_ms") else (float(x) if n.endswith("_ms") else int(x))
         return d
+
+
+class Evaluation(C.Structure):
+    _fields_ = [("predicted", C.c_uint64), ("truth", C.c_uint64), ("common", C.c_uint64),
+                ("precision", C.c_double), ("recall", C.c_double), ("ms", C.c_float)]
+
+    def as_dict(self):
+        return {"predicted": int(self.predicted), "truth": int(self.truth), "common": int(self.common),
+                "precision": float(self.precision), "recall": float(self.recall), "ms": float(self.ms)}
 
 
 class NlpError(RuntimeError):
@@ -76,6 +85,8 @@ def load_library(build_if_missing=True):
     lib.nlp_fetch_wait.argtypes = [vp]
     lib.nlp_result_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     lib.nlp_merge.argtypes = [vp, vp, vp, vp, u64, u64, C.POINTER(C.c_float)]
+    lib.nlp_set_truth.argtypes = [vp, vp, vp, u64]
+    lib.nlp_evaluate.argtypes = [vp, C.POINTER(Evaluation)]
     lib.nlp_launch_count.argtypes = [vp]
     lib.nlp_launch_count.restype = u64
     lib.nlp_stream.argtypes = [vp]
@@ -165,6 +176,24 @@ class Predictor:
         ms = C.c_float(0)
         self._check(self.lib.nlp_merge(self.h, u_ptr, v_ptr, s_ptr, n, max_edges, C.byref(ms)))
         return float(ms.value)
+
+    def set_truth(self, u, v):
+        """The held-back edges as main.cxx holds them: directed (u, v) pairs (both directions of
+        every removed edge), sorted ascending by (u, v).  numpy arrays; copied to the GPU."""
+        u = np.ascontiguousarray(u, dtype=np.uint32); v = np.ascontiguousarray(v, dtype=np.uint32)
+        assert u.shape == v.shape
+        self._check(self.lib.nlp_set_truth(self.h, u.ctypes.data if u.size else None,
+                                           v.ctypes.data if v.size else None, u.size))
+
+    def set_truth_pointers(self, u_ptr, v_ptr, n):
+        self._check(self.lib.nlp_set_truth(self.h, u_ptr, v_ptr, n))
+
+    def evaluate(self):
+        """Precision / recall of the last result against the held-back edges (main.cxx:48-57,
+        201-202), computed on the device."""
+        e = Evaluation()
+        self._check(self.lib.nlp_evaluate(self.h, C.byref(e)))
+        return e.as_dict()
 
     def launch_count(self):
         return int(self.lib.nlp_launch_count(self.h))

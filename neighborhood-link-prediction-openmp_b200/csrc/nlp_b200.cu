@@ -9,6 +9,7 @@
 #include "wedge.cuh"
 #include "select.cuh"
 #include "pairs.cuh"
+#include "evaluate.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -100,6 +101,11 @@ struct nlp_handle {
   cudaEvent_t ev_stg_ready[2] = {nullptr, nullptr}, ev_stg_done[2] = {nullptr, nullptr};
   bool stg_busy[2] = {false, false};
   int stg_next = 0;
+  // held-back edges for nlp_evaluate: packed (u << 32 | v) keys, ascending
+  DevBuf truth_key, truth_tmp, eval_ctr;
+  uint64_t truth_n = 0;
+  bool has_truth = false;
+  cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;
   // result
   int res_buf = 0;
   uint64_t res_count = 0;
@@ -967,6 +973,7 @@ int nlp_create(nlp_handle** out, int device) {
   }
   cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_frontier); cudaEventCreate(&h->ev_scored); cudaEventCreate(&h->ev_done);
   for (int i = 0; i < 7; ++i) cudaEventCreate(&h->ev_phase[i]);
+  cudaEventCreate(&h->ev_eval0); cudaEventCreate(&h->ev_eval1);
   if ((e = cudaMallocHost((void**)&h->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_hist, 12 * 256 * 8)) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_sel, sizeof(SelectState))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -1005,6 +1012,9 @@ int nlp_destroy(nlp_handle* h) {
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
   release(h->tables); release(h->touched); release(h->range_cursors); release(h->counts); release(h->totals); release(h->hist);
   release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
+  release(h->truth_key); release(h->truth_tmp); release(h->eval_ctr);
+  if (h->ev_eval0) cudaEventDestroy(h->ev_eval0);
+  if (h->ev_eval1) cudaEventDestroy(h->ev_eval1);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->h_hist) cudaFreeHost(h->h_hist);
   if (h->h_sel) cudaFreeHost(h->h_sel);
@@ -1212,6 +1222,63 @@ int nlp_merge(nlp_handle* h, const uint32_t* d_u, const uint32_t* d_v, const flo
   NLP_CUDA(h, cudaEventSynchronize(h->ev_done));
   if (select_ms) NLP_CUDA(h, cudaEventElapsedTime(select_ms, h->ev_start, h->ev_done));
   h->res_buf = ob; h->res_count = on; h->has_result = true;
+  return NLP_OK;
+}
+
+int nlp_set_truth(nlp_handle* h, const uint32_t* u, const uint32_t* v, uint64_t n) {
+  if (!h) return NLP_ERR_ARG;
+  if (n && (!u || !v)) return fail(h, NLP_ERR_ARG, "nlp_set_truth: null input");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  h->has_truth = false;
+  NLP_TRY(ensure(h, h->truth_key, n * 8));
+  NLP_TRY(ensure(h, h->truth_tmp, n * 8));
+  NLP_TRY(ensure(h, h->eval_ctr, 16));
+  NLP_CUDA(h, cudaMemsetAsync(h->eval_ctr.p, 0, 16, h->stream));
+  if (n) {
+    uint32_t* du = (uint32_t*)h->truth_tmp.p;
+    uint32_t* dv = du + n;
+    NLP_CUDA(h, cudaMemcpyAsync(du, u, n * 4, cudaMemcpyDefault, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(dv, v, n * 4, cudaMemcpyDefault, h->stream));
+    k_truth_pack<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        du, dv, n, (unsigned long long*)h->truth_key.p, (unsigned int*)h->eval_ctr.p + 2);
+    NLP_LAUNCHED(h);
+  }
+  unsigned int unsorted = 0;
+  NLP_CUDA(h, cudaMemcpyAsync(&unsorted, (unsigned int*)h->eval_ctr.p + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (unsorted) return fail(h, NLP_ERR_ARG, "nlp_set_truth: the edge list is not sorted ascending by (u, v)");
+  h->truth_n = n;
+  h->has_truth = true;
+  return NLP_OK;
+}
+
+int nlp_evaluate(nlp_handle* h, nlp_evaluation* out) {
+  if (!h) return NLP_ERR_ARG;
+  if (!out) return fail(h, NLP_ERR_ARG, "nlp_evaluate: null output");
+  if (!h->has_result) return fail(h, NLP_ERR_NO_RESULT, "nlp_evaluate: no result (run nlp_predict / nlp_merge first)");
+  if (!h->has_truth) return fail(h, NLP_ERR_NO_TRUTH, "nlp_evaluate: no held-back edges (call nlp_set_truth first)");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  memset(out, 0, sizeof *out);
+  const uint64_t count = h->res_count, n = h->truth_n;
+  unsigned long long common = 0;
+  NLP_CUDA(h, cudaEventRecord(h->ev_eval0, h->stream));
+  if (count && n) {
+    NLP_CUDA(h, cudaMemsetAsync(h->eval_ctr.p, 0, 8, h->stream));
+    const int b = h->res_buf;
+    k_evaluate<<<grid_for(count, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        (const uint32_t*)h->cu[b].p, (const uint32_t*)h->cv[b].p, count, (const unsigned long long*)h->truth_key.p, n,
+        (unsigned long long*)h->eval_ctr.p);
+    NLP_LAUNCHED(h);
+    NLP_CUDA(h, cudaMemcpyAsync(&common, h->eval_ctr.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  NLP_CUDA(h, cudaEventRecord(h->ev_eval1, h->stream));
+  NLP_CUDA(h, cudaEventSynchronize(h->ev_eval1));
+  NLP_CUDA(h, cudaEventElapsedTime(&out->ms, h->ev_eval0, h->ev_eval1));
+  out->predicted = 2 * count;                                  // main.cxx:51-54
+  out->truth = n;
+  out->common = common;                                        // main.cxx:55
+  out->precision = (double)common / (double)std::max<uint64_t>(out->predicted, 1);   // main.cxx:201
+  out->recall    = (double)common / (double)std::max<uint64_t>(out->truth, 1);       // main.cxx:202
   return NLP_OK;
 }
 

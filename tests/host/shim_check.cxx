@@ -6,6 +6,7 @@
 //   shim_check <graph.bin> <out.bin> <maxEdges|-1>
 //   graph.bin : u64 span, u64 M, u64 offsets[span+1], u32 keys[M]
 //   out.bin   : per case  u32 measure, u32 omp, u32 D, u64 n, then n x (u32 u, u32 v, f32 score)
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -74,7 +75,29 @@ int main(int argc, char** argv) {
     // a graph that stays on the GPU across predictions
     nlp_b200::DeviceGraph dg(x);
     emit(1, 1, 8, nlp_b200::predictLinksJaccardCoefficientOmp<8>(dg, o));
-    emit(7, 1, 8, nlp_b200::predictLinksAdamicAdarCoefficientOmp<8>(dg, {1, 100}));
+    auto last = nlp_b200::predictLinksAdamicAdarCoefficientOmp<8>(dg, {1, 100});
+    emit(7, 1, 8, last);
+    // evaluation on the device (main.cxx:48-57, 201-202): hold back the first half of that very
+    // prediction, predict again without fetching the edges, expect precision 1/2 and recall 1
+    {
+      vector<tuple<uint32_t, uint32_t, float>> truth;
+      const size_t half = last.edges.size() / 2;
+      for (size_t i = 0; i < half; ++i) {
+        const auto& [u, v, w] = last.edges[i];
+        truth.push_back({u, v, 1.0f}); truth.push_back({v, u, 1.0f});
+      }
+      sort(truth.begin(), truth.end());
+      nlp_b200::setHeldBackEdges(truth);
+      nlp_b200::setFetchEdges(false);
+      auto again = nlp_b200::predictLinksAdamicAdarCoefficientOmp<8>(dg, {1, 100});
+      nlp_b200::setFetchEdges(true);
+      const auto ev = nlp_b200::evaluateLastPrediction();
+      if (!again.edges.empty() || again.stats.count != last.edges.size()) throw runtime_error("setFetchEdges(false) still fetched");
+      if (ev.predicted != 2 * last.edges.size() || ev.truth != truth.size() || ev.common != truth.size())
+        throw runtime_error("evaluateLastPrediction: wrong counts");
+      if (half && (ev.recall != 1.0 || ev.precision != double(truth.size()) / double(2 * last.edges.size())))
+        throw runtime_error("evaluateLastPrediction: wrong precision / recall");
+    }
     fclose(out);
   } catch (const std::exception& e) {
     fprintf(stderr, "shim_check: %s\n", e.what());

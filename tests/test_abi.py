@@ -34,11 +34,12 @@ def test_library_exports_every_declared_symbol(nlp):
 def test_struct_layout_matches_header(nlp, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "nlp_b200.h"\n'
-                   'int main(void){printf("%zu %zu\\n", sizeof(nlp_options), sizeof(nlp_result));return 0;}\n')
+                   'int main(void){printf("%zu %zu %zu\\n", sizeof(nlp_options), sizeof(nlp_result), sizeof(nlp_evaluation));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c = map(int, subprocess.check_output([str(exe)]).split())
     assert a == C.sizeof(nlp.binding.Options) and b == C.sizeof(nlp.binding.Result)
+    assert c == C.sizeof(nlp.binding.Evaluation)
 
 
 def test_no_cpu_fallback(nlp):

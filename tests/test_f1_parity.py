@@ -52,3 +52,55 @@ def test_f1_matches_exactly(nlp, oracle, kind):
                 assert got == want, (kind, measure, D, got, want)
     finally:
         pred.close()
+
+
+def directed_truth(lo, hi):
+    """main.cxx:206-207: both directions of every removed edge, sorted by (u, v)."""
+    tu = np.concatenate([lo, hi]).astype(np.uint32)
+    tv = np.concatenate([hi, lo]).astype(np.uint32)
+    o = np.lexsort((tv, tu))
+    return tu[o], tv[o]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["clustered", "rmat"])
+def test_device_evaluation_matches_host(nlp, kind):
+    """nlp_set_truth + nlp_evaluate (precision / recall on the device, main.cxx:48-57,201-202)
+    against the host computation on the fetched edges."""
+    o, k, lo, hi = workload(nlp, kind)
+    tu, tv = directed_truth(lo, hi)
+    pred = nlp.Predictor(0)
+    try:
+        pred.set_graph(o, k)
+        with pytest.raises(nlp.NlpError) as e:
+            pred.predict("JC", 4, max_edges=10)
+            pred.evaluate()
+        assert e.value.code == 6                       # NLP_ERR_NO_TRUTH
+        with pytest.raises(nlp.NlpError) as e:
+            pred.set_truth(tu[::-1], tv[::-1])
+        assert e.value.code == 1                       # not sorted
+        pred.set_truth(tu, tv)
+        for measure in ("CN", "JC", "AA"):
+            for D in (0, 4, 32):
+                for K in (len(lo), len(lo) // 3, 1):
+                    r = pred.predict(measure, D, max_edges=K)
+                    ev = pred.evaluate()
+                    gu, gv, gs = pred.fetch(r["count"])
+                    p, rc, f1 = f1_of(gu, gv, lo, hi, len(o))
+                    assert ev["predicted"] == 2 * r["count"] and ev["truth"] == 2 * len(lo)
+                    assert ev["precision"] == p and ev["recall"] == rc, (kind, measure, D, K, ev, p, rc)
+        # a truth list with a repeated entry and ids outside the graph still matches once per edge
+        tu2 = np.concatenate([tu[:1], tu, [np.uint32(len(o) + 5)]]).astype(np.uint32)
+        tv2 = np.concatenate([tv[:1], tv, [np.uint32(1)]]).astype(np.uint32)
+        pred.set_truth(tu2, tv2)
+        r = pred.predict("JC", 0, max_edges=len(lo))
+        ev2 = pred.evaluate()
+        gu, gv, gs = pred.fetch(r["count"])
+        p, rc, f1 = f1_of(gu, gv, lo, hi, len(o))
+        assert ev2["truth"] == len(tu2) and ev2["common"] == round(p * 2 * r["count"])
+        # empty truth / empty result
+        pred.set_truth(np.empty(0, np.uint32), np.empty(0, np.uint32))
+        ev3 = pred.evaluate()
+        assert ev3["common"] == 0 and ev3["recall"] == 0.0 and ev3["precision"] == 0.0
+    finally:
+        pred.close()
