@@ -235,7 +235,7 @@ struct BinLists { uint32_t* list[NBINS]; };
 
 // flt: the float measures send every source above the 1K-slot hash bin to the sort-based path
 // range_c: counters per window of k_range (0 = that path is off); room = S-1-u
-__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, bool flt, uint32_t range_c, uint32_t room) {
+__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, bool flt, uint32_t range_c, uint32_t range_div, uint32_t room) {
   if (du <= LONG_ROW) {
     if (work <= 8u) return 0;
     if (work <= 32u) return 1;
@@ -245,17 +245,17 @@ __device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_
   if (bound <= bin_limit(3)) return 3;
   if (bound <= bin_limit(4)) return 4;
   if (range_c) {
-    // Every window costs a scan of the counters plus two binary searches and a block scan per
-    // first-hop row (~2.5K + 3.5*du SM-cycles, measured); the dense table pays an HBM sector
-    // update per wedge (~47 SM-cycles against ~4 for a shared-memory atomic, R-MAT 18/20 IHub).
+    // Every window costs a scan of the counters plus a cursor step per first-hop row; the dense
+    // table pays an HBM sector update per wedge (~47 SM-cycles against ~4 for a shared-memory
+    // atomic, R-MAT 18/20 IHub).  range_div weighs the per-row part (NLP_B200_RANGE_DIV).
     const unsigned long long passes = ((unsigned long long)room + range_c - 1) / range_c;
-    if ((unsigned long long)work >= passes * (256ull + du / 4u)) return 6;
+    if ((unsigned long long)work >= passes * (256ull + du / range_div)) return 6;
   }
   return 5;
 }
 
 __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long long* __restrict__ work64, int rank, int world,
-                                             bool flt, uint32_t range_c, uint32_t* __restrict__ work, BinLists bl, Counters* ctr) {
+                                             bool flt, uint32_t range_c, uint32_t range_div, uint32_t* __restrict__ work, BinLists bl, Counters* ctr) {
   __shared__ unsigned long long s_cnt[NBINS], s_sum[NBINS], s_base[NBINS], s_max;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < NBINS) { s_cnt[threadIdx.x] = 0; s_sum[threadIdx.x] = 0; }
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) { bin = choose_bin(w, bound, g.deg[u], flt, range_c, room); need = bin < 2 ? w : bound; }
+        if (bound) { bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, room); need = bin < 2 ? w : bound; }
       }
     }
     #pragma unroll
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) bin = choose_bin(w, bound, g.deg[u], flt, range_c, room);
+        if (bound) bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, room);
       }
     }
     #pragma unroll

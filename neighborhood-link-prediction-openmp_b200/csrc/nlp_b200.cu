@@ -64,6 +64,7 @@ struct nlp_handle {
   int cluster_mode = 0;                      // 0: single-CTA k_range only (default: remote shared-memory atomics
                                              // measured 1.3x/2x/3.3x slower at cluster size 2/4/8, R-MAT 20 IHub),
                                              // 1: auto, n > 1: force clusters of n CTAs
+  uint32_t range_div = 4;                    // weight of the per-row window cost in the k_range / k_dense rule (frontier.cuh)
   int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
@@ -571,15 +572,17 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   const uint32_t S = h->S;
   const DevGraph g = dev_graph(h);
   if (h->sym_state == 0) {
-    NLP_TRY(ensure(h, h->sym_flag, 16));
-    NLP_CUDA(h, cudaMemsetAsync(h->sym_flag.p, 0, 16, h->stream));
+    NLP_TRY(ensure(h, h->sym_flag, 32));
+    NLP_CUDA(h, cudaMemsetAsync(h->sym_flag.p, 0, 32, h->stream));
     if (h->M) {
-      k_symmetry<<<grid_for(h->M, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, h->M, (unsigned int*)h->sym_flag.p);
+      k_symmetry<<<grid_for(h->M, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, h->M, (unsigned int*)h->sym_flag.p,
+                                                                                (unsigned long long*)h->sym_flag.p + 1);
       NLP_LAUNCHED(h);
     }
-    unsigned int f = 0;
-    NLP_CUDA(h, cudaMemcpyAsync(&f, h->sym_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long sf[3] = {0, 0, 0};              // {asym flag, entries u < w, entries u > w}
+    NLP_CUDA(h, cudaMemcpyAsync(sf, h->sym_flag.p, 24, cudaMemcpyDeviceToHost, h->stream));
     NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    const bool f = (unsigned int)sf[0] != 0u || sf[1] != sf[2];
     h->sym_state = f ? 2 : 1;
     // the check is graph preparation, not part of the prediction: restart the clock
     NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
@@ -775,7 +778,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   // the float measures need the ordered single-warp accumulation of k_dense
   const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS * range_cluster_size(h) : 0u;
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
-                                                                  false, range_c, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
+                                                                  false, range_c, h->range_div, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -949,6 +952,7 @@ int nlp_create(nlp_handle** out, int device) {
   nlp_handle* h = new nlp_handle();
   h->device = device;
   if (const char* e = getenv("NLP_B200_RANGE")) h->range_mode = atoi(e);   // experiment knobs
+  if (const char* e = getenv("NLP_B200_RANGE_DIV")) h->range_div = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
   if (const char* e = getenv("NLP_B200_CLUSTER")) h->cluster_mode = atoi(e);
   auto bail = [&](const char* what, cudaError_t err) {

@@ -23,12 +23,17 @@
 
 namespace nlp {
 
-// asym != 0 afterwards <=> some entry (u, w) has a different multiplicity than (w, u).
-__global__ void __launch_bounds__(256) k_symmetry(DevGraph g, uint64_t M, unsigned int* __restrict__ asym) {
+// Rows are symmetric <=> asym == 0 and dir[0] == dir[1] afterwards.  Only the entries (u, w) with
+// u < w look up their mirror image (multiplicity of u in row w); dir[0] / dir[1] count the entries
+// with u < w / u > w.  If every looked-up pair matches, the u > w side holds exactly the mirrored
+// entries plus the entries nobody looked up, so equal counts mean there are none of those.
+__global__ void __launch_bounds__(256) k_symmetry(DevGraph g, uint64_t M, unsigned int* __restrict__ asym,
+                                                  unsigned long long* __restrict__ dir) {
   const uint32_t* __restrict__ keys = g.keys;
   const int lane = threadIdx.x & 31;
   const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long n_up = 0, n_down = 0;
   for (uint64_t base = warp0 * 32u; base < M; base += nwarps * 32u) {
     // row of the warp's first entry by bisection (same loads in every lane: broadcast), then
     // every lane walks forward to its own row -- 32 consecutive entries span few rows
@@ -42,11 +47,14 @@ __global__ void __launch_bounds__(256) k_symmetry(DevGraph g, uint64_t M, unsign
     uint32_t u = lo;
     while (__ldg(g.off + u + 1) <= e) ++u;
     const uint32_t w = __ldg(keys + e);
+    if (w >= g.S) { atomicOr(asym, 1u); continue; }
+    if (w == u) continue;                                      // a self-loop is its own mirror image
+    if (w < u) { ++n_down; continue; }
+    ++n_up;
     const uint64_t ub = __ldg(g.off + u), ue = __ldg(g.off + u + 1);
-    if (e > ub && __ldg(keys + e - 1) == w) continue;          // counted at the first entry of the run
+    if (e > ub && __ldg(keys + e - 1) == w) continue;          // looked up at the first entry of the run
     uint32_t mult = 1;
     while (e + mult < ue && __ldg(keys + e + mult) == w) ++mult;
-    if (w >= g.S) { atomicOr(asym, 1u); continue; }
     const uint64_t wb = __ldg(g.off + w);
     const uint32_t dw = (uint32_t)(__ldg(g.off + w + 1) - wb);
     uint32_t a = 0, b = dw;
@@ -57,6 +65,15 @@ __global__ void __launch_bounds__(256) k_symmetry(DevGraph g, uint64_t M, unsign
     uint32_t c = 0;
     while (a + c < dw && __ldg(keys + wb + a + c) == u) ++c;
     if (c != mult) atomicOr(asym, 1u);
+  }
+  #pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) {
+    n_up   += __shfl_xor_sync(NLP_FULL, n_up, k);
+    n_down += __shfl_xor_sync(NLP_FULL, n_down, k);
+  }
+  if (lane == 0) {
+    if (n_up)   atomicAdd(dir + 0, n_up);
+    if (n_down) atomicAdd(dir + 1, n_down);
   }
 }
 

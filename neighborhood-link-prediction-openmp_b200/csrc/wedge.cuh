@@ -660,18 +660,25 @@ __device__ __forceinline__ unsigned long long gallop_to(const uint32_t* __restri
   return hi;
 }
 
-// Wedges behind up to RANGE_THREADS first-hop entries (thread t holds entry t) whose v lies in
-// [vlo, vhi): cnt[v - vlo] += 1.  The window parts of all rows are laid end to end and dealt to
-// the threads of the WHOLE block, so one hub row among the entries is shared by 1024 threads
-// instead of stalling the one warp that drew it (ncu: 54 % of the first version's stall samples
-// sat at the barrier behind such warps).  cur[] / end[] (global scratch of this block, one slot
-// per first-hop entry) carry every row's position from window to window: the first window finds
-// the first key > u by bisection and stores the row end, later windows only read the two words
-// (coalesced) and gallop forward.
-__device__ __forceinline__ void range_batch(const Params& p, bool has, bool first, uint32_t w, uint32_t vlo, uint32_t vhi,
-                                            unsigned long long* cur, unsigned long long* end, uint32_t* cnt,
-                                            uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
+// One window of one source.  A (first-hop row, window) visit usually finds next to nothing -- at
+// R-MAT 22 a hub source sees 80 windows and 0.35 entries per row and window -- so the visits must
+// not cost a block barrier each (the first version batched 1024 rows between barriers and spent
+// its time there: one wedge per thread and batch).  Now WARPS draw chunks of 32 consecutive
+// first-hop entries from a shared-memory ticket counter and stream the window parts of those 32
+// rows on their own, packed back to back over the lanes (shuffles only, no barrier).  Only rows
+// with more than RANGE_BIG entries inside the window are queued (at most RANGE_QCAP per window)
+// and streamed by the whole block after the warps are done, so a hub row among the entries is
+// shared by 1024 threads instead of stalling the warp that drew it.
+// cur[] / end[] (global scratch of this block, one slot per first-hop entry) carry every row's
+// position from window to window: the first window finds the first key > u by bisection and
+// stores the row end, later windows only read the two words (coalesced) and gallop forward.
+enum { RANGE_BIG = 256, RANGE_QCAP = RANGE_THREADS };
+
+__device__ __forceinline__ void range_warp_chunk(const Params& p, bool has, bool first, uint32_t w, uint32_t vlo, uint32_t vhi,
+                                                 unsigned long long* cur, unsigned long long* end, uint32_t* cnt,
+                                                 unsigned long long* s_qa, uint32_t* s_qdw, uint32_t* s_qn) {
   const uint32_t* __restrict__ keys = p.g.keys;
+  const int lane = threadIdx.x & 31;
   unsigned long long a = 0;
   uint32_t dw = 0;
   if (has) {
@@ -688,8 +695,43 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, bool firs
     *cur = b;
     dw = (uint32_t)(b - a);
   }
-  s_wb[threadIdx.x] = a;
-  block_scan_u32(dw, s_inc, s_wsum);                  // k_range is only used when 1024 * maxdeg < 2^32
+  if (dw > (uint32_t)RANGE_BIG) {                     // long part: leave it to the whole block
+    const uint32_t slot = atomicAdd(s_qn, 1u);
+    if (slot < (uint32_t)RANGE_QCAP) { s_qa[slot] = a; s_qdw[slot] = dw; dw = 0; }
+  }
+  uint32_t inc = dw;                                  // inclusive scan of the part lengths
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const uint32_t tot = __shfl_sync(NLP_FULL, inc, 31);
+  for (uint32_t sb = 0; sb < tot; sb += 32u) {
+    const uint32_t idx = sb + lane;
+    int j = 0;                                        // smallest j with inc[j] > idx
+    #pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
+      if (x <= idx) j += step;
+    }
+    const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
+    const uint32_t dwj = __shfl_sync(NLP_FULL, dw, j);
+    const unsigned long long aj = __shfl_sync(NLP_FULL, a, j);
+    if (idx < tot) {
+      const uint32_t v = __ldg(keys + aj + (idx - (incj - dwj)));
+      atomicAdd(cnt + (v - vlo), 1u);                                // inc/predict.hxx:156-158
+    }
+  }
+}
+
+// The queued long parts (entry t of the queue in s_wb[t] / s_inc[t], t < qn <= RANGE_THREADS) laid
+// end to end and dealt to the threads of the whole block.  k_range is only used when
+// 1024 * maxdeg < 2^32, so the scan cannot overflow.
+__device__ __forceinline__ void range_queue(const Params& p, uint32_t qn, uint32_t vlo, uint32_t* cnt,
+                                            uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
+  const uint32_t* __restrict__ keys = p.g.keys;
+  const uint32_t dw = threadIdx.x < qn ? s_inc[threadIdx.x] : 0u;   // own slot: read before the scan rewrites it
+  block_scan_u32(dw, s_inc, s_wsum);
   const uint32_t tot = s_inc[RANGE_THREADS - 1];
   for (uint32_t idx = threadIdx.x; idx < tot; idx += RANGE_THREADS) {
     uint32_t lo = 0, hi = RANGE_THREADS - 1;          // smallest j with s_inc[j] > idx
@@ -716,6 +758,7 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
   __shared__ uint32_t s_wsum[32];
   __shared__ int s_go;
   __shared__ uint32_t s_qi;
+  __shared__ uint32_t s_ticket, s_qn;                 // chunk tickets / queued long parts of the current window
   __shared__ unsigned int s_emitted;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const uint32_t* __restrict__ keys = p.g.keys;
@@ -746,15 +789,30 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
       const uint32_t vlo = (uint32_t)lo64;
       const uint32_t vhi = (uint32_t)(lo64 + C < p.g.S ? lo64 + C : p.g.S);
       const bool first = lo64 == (uint64_t)u + 1;
-      for (uint32_t c = 0; c < f.npieces; ++c) {
+      if (tid == 0) { s_ticket = 0u; s_qn = 0u; }
+      __syncthreads();
+      // chunks of 32 consecutive first-hop entries; a long first-hop row is a sequence of pieces,
+      // CHUNK entries apart (frontier.cuh), each with its own count
+      const uint32_t per_piece = f.npieces == 1 ? (f.single_count + 31u) / 32u : CHUNK / 32u;
+      const uint32_t nchunks = f.npieces * per_piece;
+      for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&s_ticket, 1u);
+        t = __shfl_sync(NLP_FULL, t, 0);
+        if (t >= nchunks) break;
+        const uint32_t c = t / per_piece, k = t - c * per_piece;
         const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
+        if (k * 32u >= pc) continue;
         const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
-        for (uint32_t base = 0; base < pc; base += RANGE_THREADS) {
-          const uint32_t i = base + tid;
-          const bool has = i < pc;
-          const uint64_t ci = (uint64_t)c * CHUNK + i;
-          range_batch(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, cur + ci, end + ci, cnt, s_inc, s_wb, s_wsum);
-        }
+        const uint32_t i = k * 32u + lane;
+        const bool has = i < pc;
+        const uint64_t ci = (uint64_t)c * CHUNK + i;
+        range_warp_chunk(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, cur + ci, end + ci, cnt, s_wb, s_inc, &s_qn);
+      }
+      __syncthreads();
+      {
+        const uint32_t qn = s_qn < (uint32_t)RANGE_QCAP ? s_qn : (uint32_t)RANGE_QCAP;   // same value in every thread
+        if (qn) range_queue(p, qn, vlo, cnt, s_inc, s_wb, s_wsum);
       }
       {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
         const uint32_t a = lower_bound_row(keys, ub, du, vlo);
