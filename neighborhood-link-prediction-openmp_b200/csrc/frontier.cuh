@@ -248,8 +248,10 @@ __device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_
     // Every window costs a scan of the counters plus a cursor step per first-hop row; the dense
     // table pays an HBM sector update per wedge (~47 SM-cycles against ~4 for a shared-memory
     // atomic, R-MAT 18/20 IHub).  range_div weighs the per-row part (NLP_B200_RANGE_DIV).
-    const unsigned long long passes = ((unsigned long long)room + range_c - 1) / range_c;
-    if ((unsigned long long)work >= passes * (256ull + du / range_div)) return 6;
+    // Bit 31 of range_div: sources with deg < 2^15 count in half words, their windows are twice as wide.
+    const unsigned long long rc = (unsigned long long)range_c << (((range_div >> 31) && du < 32768u) ? 1 : 0);
+    const unsigned long long passes = ((unsigned long long)room + rc - 1) / rc;
+    if ((unsigned long long)work >= passes * (256ull + du / (range_div & 0x7fffffffu))) return 6;
   }
   return 5;
 }

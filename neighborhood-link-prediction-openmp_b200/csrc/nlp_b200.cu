@@ -64,6 +64,7 @@ struct nlp_handle {
   int cluster_mode = 0;                      // 0: single-CTA k_range only (default: remote shared-memory atomics
                                              // measured 1.3x/2x/3.3x slower at cluster size 2/4/8, R-MAT 20 IHub),
                                              // 1: auto, n > 1: force clusters of n CTAs
+  int range_half = 1;                        // k_range: half-word counters for sources with deg < 2^15 (NLP_B200_RANGE_HALF=0: off)
   uint32_t range_div = 4;                    // weight of the per-row window cost in the k_range / k_dense rule (frontier.cuh)
   int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
   DevBuf list[NBINS], defer[NBINS];
@@ -778,7 +779,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   // the float measures need the ordered single-warp accumulation of k_dense
   const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS * range_cluster_size(h) : 0u;
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
-                                                                  false, range_c, h->range_div, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
+                                                                  false, range_c, h->range_div | (h->range_half ? 0x80000000u : 0u), (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -829,6 +830,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   Params p;
   p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
   p.coop = (h->maxdeg < (1u << 22) && h->coop_mode != 0) ? 1u : 0u;
+  p.range_half = h->range_half ? 1u : 0u;
   p.elig = lhub ? (const uint32_t*)h->elig.p : nullptr;
   p.ekeys = lhub ? (const uint32_t*)h->ekeys.p : nullptr;
   p.ecount = lhub ? (const uint32_t*)h->ecount.p : nullptr;
@@ -952,6 +954,7 @@ int nlp_create(nlp_handle** out, int device) {
   nlp_handle* h = new nlp_handle();
   h->device = device;
   if (const char* e = getenv("NLP_B200_RANGE")) h->range_mode = atoi(e);   // experiment knobs
+  if (const char* e = getenv("NLP_B200_RANGE_HALF")) h->range_half = atoi(e);
   if (const char* e = getenv("NLP_B200_RANGE_DIV")) h->range_div = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
   if (const char* e = getenv("NLP_B200_CLUSTER")) h->cluster_mode = atoi(e);

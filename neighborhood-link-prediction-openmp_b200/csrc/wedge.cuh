@@ -646,10 +646,12 @@ __device__ __forceinline__ uint32_t lower_bound_row(const uint32_t* __restrict__
 
 // First position in [a, e) (absolute indices into keys, sorted row) whose key is >= x: gallop from
 // a, then bisect.  Window after window the cursor only moves forward, so a step costs O(log of
-// the segment it skips) dependent loads instead of O(log of the row).
+// the segment it skips) dependent loads instead of O(log of the row).  KNOWN_LESS: the caller
+// already knows keys[a] < x (and a < e).
+template <bool KNOWN_LESS>
 __device__ __forceinline__ unsigned long long gallop_to(const uint32_t* __restrict__ keys, unsigned long long a,
                                                         unsigned long long e, uint32_t x) {
-  if (a >= e || __ldg(keys + a) >= x) return a;
+  if (!KNOWN_LESS && (a >= e || __ldg(keys + a) >= x)) return a;
   unsigned long long lo = a, step = 1;                 // keys[lo] < x
   while (lo + step < e && __ldg(keys + lo + step) < x) { lo += step; step <<= 1; }
   unsigned long long hi = lo + step < e ? lo + step : e;   // keys[hi] >= x, or hi == e
@@ -660,78 +662,63 @@ __device__ __forceinline__ unsigned long long gallop_to(const uint32_t* __restri
   return hi;
 }
 
-// One window of one source.  A (first-hop row, window) visit usually finds next to nothing -- at
-// R-MAT 22 a hub source sees 80 windows and 0.35 entries per row and window -- so the visits must
-// not cost a block barrier each (the first version batched 1024 rows between barriers and spent
-// its time there: one wedge per thread and batch).  Now WARPS draw chunks of 32 consecutive
-// first-hop entries from a shared-memory ticket counter and stream the window parts of those 32
-// rows on their own, packed back to back over the lanes (shuffles only, no barrier).  Only rows
-// with more than RANGE_BIG entries inside the window are queued (at most RANGE_QCAP per window)
-// and streamed by the whole block after the warps are done, so a hub row among the entries is
-// shared by 1024 threads instead of stalling the warp that drew it.
-// cur[] / end[] (global scratch of this block, one slot per first-hop entry) carry every row's
-// position from window to window: the first window finds the first key > u by bisection and
-// stores the row end, later windows only read the two words (coalesced) and gallop forward.
-enum { RANGE_BIG = 256, RANGE_QCAP = RANGE_THREADS };
+// HALF: two 16-bit counters per word (see k_range); the halves cannot carry into each other
+// because a count never exceeds deg(u) < 2^15.
+template <bool HALF>
+__device__ __forceinline__ void range_count(uint32_t* cnt, uint32_t x) {
+  if (HALF) atomicAdd(cnt + (x >> 1), (x & 1u) ? 0x10000u : 1u);
+  else atomicAdd(cnt + x, 1u);                        // inc/predict.hxx:156-158
+}
 
-__device__ __forceinline__ void range_warp_chunk(const Params& p, bool has, bool first, uint32_t w, uint32_t vlo, uint32_t vhi,
-                                                 unsigned long long* cur, unsigned long long* end, uint32_t* cnt,
-                                                 unsigned long long* s_qa, uint32_t* s_qdw, uint32_t* s_qn) {
+// Wedges behind up to RANGE_THREADS first-hop entries (thread t holds entry t) whose v lies in
+// [vlo, vhi): counter[v - vlo] += 1.  The window parts of all rows are laid end to end and dealt
+// to the threads of the WHOLE block, so one hub row among the entries is shared by 1024 threads
+// instead of stalling the one warp that drew it (ncu: 54 % of the first version's stall samples
+// sat at the barrier behind such warps).
+// rec[] (global scratch of this block, one 16-byte record per first-hop entry: position, entries
+// left, key at the position) carries every row from window to window: the first window finds the
+// first key > u by bisection, later windows read the record (one coalesced 16-byte load) and
+// know from the cached key whether the row has anything in the window at all -- at R-MAT 22 a
+// hub source walks 80 windows and two thirds of its (row, window) visits find nothing, and those
+// now cost neither a dependent key load nor a store.
+__device__ __forceinline__ uint4 range_pack(unsigned long long pos, unsigned long long e, uint32_t next) {
+  return make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), (uint32_t)(e - pos), next);
+}
+
+template <bool HALF>
+__device__ __forceinline__ void range_batch(const Params& p, bool has, bool first, uint32_t w, uint32_t vlo, uint32_t vhi,
+                                            uint4* rec, uint32_t* cnt,
+                                            uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
   const uint32_t* __restrict__ keys = p.g.keys;
-  const int lane = threadIdx.x & 31;
   unsigned long long a = 0;
   uint32_t dw = 0;
   if (has) {
     unsigned long long e;
+    uint32_t next;
+    bool moved = false;
     if (first) {
       const unsigned long long wb = __ldg(p.g.off + w);
       e = __ldg(p.g.off + w + 1);
       a = wb + lower_bound_row(keys, wb, (uint32_t)(e - wb), vlo);
-      *end = e;
+      next = a < e ? __ldg(keys + a) : 0xffffffffu;
+      moved = true;
     } else {
-      a = *cur; e = *end;
+      const uint4 r = *rec;
+      a = (unsigned long long)r.x | ((unsigned long long)r.y << 32);
+      e = a + r.z;
+      next = r.w;
     }
-    const unsigned long long b = vhi >= p.g.S ? e : gallop_to(keys, a, e, vhi);
-    *cur = b;
+    unsigned long long b = a;
+    if (next < vhi) {                                 // the row has entries in this window (so a < e)
+      b = vhi >= p.g.S ? e : gallop_to<true>(keys, a, e, vhi);
+      next = b < e ? __ldg(keys + b) : 0xffffffffu;
+      moved = true;
+    }
+    if (moved) *rec = range_pack(b, e, next);
     dw = (uint32_t)(b - a);
   }
-  if (dw > (uint32_t)RANGE_BIG) {                     // long part: leave it to the whole block
-    const uint32_t slot = atomicAdd(s_qn, 1u);
-    if (slot < (uint32_t)RANGE_QCAP) { s_qa[slot] = a; s_qdw[slot] = dw; dw = 0; }
-  }
-  uint32_t inc = dw;                                  // inclusive scan of the part lengths
-  #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
-    if (lane >= d) inc += t;
-  }
-  const uint32_t tot = __shfl_sync(NLP_FULL, inc, 31);
-  for (uint32_t sb = 0; sb < tot; sb += 32u) {
-    const uint32_t idx = sb + lane;
-    int j = 0;                                        // smallest j with inc[j] > idx
-    #pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-      const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
-      if (x <= idx) j += step;
-    }
-    const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
-    const uint32_t dwj = __shfl_sync(NLP_FULL, dw, j);
-    const unsigned long long aj = __shfl_sync(NLP_FULL, a, j);
-    if (idx < tot) {
-      const uint32_t v = __ldg(keys + aj + (idx - (incj - dwj)));
-      atomicAdd(cnt + (v - vlo), 1u);                                // inc/predict.hxx:156-158
-    }
-  }
-}
-
-// The queued long parts (entry t of the queue in s_wb[t] / s_inc[t], t < qn <= RANGE_THREADS) laid
-// end to end and dealt to the threads of the whole block.  k_range is only used when
-// 1024 * maxdeg < 2^32, so the scan cannot overflow.
-__device__ __forceinline__ void range_queue(const Params& p, uint32_t qn, uint32_t vlo, uint32_t* cnt,
-                                            uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
-  const uint32_t* __restrict__ keys = p.g.keys;
-  const uint32_t dw = threadIdx.x < qn ? s_inc[threadIdx.x] : 0u;   // own slot: read before the scan rewrites it
-  block_scan_u32(dw, s_inc, s_wsum);
+  s_wb[threadIdx.x] = a;
+  block_scan_u32(dw, s_inc, s_wsum);                  // k_range is only used when 1024 * maxdeg < 2^32
   const uint32_t tot = s_inc[RANGE_THREADS - 1];
   for (uint32_t idx = threadIdx.x; idx < tot; idx += RANGE_THREADS) {
     uint32_t lo = 0, hi = RANGE_THREADS - 1;          // smallest j with s_inc[j] > idx
@@ -741,27 +728,96 @@ __device__ __forceinline__ void range_queue(const Params& p, uint32_t qn, uint32
     }
     const uint32_t before = lo ? s_inc[lo - 1] : 0u;
     const uint32_t v = __ldg(keys + s_wb[lo] + (idx - before));
-    atomicAdd(cnt + (v - vlo), 1u);                                  // inc/predict.hxx:156-158
+    range_count<HALF>(cnt, v - vlo);
   }
   __syncthreads();
+}
+
+// All windows of one source.  HALF = 16-bit counters, two per word, so a window spans 2 * C
+// vertices and the source needs half the windows (half the (row, window) visits): valid while no
+// count can reach 2^15, i.e. deg(u) < 32768 (a count is at most min(deg u, deg v)); bit 15 of a
+// half is the "touched, then zeroed" mark.  Returns what this thread emitted.
+template <bool HALF>
+__device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, uint64_t ub, uint32_t du, const FirstHop& f,
+                                                 uint32_t C, uint4* rec, uint32_t* cnt, uint32_t* s_inc,
+                                                 unsigned long long* s_wb, uint32_t* s_wsum, Tally& tally) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const uint32_t* __restrict__ keys = p.g.keys;
+  const uint32_t span = HALF ? 2u * C : C;            // vertices per window
+  uint32_t emitted = 0;
+  for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += span) {
+    const uint32_t vlo = (uint32_t)lo64;
+    const uint32_t vhi = (uint32_t)(lo64 + span < p.g.S ? lo64 + span : p.g.S);
+    const bool first = lo64 == (uint64_t)u + 1;
+    for (uint32_t c = 0; c < f.npieces; ++c) {
+      const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
+      const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
+      for (uint32_t base = 0; base < pc; base += RANGE_THREADS) {
+        const uint32_t i = base + tid;
+        const bool has = i < pc;
+        const uint64_t ci = (uint64_t)c * CHUNK + i;
+        range_batch<HALF>(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, rec + ci, cnt, s_inc, s_wb, s_wsum);
+      }
+    }
+    {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
+      const uint32_t a = lower_bound_row(keys, ub, du, vlo);
+      const uint32_t b = a + lower_bound_row(keys, ub + a, du - a, vhi);
+      for (uint32_t i = a + tid; i < b; i += blockDim.x) {
+        const uint32_t x = __ldg(keys + ub + i) - vlo;
+        if (HALF) {   // neighbours share words: atomics, one half each
+          const uint32_t sh = (x & 1u) * 16u;
+          if ((cnt[x >> 1] >> sh) & 0xffffu) {
+            atomicAnd(cnt + (x >> 1), ~(0x7fffu << sh));
+            atomicOr(cnt + (x >> 1), 0x8000u << sh);
+          }
+        } else {
+          if (cnt[x] != 0u) cnt[x] = RANGE_ZEROED;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t len = vhi - vlo;
+    if (HALF) {
+      const uint32_t words = (len + 1u) >> 1;
+      for (uint32_t sb = (uint32_t)warp * 32u; sb < words; sb += (uint32_t)nw * 32u) {
+        const uint32_t i = sb + lane;
+        uint32_t c2 = 0;
+        if (i < words) { c2 = cnt[i]; if (c2) cnt[i] = 0u; }
+        if (__any_sync(NLP_FULL, c2 != 0u)) {
+          const uint32_t c0 = c2 & 0xffffu, c1 = c2 >> 16;
+          if (__any_sync(NLP_FULL, c0 != 0u))
+            emitted += score_and_emit(p, c0 != 0u, u, du, vlo + 2u * i, c0 & 0x7fffu, 0.0f, tally);
+          if (__any_sync(NLP_FULL, c1 != 0u))
+            emitted += score_and_emit(p, c1 != 0u, u, du, vlo + 2u * i + 1u, c1 & 0x7fffu, 0.0f, tally);
+        }
+      }
+    } else {
+      for (uint32_t sb = (uint32_t)warp * 32u; sb < len; sb += (uint32_t)nw * 32u) {
+        const uint32_t i = sb + lane;
+        uint32_t c = 0;
+        if (i < len) { c = cnt[i]; if (c) cnt[i] = 0u; }
+        if (__any_sync(NLP_FULL, c != 0u))
+          emitted += score_and_emit(p, c != 0u, u, du, vlo + i, c & ~RANGE_ZEROED, 0.0f, tally);
+      }
+    }
+    __syncthreads();
+  }
+  return emitted;
 }
 
 template <bool ADMIT>
 __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
                                                              uint32_t* __restrict__ deferred, uint32_t C,
                                                              unsigned long long* __restrict__ cursors, uint64_t cursor_stride) {
-  extern __shared__ uint32_t cnt[];                   // C counters
-  unsigned long long* cur = cursors + (uint64_t)blockIdx.x * 2 * cursor_stride;   // [cursor_stride] positions
-  unsigned long long* end = cur + cursor_stride;                                  // [cursor_stride] row ends
+  extern __shared__ uint32_t cnt[];                   // C counters (or 2 * C half-word counters)
+  uint4* rec = reinterpret_cast<uint4*>(cursors + (uint64_t)blockIdx.x * 2 * cursor_stride);   // [cursor_stride] row records
   __shared__ unsigned long long s_wb[RANGE_THREADS];
   __shared__ uint32_t s_inc[RANGE_THREADS];
   __shared__ uint32_t s_wsum[32];
   __shared__ int s_go;
   __shared__ uint32_t s_qi;
-  __shared__ uint32_t s_ticket, s_qn;                 // chunk tickets / queued long parts of the current window
   __shared__ unsigned int s_emitted;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const uint32_t* __restrict__ keys = p.g.keys;
+  const int tid = threadIdx.x, lane = tid & 31;
   Tally tally;
   for (uint32_t i = tid; i < C; i += blockDim.x) cnt[i] = 0u;
   if (tid == 0) s_emitted = 0;
@@ -784,55 +840,9 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
     const uint64_t ub = __ldg(p.g.off + u);
     const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
     const FirstHop f = first_hop(p, u, ub, du);
-    uint32_t emitted = 0;
-    for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += C) {
-      const uint32_t vlo = (uint32_t)lo64;
-      const uint32_t vhi = (uint32_t)(lo64 + C < p.g.S ? lo64 + C : p.g.S);
-      const bool first = lo64 == (uint64_t)u + 1;
-      if (tid == 0) { s_ticket = 0u; s_qn = 0u; }
-      __syncthreads();
-      // chunks of 32 consecutive first-hop entries; a long first-hop row is a sequence of pieces,
-      // CHUNK entries apart (frontier.cuh), each with its own count
-      const uint32_t per_piece = f.npieces == 1 ? (f.single_count + 31u) / 32u : CHUNK / 32u;
-      const uint32_t nchunks = f.npieces * per_piece;
-      for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&s_ticket, 1u);
-        t = __shfl_sync(NLP_FULL, t, 0);
-        if (t >= nchunks) break;
-        const uint32_t c = t / per_piece, k = t - c * per_piece;
-        const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
-        if (k * 32u >= pc) continue;
-        const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
-        const uint32_t i = k * 32u + lane;
-        const bool has = i < pc;
-        const uint64_t ci = (uint64_t)c * CHUNK + i;
-        range_warp_chunk(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, cur + ci, end + ci, cnt, s_wb, s_inc, &s_qn);
-      }
-      __syncthreads();
-      {
-        const uint32_t qn = s_qn < (uint32_t)RANGE_QCAP ? s_qn : (uint32_t)RANGE_QCAP;   // same value in every thread
-        if (qn) range_queue(p, qn, vlo, cnt, s_inc, s_wb, s_wsum);
-      }
-      {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
-        const uint32_t a = lower_bound_row(keys, ub, du, vlo);
-        const uint32_t b = a + lower_bound_row(keys, ub + a, du - a, vhi);
-        for (uint32_t i = a + tid; i < b; i += blockDim.x) {
-          const uint32_t x = __ldg(keys + ub + i) - vlo;
-          if (cnt[x] != 0u) cnt[x] = RANGE_ZEROED;
-        }
-      }
-      __syncthreads();
-      const uint32_t len = vhi - vlo;
-      for (uint32_t sb = (uint32_t)warp * 32u; sb < len; sb += (uint32_t)nw * 32u) {
-        const uint32_t i = sb + lane;
-        uint32_t c = 0;
-        if (i < len) { c = cnt[i]; if (c) cnt[i] = 0u; }
-        if (__any_sync(NLP_FULL, c != 0u))
-          emitted += score_and_emit(p, c != 0u, u, du, vlo + i, c & ~RANGE_ZEROED, 0.0f, tally);
-      }
-      __syncthreads();
-    }
+    const uint32_t emitted = (du < 32768u && p.range_half)
+        ? range_source<true>(p, u, ub, du, f, C, rec, cnt, s_inc, s_wb, s_wsum, tally)
+        : range_source<false>(p, u, ub, du, f, C, rec, cnt, s_inc, s_wb, s_wsum, tally);
     if (ADMIT) {
       if (lane == 0 && emitted) atomicAdd(&s_emitted, emitted);
       __syncthreads();
