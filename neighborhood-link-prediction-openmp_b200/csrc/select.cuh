@@ -133,25 +133,16 @@ __host__ __device__ constexpr uint32_t scatter_smem_bytes(bool has3) {
   return SORT_TILE * 4u * (has3 ? 3u : 2u) + SORT_TILE * 2u + SORT_WARPS * 256u * 4u + 256u * 4u + SORT_WARPS * 4u + 16u;
 }
 
-// Lanes whose 8-bit digit equals this lane's (bit 8 set = lane holds nothing and matches nobody).
-// Eight ballots instead of match.any: MATCH.ANY measured ~270 cycles of issue per SM sub-partition
-// on B200 (ncu: 40 % of k_scatter's stall samples sat behind it), ballots pipeline.
-__device__ __forceinline__ unsigned match_digit(uint32_t d) {
-  unsigned m = __ballot_sync(NLP_FULL, d < 256u);
-  #pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    const unsigned bal = __ballot_sync(NLP_FULL, (d >> b) & 1u);
-    m &= ((d >> b) & 1u) ? bal : ~bal;
-  }
-  return d < 256u ? m : 0u;
-}
-
 // Stable scatter of one tile.  The tile's arrays arrive in shared memory by TMA bulk copies (no
 // registers, whole tile in flight at once; the buffers are padded to a multiple of SORT_TILE so a
-// full tile can always be read).  Ranks inside a warp come from match.any, warps are ordered by a
-// shared-memory scan, tiles by the scanned count matrix.  A tile-local permutation sorts the tile
-// by digit, so records leave in tile order and every digit's records form one contiguous run: a
-// warp store touches the 2-3 runs it straddles instead of 32 different lines.
+// full tile can always be read).  Ranks inside a warp come from digit masks: every lane ORs its
+// bit into a warp-private word per digit (shared memory) and reads the word back -- one atomic and
+// one load per record.  (The first version built the mask from nine ballots and spent 60 % of the
+// kernel's instructions -- LOP3 / ISETP / SEL / SHF / VOTE on the ncu source page -- doing so;
+// MATCH.ANY itself measured ~270 cycles of issue per SM sub-partition on B200.)  Warps are ordered
+// by a shared-memory scan, tiles by the scanned count matrix.  A tile-local permutation sorts the
+// tile by digit, so records leave in tile order and every digit's records form one contiguous
+// run: a warp store touches the 2-3 runs it straddles instead of 32 different lines.
 template <bool HAS3>
 __global__ void __launch_bounds__(SORT_THREADS, HAS3 ? 3 : 4)
 k_scatter(const uint32_t* __restrict__ iu, const uint32_t* __restrict__ iv, const uint32_t* __restrict__ is,
@@ -174,7 +165,10 @@ k_scatter(const uint32_t* __restrict__ iu, const uint32_t* __restrict__ iv, cons
     bulk_g2s(raw + SORT_TILE, iv + tbase, SORT_TILE * 4, s_bar);
     if (HAS3) bulk_g2s(raw + 2 * SORT_TILE, is + tbase, SORT_TILE * 4, s_bar);
   }
-  for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
+  // digit masks of the ranking phase; the permutation (written after that phase) reuses the space
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_perm);          // [SORT_WARPS][256] == SORT_TILE * 2 bytes
+  static_assert(SORT_WARPS * 256 * 4 == SORT_TILE * 2, "digit masks alias the tile permutation");
+  for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) { (&s_hist[0][0])[i] = 0; s_mask[i] = 0; }
   __syncthreads();
   mbar_wait(s_bar, 0);
   const uint32_t tile_n = (uint32_t)(n - tbase < (uint64_t)SORT_TILE ? n - tbase : (uint64_t)SORT_TILE);
@@ -182,31 +176,22 @@ k_scatter(const uint32_t* __restrict__ iu, const uint32_t* __restrict__ iv, cons
   const uint32_t* kw = word == 0 ? raw + SORT_TILE : word == 1 ? raw : raw + 2 * SORT_TILE;
   uint32_t pre[SORT_ROUNDS];
   const unsigned lt = (1u << lane) - 1u;
-  // match.any has a long latency: issue a batch of independent matches first, then walk the
-  // (serial) warp-private counter updates
-  constexpr int BATCH = 8;
+  uint32_t* my_mask = s_mask + warp * 256;
   #pragma unroll
-  for (int rb = 0; rb < SORT_ROUNDS; rb += BATCH) {
-    uint32_t dd[BATCH];
-    unsigned mm[BATCH];
-    #pragma unroll
-    for (int q = 0; q < BATCH; ++q) {
-      const uint32_t idx = (uint32_t)warp * (32 * SORT_ROUNDS) + (rb + q) * 32 + lane;
-      uint32_t x = kw[idx];
-      if (word == 2) x = desc_key(x);
-      dd[q] = idx < tile_n ? ((x >> shift) & 255u) : 256u;
-      mm[q] = match_digit(dd[q]);
-    }
-    #pragma unroll
-    for (int q = 0; q < BATCH; ++q) {
-      const bool valid = dd[q] < 256u;
-      const uint32_t d = dd[q] & 255u;
-      const uint32_t before = valid ? s_hist[warp][d] : 0u;
-      pre[rb + q] = (d << 16) | (before + __popc(mm[q] & lt));     // digit and rank inside (warp, digit)
-      __syncwarp();
-      if (valid && (__ffs(mm[q]) - 1) == lane) s_hist[warp][d] = before + __popc(mm[q]);
-      __syncwarp();
-    }
+  for (int r = 0; r < SORT_ROUNDS; ++r) {
+    const uint32_t idx = (uint32_t)warp * (32 * SORT_ROUNDS) + r * 32 + lane;
+    uint32_t x = kw[idx];
+    if (word == 2) x = desc_key(x);
+    const bool valid = idx < tile_n;
+    const uint32_t d = (x >> shift) & 255u;
+    if (valid) atomicOr(my_mask + d, 1u << lane);
+    __syncwarp();
+    const unsigned m = valid ? *reinterpret_cast<volatile uint32_t*>(my_mask + d) : 0u;   // lanes holding digit d
+    const uint32_t before = valid ? s_hist[warp][d] : 0u;
+    pre[r] = (d << 16) | (before + __popc(m & lt));                // digit and rank inside (warp, digit)
+    __syncwarp();
+    if (valid && (__ffs(m) - 1) == lane) { s_hist[warp][d] = before + __popc(m); my_mask[d] = 0u; }
+    __syncwarp();
   }
   __syncthreads();
   {   // thread t owns digit t
