@@ -799,29 +799,56 @@ __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, ui
       }
     }
     __syncthreads();
+    // Scoring.  The touched counters are sparse -- ncu, R-MAT 18 IHub: 4 of 32 lanes of the scan held
+    // a candidate, and the warp-wide scoring call per scan step was 60 % of the kernel's
+    // instructions -- so every warp first COMPACTS the touched vertices of its scan steps into a
+    // 64-entry staging list (the shared memory of the batch phase, idle now) and scores 32 of
+    // them at a time with all lanes busy.  The count is read back from the counter when the
+    // vertex is scored; the window's counters are cleared together afterwards.
     const uint32_t len = vhi - vlo;
-    if (HALF) {
-      const uint32_t words = (len + 1u) >> 1;
-      for (uint32_t sb = (uint32_t)warp * 32u; sb < words; sb += (uint32_t)nw * 32u) {
+    {
+      uint32_t* stage = reinterpret_cast<uint32_t*>(s_wb) + warp * 64;      // s_wb: 1024 x 8 B = 32 warps x 64 x 4 B
+      const unsigned lt = (1u << lane) - 1u;
+      uint32_t fill = 0;                                                    // pending vertices of this warp (uniform)
+      auto score32 = [&](bool has) {
+        uint32_t v = 0, c = 0;
+        if (has) {
+          v = stage[lane];
+          const uint32_t x = v - vlo;
+          c = HALF ? ((cnt[x >> 1] >> ((x & 1u) * 16u)) & 0x7fffu) : (cnt[x] & ~RANGE_ZEROED);
+        }
+        emitted += score_and_emit(p, has, u, du, v, c, 0.0f, tally);
+      };
+      auto push = [&](bool has, uint32_t v) {
+        const unsigned m = __ballot_sync(NLP_FULL, has);
+        if (!m) return;
+        if (has) stage[fill + __popc(m & lt)] = v;
+        fill += (uint32_t)__popc(m);
+        __syncwarp();
+        if (fill >= 32u) {
+          score32(true);
+          const uint32_t rest = fill - 32u;
+          const uint32_t t = lane < rest ? stage[32 + lane] : 0u;
+          __syncwarp();
+          if (lane < rest) stage[lane] = t;
+          fill = rest;
+          __syncwarp();
+        }
+      };
+      const uint32_t slots = HALF ? (len + 1u) >> 1 : len;
+      for (uint32_t sb = (uint32_t)warp * 32u; sb < slots; sb += (uint32_t)nw * 32u) {
         const uint32_t i = sb + lane;
-        uint32_t c2 = 0;
-        if (i < words) { c2 = cnt[i]; if (c2) cnt[i] = 0u; }
-        if (__any_sync(NLP_FULL, c2 != 0u)) {
-          const uint32_t c0 = c2 & 0xffffu, c1 = c2 >> 16;
-          if (__any_sync(NLP_FULL, c0 != 0u))
-            emitted += score_and_emit(p, c0 != 0u, u, du, vlo + 2u * i, c0 & 0x7fffu, 0.0f, tally);
-          if (__any_sync(NLP_FULL, c1 != 0u))
-            emitted += score_and_emit(p, c1 != 0u, u, du, vlo + 2u * i + 1u, c1 & 0x7fffu, 0.0f, tally);
+        const uint32_t c = i < slots ? cnt[i] : 0u;
+        if (HALF) {
+          push((c & 0xffffu) != 0u, vlo + 2u * i);
+          push((c >> 16) != 0u, vlo + 2u * i + 1u);
+        } else {
+          push(c != 0u, vlo + i);
         }
       }
-    } else {
-      for (uint32_t sb = (uint32_t)warp * 32u; sb < len; sb += (uint32_t)nw * 32u) {
-        const uint32_t i = sb + lane;
-        uint32_t c = 0;
-        if (i < len) { c = cnt[i]; if (c) cnt[i] = 0u; }
-        if (__any_sync(NLP_FULL, c != 0u))
-          emitted += score_and_emit(p, c != 0u, u, du, vlo + i, c & ~RANGE_ZEROED, 0.0f, tally);
-      }
+      if (fill) score32((uint32_t)lane < fill);
+      __syncthreads();                                                      // every warp has read its counts
+      for (uint32_t i = tid; i < slots; i += blockDim.x) cnt[i] = 0u;
     }
     __syncthreads();
   }
