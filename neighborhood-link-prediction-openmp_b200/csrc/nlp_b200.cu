@@ -79,7 +79,7 @@ struct nlp_handle {
   DevBuf cu[2], cv[2], cs[2];
   uint64_t cand_cap = 0;
   // dense spill tables
-  DevBuf tables, touched, range_cursors;
+  DevBuf tables, touched, range_cursors, range_touched;
   // select / sort scratch
   DevBuf counts, totals, hist, sel, cursor2;
   DevBuf oc_counts, oc_off;                  // ordered compaction (pair path top-K)
@@ -506,8 +506,11 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
     // per block: row cursor + row end for every first-hop entry of its current source
     const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
     NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * 2 * stride * 8));
+    // per block: the vertices of its current window that have a count (at most 2 * RANGE_COUNTERS)
+    NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * 2 * RANGE_COUNTERS * 4));
     k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS,
-                                                             (unsigned long long*)h->range_cursors.p, stride);
+                                                             (unsigned long long*)h->range_cursors.p, stride,
+                                                             (uint32_t*)h->range_touched.p);
     NLP_LAUNCHED(h);
     return NLP_OK;
   }
@@ -1017,7 +1020,7 @@ int nlp_destroy(nlp_handle* h) {
   for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
-  release(h->tables); release(h->touched); release(h->range_cursors); release(h->counts); release(h->totals); release(h->hist);
+  release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->counts); release(h->totals); release(h->hist);
   release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
   release(h->truth_key); release(h->truth_tmp); release(h->eval_ctr);
   if (h->ev_eval0) cudaEventDestroy(h->ev_eval0);

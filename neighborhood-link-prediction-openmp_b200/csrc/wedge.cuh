@@ -665,9 +665,12 @@ __device__ __forceinline__ unsigned long long gallop_to(const uint32_t* __restri
 // HALF: two 16-bit counters per word (see k_range); the halves cannot carry into each other
 // because a count never exceeds deg(u) < 2^15.
 template <bool HALF>
-__device__ __forceinline__ void range_count(uint32_t* cnt, uint32_t x) {
-  if (HALF) atomicAdd(cnt + (x >> 1), (x & 1u) ? 0x10000u : 1u);
-  else atomicAdd(cnt + x, 1u);                        // inc/predict.hxx:156-158
+__device__ __forceinline__ bool range_count(uint32_t* cnt, uint32_t x) {   // true: first wedge that reaches this vertex
+  if (HALF) {
+    const uint32_t sh = (x & 1u) * 16u;
+    return ((atomicAdd(cnt + (x >> 1), 1u << sh) >> sh) & 0xffffu) == 0u;
+  }
+  return atomicAdd(cnt + x, 1u) == 0u;                // inc/predict.hxx:156-158
 }
 
 // Wedges behind up to RANGE_THREADS first-hop entries (thread t holds entry t) whose v lies in
@@ -687,7 +690,7 @@ __device__ __forceinline__ uint4 range_pack(unsigned long long pos, unsigned lon
 
 template <bool HALF>
 __device__ __forceinline__ void range_batch(const Params& p, bool has, bool first, uint32_t w, uint32_t vlo, uint32_t vhi,
-                                            uint4* rec, uint32_t* cnt,
+                                            uint4* rec, uint32_t* cnt, uint32_t* touched, uint32_t* s_tn,
                                             uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
   const uint32_t* __restrict__ keys = p.g.keys;
   unsigned long long a = 0;
@@ -749,8 +752,8 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, bool firs
       #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = (c0 + (uint32_t)(h + k) < tot) ? __ldg(keys + addr[k]) : 0u;
       #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c0 + (uint32_t)(h + k) < tot) range_count<HALF>(cnt, v[k] - vlo);
+      for (int k = 0; k < 4; ++k)     // the first wedge that reaches a vertex also lists it for the scoring phase
+        if (c0 + (uint32_t)(h + k) < tot && range_count<HALF>(cnt, v[k] - vlo)) touched[atomicAdd(s_tn, 1u)] = v[k];
     }
   }
   __syncthreads();
@@ -762,8 +765,8 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, bool firs
 // half is the "touched, then zeroed" mark.  Returns what this thread emitted.
 template <bool HALF>
 __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, uint64_t ub, uint32_t du, const FirstHop& f,
-                                                 uint32_t C, uint4* rec, uint32_t* cnt, uint32_t* s_inc,
-                                                 unsigned long long* s_wb, uint32_t* s_wsum, Tally& tally) {
+                                                 uint32_t C, uint4* rec, uint32_t* cnt, uint32_t* touched, uint32_t* s_tn,
+                                                 uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum, Tally& tally) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const uint32_t* __restrict__ keys = p.g.keys;
   const uint32_t span = HALF ? 2u * C : C;            // vertices per window
@@ -779,7 +782,7 @@ __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, ui
         const uint32_t i = base + tid;
         const bool has = i < pc;
         const uint64_t ci = (uint64_t)c * CHUNK + i;
-        range_batch<HALF>(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, rec + ci, cnt, s_inc, s_wb, s_wsum);
+        range_batch<HALF>(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, rec + ci, cnt, touched, s_tn, s_inc, s_wb, s_wsum);
       }
     }
     {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
@@ -799,56 +802,29 @@ __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, ui
       }
     }
     __syncthreads();
-    // Scoring.  The touched counters are sparse -- ncu, R-MAT 18 IHub: 4 of 32 lanes of the scan held
-    // a candidate, and the warp-wide scoring call per scan step was 60 % of the kernel's
-    // instructions -- so every warp first COMPACTS the touched vertices of its scan steps into a
-    // 64-entry staging list (the shared memory of the batch phase, idle now) and scores 32 of
-    // them at a time with all lanes busy.  The count is read back from the counter when the
-    // vertex is scored; the window's counters are cleared together afterwards.
-    const uint32_t len = vhi - vlo;
+    // Scoring walks the list of touched vertices (appended by the first wedge that reached each),
+    // 32 at a time with all lanes busy, and reads the count back from the counter.  (Scanning the
+    // window's counters instead -- 12 % of them touched at R-MAT 18 IHub -- was a third of the
+    // kernel's instructions, and scoring straight from the scan, 4 of 32 lanes busy, 60 %: ncu.)
+    // The window's counters are cleared together afterwards.
     {
-      uint32_t* stage = reinterpret_cast<uint32_t*>(s_wb) + warp * 64;      // s_wb: 1024 x 8 B = 32 warps x 64 x 4 B
-      const unsigned lt = (1u << lane) - 1u;
-      uint32_t fill = 0;                                                    // pending vertices of this warp (uniform)
-      auto score32 = [&](bool has) {
+      const uint32_t tn = *s_tn;
+      for (uint32_t sb = (uint32_t)warp * 32u; sb < tn; sb += (uint32_t)nw * 32u) {
+        const uint32_t i = sb + lane;
+        const bool has = i < tn;
         uint32_t v = 0, c = 0;
         if (has) {
-          v = stage[lane];
+          v = __ldcg(touched + i);
           const uint32_t x = v - vlo;
           c = HALF ? ((cnt[x >> 1] >> ((x & 1u) * 16u)) & 0x7fffu) : (cnt[x] & ~RANGE_ZEROED);
         }
         emitted += score_and_emit(p, has, u, du, v, c, 0.0f, tally);
-      };
-      auto push = [&](bool has, uint32_t v) {
-        const unsigned m = __ballot_sync(NLP_FULL, has);
-        if (!m) return;
-        if (has) stage[fill + __popc(m & lt)] = v;
-        fill += (uint32_t)__popc(m);
-        __syncwarp();
-        if (fill >= 32u) {
-          score32(true);
-          const uint32_t rest = fill - 32u;
-          const uint32_t t = lane < rest ? stage[32 + lane] : 0u;
-          __syncwarp();
-          if (lane < rest) stage[lane] = t;
-          fill = rest;
-          __syncwarp();
-        }
-      };
-      const uint32_t slots = HALF ? (len + 1u) >> 1 : len;
-      for (uint32_t sb = (uint32_t)warp * 32u; sb < slots; sb += (uint32_t)nw * 32u) {
-        const uint32_t i = sb + lane;
-        const uint32_t c = i < slots ? cnt[i] : 0u;
-        if (HALF) {
-          push((c & 0xffffu) != 0u, vlo + 2u * i);
-          push((c >> 16) != 0u, vlo + 2u * i + 1u);
-        } else {
-          push(c != 0u, vlo + i);
-        }
       }
-      if (fill) score32((uint32_t)lane < fill);
       __syncthreads();                                                      // every warp has read its counts
+      const uint32_t len = vhi - vlo;
+      const uint32_t slots = HALF ? (len + 1u) >> 1 : len;
       for (uint32_t i = tid; i < slots; i += blockDim.x) cnt[i] = 0u;
+      if (tid == 0) *s_tn = 0u;
     }
     __syncthreads();
   }
@@ -858,8 +834,10 @@ __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, ui
 template <bool ADMIT>
 __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
                                                              uint32_t* __restrict__ deferred, uint32_t C,
-                                                             unsigned long long* __restrict__ cursors, uint64_t cursor_stride) {
+                                                             unsigned long long* __restrict__ cursors, uint64_t cursor_stride,
+                                                             uint32_t* __restrict__ touched_all) {
   extern __shared__ uint32_t cnt[];                   // C counters (or 2 * C half-word counters)
+  uint32_t* touched = touched_all + (uint64_t)blockIdx.x * 2u * C;          // vertices of the current window with a count
   uint4* rec = reinterpret_cast<uint4*>(cursors + (uint64_t)blockIdx.x * 2 * cursor_stride);   // [cursor_stride] row records
   __shared__ unsigned long long s_wb[RANGE_THREADS];
   __shared__ uint32_t s_inc[RANGE_THREADS];
@@ -867,10 +845,11 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
   __shared__ int s_go;
   __shared__ uint32_t s_qi;
   __shared__ unsigned int s_emitted;
+  __shared__ uint32_t s_tn;                           // entries of touched[]
   const int tid = threadIdx.x, lane = tid & 31;
   Tally tally;
   for (uint32_t i = tid; i < C; i += blockDim.x) cnt[i] = 0u;
-  if (tid == 0) s_emitted = 0;
+  if (tid == 0) { s_emitted = 0; s_tn = 0u; }
   __syncthreads();
   for (;;) {
     if (tid == 0) s_qi = (uint32_t)atomicAdd(&p.ctr->queue[bin], 1ull);     // dynamic: sources differ by 1000x in work
@@ -891,8 +870,8 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
     const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
     const FirstHop f = first_hop(p, u, ub, du);
     const uint32_t emitted = (du < 32768u && p.range_half)
-        ? range_source<true>(p, u, ub, du, f, C, rec, cnt, s_inc, s_wb, s_wsum, tally)
-        : range_source<false>(p, u, ub, du, f, C, rec, cnt, s_inc, s_wb, s_wsum, tally);
+        ? range_source<true>(p, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally)
+        : range_source<false>(p, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally);
     if (ADMIT) {
       if (lane == 0 && emitted) atomicAdd(&s_emitted, emitted);
       __syncthreads();
