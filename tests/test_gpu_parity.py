@@ -170,6 +170,53 @@ def test_properties_at_scale(pred, nlp):
         assert r["first_hop"] == int(k.numel()) and r["wedges"] >= r["candidates"] >= r["kept"]
 
 
+def test_paths_agree_at_scale(nlp, monkeypatch):
+    """Independent code paths must give the same bits at a size no CPU oracle finishes quickly:
+    LHub through the source-centric kernels and through the pair path (R-MAT 20, D = 16), and IHub
+    common neighbours / Jaccard with word counters and with half-word counters in k_range
+    (R-MAT 18); the wedge counter equals sum of deg^2 (W(0))."""
+    import torch
+    g = nlp.graphs
+    o, k = g.rmat(20, 16, 43, permute=True, device="cuda")
+    o, k, rl, rh = g.remove_edges(o, k, 0.1, 1043)
+    K = int(rl.numel())
+    p = nlp.Predictor(0)
+    try:
+        p.set_graph_pointers(o.data_ptr(), k.data_ptr(), o.numel() - 1, device=True, keep=(o, k))
+        for m in ("JC", "AA", "LHN"):
+            res = []
+            for path in (SOURCE_PATH, PAIR_PATH):
+                p.set_path(path)
+                r = p.predict(m, 16, max_edges=K)
+                assert r["path"] == path
+                res.append((r, p.fetch(r["count"])))
+            assert parity.compare(res[0][1], res[1][1], "paths %s" % m) is None
+            for c in ("wedges", "candidates", "kept", "eligible_first_hop"):
+                assert res[0][0][c] == res[1][0][c], (m, c)
+    finally:
+        p.close()
+    o, k = g.rmat(18, 16, 42, device="cuda")
+    o, k, rl, rh = g.remove_edges(o, k, 0.01, 1042)
+    K = int(rl.numel())
+    deg = (o[1:] - o[:-1])
+    want_wedges = int((deg * deg).sum())
+    out = {}
+    for half in ("1", "0"):
+        monkeypatch.setenv("NLP_B200_RANGE_HALF", half)
+        p = nlp.Predictor(0)
+        try:
+            p.set_graph_pointers(o.data_ptr(), k.data_ptr(), o.numel() - 1, device=True, keep=(o, k))
+            for m in ("CN", "JC"):
+                r = p.predict(m, 0, max_edges=K)
+                assert r["wedges"] == want_wedges and r["bin_sources"][6] > 0
+                out[(half, m)] = (r, p.fetch(r["count"]))
+        finally:
+            p.close()
+    for m in ("CN", "JC"):
+        assert parity.compare(out[("1", m)][1], out[("0", m)][1], "half vs word counters %s" % m) is None
+        assert out[("1", m)][0]["candidates"] == out[("0", m)][0]["candidates"]
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
