@@ -13,6 +13,11 @@ PREDICT_LINKS does (main.cxx:50).  Metric: predicted edges per second of whole-j
   value : graph already resident in HBM, results left in HBM (device time, CUDA events).
   e2e   : the same step through the C ABI with HOST buffers -- nlp_set_graph() from pinned host
           memory and nlp_fetch() of every measure's (u, v, score) list inside the timed region.
+
+N > 1 (torchrun, one rank per GPU, CSR replicated): by default every rank runs a whole step on its
+own batch -- an independent random removal, as main.cxx:163 draws REPEAT_BATCH of them -- with no
+data-path collective ("scaling": "weak"); --shard measures deals the nine predictions of ONE batch
+to the ranks, --shard sources partitions the sources of every prediction (all-gather + merge).
 """
 import argparse
 import json
