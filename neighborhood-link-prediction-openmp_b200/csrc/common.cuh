@@ -67,7 +67,7 @@ struct Params {
   uint32_t D;          // MINDEGREE1 (0 = IHub)
   uint32_t F2;         // MAXFACTOR2
   uint32_t coop;       // count measures: block-cooperative wedge streaming (maxdeg small enough)
-  uint32_t range_half; // k_range: 16-bit counters (windows twice as wide) for sources with deg < 2^15
+  uint32_t range_half; // k_range: sources with deg < range_half count in half words (windows twice as wide); 0 = never
   int      measure;
   float    min_score;
   const uint32_t* elig;     // LHub eligibility bitmask (bit w = deg(w) <= D), null for IHub

@@ -44,6 +44,37 @@ __global__ void __launch_bounds__(256) k_chunk_fill(const uint32_t* __restrict__
   }
 }
 
+// Largest number of equal entries in one row (1 for a simple graph; rows are sorted, so equal
+// entries are adjacent).  The reference counts ENTRIES, so with multiset rows a pair's count can
+// reach deg(u) times this number -- k_range's half-word counters need the bound.  One warp per 32
+// consecutive entries; the row of the first by bisection, the lanes walk forward from there.
+__global__ void __launch_bounds__(256) k_max_multiplicity(DevGraph g, uint64_t M, unsigned int* __restrict__ out) {
+  const uint32_t* __restrict__ keys = g.keys;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t best = 1;
+  for (uint64_t base = warp0 * 32u; base < M; base += nwarps * 32u) {
+    uint32_t lo = 0, hi = g.S;                       // off[lo] <= base < off[hi]
+    while (lo + 1 < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldg(g.off + mid) <= base) lo = mid; else hi = mid;
+    }
+    const uint64_t e = base + lane;
+    if (e >= M) continue;
+    uint32_t u = lo;
+    while (__ldg(g.off + u + 1) <= e) ++u;
+    const uint64_t ub = __ldg(g.off + u), ue = __ldg(g.off + u + 1);
+    const uint32_t w = __ldg(keys + e);
+    if (e > ub && __ldg(keys + e - 1) == w) continue;          // measured at the first entry of the run
+    uint32_t mult = 1;
+    while (e + mult < ue && __ldg(keys + e + mult) == w) ++mult;
+    best = mult > best ? mult : best;
+  }
+  best = __reduce_max_sync(NLP_FULL, best);
+  if (lane == 0 && best > 1u) atomicMax(out, best);
+}
+
 // One thread builds one 32-bit word of the mask.
 __global__ void __launch_bounds__(256) k_elig(const uint32_t* __restrict__ deg, uint32_t S, uint32_t D,
                                               uint32_t* __restrict__ bits) {
@@ -235,7 +266,8 @@ struct BinLists { uint32_t* list[NBINS]; };
 
 // flt: the float measures send every source above the 1K-slot hash bin to the sort-based path
 // range_c: counters per window of k_range (0 = that path is off); room = S-1-u
-__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, bool flt, uint32_t range_c, uint32_t range_div, uint32_t room) {
+__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, bool flt, uint32_t range_c, uint32_t range_div,
+                                          uint32_t half_deg, uint32_t room) {
   if (du <= LONG_ROW) {
     if (work <= 8u) return 0;
     if (work <= 32u) return 1;
@@ -248,16 +280,17 @@ __device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_
     // Every window costs a scan of the counters plus a cursor step per first-hop row; the dense
     // table pays an HBM sector update per wedge (~47 SM-cycles against ~4 for a shared-memory
     // atomic, R-MAT 18/20 IHub).  range_div weighs the per-row part (NLP_B200_RANGE_DIV).
-    // Bit 31 of range_div: sources with deg < 2^15 count in half words, their windows are twice as wide.
-    const unsigned long long rc = (unsigned long long)range_c << (((range_div >> 31) && du < 32768u) ? 1 : 0);
+    // Sources with deg < half_deg count in half words: their windows are twice as wide.
+    const unsigned long long rc = (unsigned long long)range_c << (du < half_deg ? 1 : 0);
     const unsigned long long passes = ((unsigned long long)room + rc - 1) / rc;
-    if ((unsigned long long)work >= passes * (256ull + du / (range_div & 0x7fffffffu))) return 6;
+    if ((unsigned long long)work >= passes * (256ull + du / range_div)) return 6;
   }
   return 5;
 }
 
 __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long long* __restrict__ work64, int rank, int world,
-                                             bool flt, uint32_t range_c, uint32_t range_div, uint32_t* __restrict__ work, BinLists bl, Counters* ctr) {
+                                             bool flt, uint32_t range_c, uint32_t range_div, uint32_t half_deg, uint32_t* __restrict__ work, BinLists bl,
+                                             Counters* ctr) {
   __shared__ unsigned long long s_cnt[NBINS], s_sum[NBINS], s_base[NBINS], s_max;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < NBINS) { s_cnt[threadIdx.x] = 0; s_sum[threadIdx.x] = 0; }
@@ -278,7 +311,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) { bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, room); need = bin < 2 ? w : bound; }
+        if (bound) { bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, half_deg, room); need = bin < 2 ? w : bound; }
       }
     }
     #pragma unroll
@@ -318,7 +351,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, room);
+        if (bound) bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, half_deg, room);
       }
     }
     #pragma unroll

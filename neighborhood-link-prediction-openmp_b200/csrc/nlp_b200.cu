@@ -47,6 +47,7 @@ struct nlp_handle {
   uint32_t S = 0;
   uint64_t M = 0;
   uint32_t maxdeg = 0;
+  uint32_t maxmult = 0;                      // largest multiplicity of an entry in a row; 0 = not measured yet
   bool has_graph = false;
   DevBuf deg, work, work64, elig, maxdeg_dev;
   DevBuf chunk_base, chunk_src, chunk_cnt;   // long rows (deg > LONG_ROW) cut into CHUNK-entry pieces
@@ -257,6 +258,7 @@ int finish_graph(nlp_handle* h) {
   h->M = m;
   h->maxdeg = md;
   h->gtable_n = 0;
+  h->maxmult = 0;
   h->sym_state = 0;
   h->pair_sizes.clear();
   clear_pair_cache(h);
@@ -726,6 +728,29 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   return NLP_OK;
 }
 
+// Sources of k_range with deg(u) below the returned limit may count in half words: a count is at
+// most deg(u) x (largest multiplicity of an entry in a row) and must stay below 2^15.  The
+// multiplicity is measured once per graph, the first time the range path is about to be used.
+int half_word_limit(nlp_handle* h, bool range_on, uint32_t* limit) {
+  *limit = 0;
+  if (!range_on || !h->range_half || range_cluster_size(h) > 1) return NLP_OK;
+  if (h->maxmult == 0) {
+    NLP_TRY(ensure(h, h->sym_flag, 32));
+    NLP_CUDA(h, cudaMemsetAsync((char*)h->sym_flag.p + 24, 0, 8, h->stream));
+    if (h->M) {
+      k_max_multiplicity<<<grid_for(h->M, 256, h->num_sms * 16), 256, 0, h->stream>>>(dev_graph(h), h->M,
+                                                                                       (unsigned int*)((char*)h->sym_flag.p + 24));
+      NLP_LAUNCHED(h);
+    }
+    unsigned int mm = 0;
+    NLP_CUDA(h, cudaMemcpyAsync(&mm, (char*)h->sym_flag.p + 24, 4, cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->maxmult = mm > 1u ? mm : 1u;
+  }
+  *limit = 32768u / h->maxmult;
+  return NLP_OK;
+}
+
 template <bool FLT>
 int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_buf, uint64_t* out_fill) {
   const uint32_t S = h->S;
@@ -781,8 +806,10 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   // count measures may send hub-heavy sources to the windowed shared-memory counters (k_range);
   // the float measures need the ordered single-warp accumulation of k_dense
   const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS * range_cluster_size(h) : 0u;
+  uint32_t half_deg = 0;
+  NLP_TRY(half_word_limit(h, range_c != 0u, &half_deg));
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
-                                                                  false, range_c, h->range_div | (h->range_half ? 0x80000000u : 0u), (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
+                                                                  false, range_c, h->range_div, half_deg, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -833,7 +860,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   Params p;
   p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
   p.coop = (h->maxdeg < (1u << 22) && h->coop_mode != 0) ? 1u : 0u;
-  p.range_half = h->range_half ? 1u : 0u;
+  p.range_half = half_deg;
   p.elig = lhub ? (const uint32_t*)h->elig.p : nullptr;
   p.ekeys = lhub ? (const uint32_t*)h->ekeys.p : nullptr;
   p.ecount = lhub ? (const uint32_t*)h->ecount.p : nullptr;

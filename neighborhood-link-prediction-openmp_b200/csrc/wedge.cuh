@@ -761,8 +761,10 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, bool firs
 
 // All windows of one source.  HALF = 16-bit counters, two per word, so a window spans 2 * C
 // vertices and the source needs half the windows (half the (row, window) visits): valid while no
-// count can reach 2^15, i.e. deg(u) < 32768 (a count is at most min(deg u, deg v)); bit 15 of a
-// half is the "touched, then zeroed" mark.  Returns what this thread emitted.
+// count can reach 2^15.  A count is at most deg(u) x (largest multiplicity of an entry in a row),
+// so the host allows it for deg(u) < 2^15 / that multiplicity (Params::range_half; the reference
+// counts entries, and rows may be multisets).  Bit 15 of a half is the "touched, then zeroed"
+// mark.  Returns what this thread emitted.
 template <bool HALF>
 __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, uint64_t ub, uint32_t du, const FirstHop& f,
                                                  uint32_t C, uint4* rec, uint32_t* cnt, uint32_t* touched, uint32_t* s_tn,
@@ -869,7 +871,7 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
     const uint64_t ub = __ldg(p.g.off + u);
     const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
     const FirstHop f = first_hop(p, u, ub, du);
-    const uint32_t emitted = (du < 32768u && p.range_half)
+    const uint32_t emitted = du < p.range_half
         ? range_source<true>(p, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally)
         : range_source<false>(p, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally);
     if (ADMIT) {
