@@ -3,6 +3,9 @@
 * ``oracle_predict``  -> oracle/liboracle.so   (plain-C restatement, oracle/nlp_oracle.c)
 * ``RefGraph``        -> oracle/_ref/libnlpref.so (UNMODIFIED reference templates compiled
                          from /root/reference by oracle/Makefile; see oracle/ref_driver.cxx)
+* ``oracle_edge_deletions`` / ``ref_edge_deletions`` -> the random edge removal that precedes the
+                         prediction (inc/batch.hxx), restated in oracle/batch_oracle.c and wrapped
+                         from the reference in oracle/ref_batch_driver.cxx
 
 Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs may import this module.  The product path never does.
@@ -51,6 +54,11 @@ def _load_oracle():
             C.c_float, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
             C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(OracleStats)]
         lib.nlp_oracle_free.argtypes = [C.c_void_p]
+        lib.nlp_oracle_edge_deletions.restype = C.c_int
+        lib.nlp_oracle_edge_deletions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.nlp_oracle_batch_free.argtypes = [C.c_void_p]
         _oracle = lib
     return _oracle
 
@@ -87,6 +95,47 @@ def oracle_predict(offsets, keys, measure, min_degree1=4, max_edges=UNBOUNDED, m
     for p in (pu, pv, ps):
         lib.nlp_oracle_free(p)
     return u, v, s, st.as_dict()
+
+
+def oracle_edge_deletions(offsets, keys, seed, batch_size):
+    """The C restatement of generateEdgeDeletions + tidyBatchUpdateU (inc/batch.hxx:99-112, 200-208)
+    with std::default_random_engine(seed).  Returns (u, v, engine_words_consumed): the sorted unique
+    directed list of removed edges."""
+    lib = _load_oracle()
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    pu, pv = C.c_void_p(), C.c_void_p()
+    n, words = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.nlp_oracle_edge_deletions(offsets.ctypes.data, keys.ctypes.data if keys.size else None,
+                                       offsets.shape[0] - 1, seed, batch_size,
+                                       C.byref(pu), C.byref(pv), C.byref(n), C.byref(words))
+    if rc != 0:
+        raise MemoryError("nlp_oracle_edge_deletions failed")
+    u = _copy_out(pu.value, int(n.value), np.uint32)
+    v = _copy_out(pv.value, int(n.value), np.uint32)
+    lib.nlp_oracle_batch_free(pu); lib.nlp_oracle_batch_free(pv)
+    return u, v, int(words.value)
+
+
+def ref_batch_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libnlpref_batch.so"))
+
+
+def ref_edge_deletions(offsets, keys, seed, batch_size):
+    """The reference's own generateEdgeDeletions + tidyBatchUpdateU on a DiGraph built from the CSR."""
+    lib = C.CDLL(os.path.join(_HERE, "_ref", "libnlpref_batch.so"))
+    lib.nlpref_edge_deletions.restype = C.c_int64
+    lib.nlpref_edge_deletions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+                                          C.c_void_p, C.c_void_p, C.c_uint64]
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    cap = 2 * batch_size + 2
+    u = np.empty(cap, np.uint32); v = np.empty(cap, np.uint32)
+    n = lib.nlpref_edge_deletions(offsets.ctypes.data, keys.ctypes.data if keys.size else None,
+                                  offsets.shape[0] - 1, seed, batch_size, u.ctypes.data, v.ctypes.data, cap)
+    if n < 0:
+        raise ValueError("nlpref_edge_deletions: capacity")
+    return u[:n].copy(), v[:n].copy()
 
 
 def ref_available():

@@ -1,0 +1,38 @@
+// TEST INFRASTRUCTURE ONLY -- C-callable wrapper around the UNMODIFIED reference batch generator
+// (inc/batch.hxx: generateEdgeDeletions + tidyBatchUpdateU, as runBatches calls them at
+// main.cxx:165-168), compiled from the sources where they lie (-I/root/reference, see
+// oracle/Makefile) into oracle/_ref/libnlpref_batch.so.  Nothing from the reference is copied.
+// Used by tests/test_batch_oracle.py to pin oracle/batch_oracle.c.
+#include <cstdint>
+#include <cstdlib>
+#include <random>
+#include <tuple>
+#include <vector>
+#include "inc/main.hxx"
+
+using namespace std;
+
+extern "C" {
+
+// offsets[span+1], keys[M] -> reference DiGraph (the class main.cxx uses), then the reference's
+// own sampling with std::default_random_engine(seed).  Returns the number of directed deletions
+// written to out_u / out_v (capacity `cap`), or -1 if the capacity is too small.
+int64_t nlpref_edge_deletions(const uint64_t* offsets, const uint32_t* keys, uint32_t span, uint32_t seed,
+                              uint64_t batch_size, uint32_t* out_u, uint32_t* out_v, uint64_t cap) {
+  using K = uint32_t;
+  DiGraph<K, None, None> x;
+  for (uint32_t u = 1; u < span; ++u) x.addVertex(u);
+  for (uint32_t u = 0; u < span; ++u)
+    for (uint64_t e = offsets[u]; e < offsets[u + 1]; ++e) x.addEdge(u, keys[e]);
+  updateOmpU(x);
+  default_random_engine rnd(seed);
+  auto deletions = generateEdgeDeletions(rnd, x, size_t(batch_size), 1, x.span() - 1, true);
+  vector<tuple<K, K>> insertions;
+  tidyBatchUpdateU(deletions, insertions, x);
+  if (deletions.size() > cap) return -1;
+  size_t i = 0;
+  for (const auto& [u, v] : deletions) { out_u[i] = u; out_v[i] = v; ++i; }
+  return (int64_t)deletions.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+"""CPU: the random edge removal that precedes every prediction (inc/batch.hxx:99-112, 200-208;
+SURVEY.md section 8f-3, not on the GPU yet).  The plain-C restatement (oracle/batch_oracle.c) must
+reproduce the compiled reference draw for draw -- same std::default_random_engine seed, same
+removed edges -- and the slot-parallel formulation (tests/batch_parallel.py, the algorithm for a
+GPU kernel) must reproduce both."""
+import os
+
+import numpy as np
+import pytest
+
+import batch_parallel
+
+HAVE_REF = os.path.isdir("/root/reference") or os.path.exists(
+    os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libnlpref_batch.so"))
+
+
+def graphs(nlp):
+    g = nlp.graphs
+    return {
+        "rmat12": g.to_numpy(*g.rmat(12, 16, 31)),             # many isolated vertices: retries
+        "road60": g.to_numpy(*g.road_lattice(60, 0.6, 33)),
+        "web20k": g.to_numpy(*g.web_crawl(20000, 10, window=500, seed=36)),
+        "empty": (np.zeros(6, np.uint64), np.empty(0, np.uint32)),      # every draw fails five times
+    }
+
+
+SEEDS = (0, 1, 12345, 2147483647, 4000000000)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="compiled reference (oracle/_ref/libnlpref_batch.so) not available")
+def test_oracle_matches_reference_batch_generator(nlp, oracle):
+    if not oracle.ref_batch_available():
+        pytest.skip("oracle/_ref/libnlpref_batch.so missing")
+    for name, (off, keys) in graphs(nlp).items():
+        for seed in SEEDS:
+            for B in (0, 1, 17, max(2, len(keys) // 20)):
+                u, v, words = oracle.oracle_edge_deletions(off, keys, seed, B)
+                ru, rv = oracle.ref_edge_deletions(off, keys, seed, B)
+                assert len(u) == len(ru) and (u == ru).all() and (v == rv).all(), (name, seed, B)
+
+
+def test_slot_parallel_formulation_matches_oracle(nlp, oracle):
+    for name, (off, keys) in graphs(nlp).items():
+        for seed in SEEDS:
+            for B in (1, 2, 17, 1000, max(2, len(keys) // 20)):
+                u, v, words = oracle.oracle_edge_deletions(off, keys, seed, B)
+                pu, pv, pwords = batch_parallel.edge_deletions_parallel(off, keys, seed, B)
+                assert len(u) == len(pu) and (u == pu).all() and (v == pv).all(), (name, seed, B)
+                assert words == pwords, (name, seed, B, words, pwords)
+
+
+def test_removed_edges_exist_and_are_symmetric(nlp, oracle):
+    off, keys = graphs(nlp)["rmat12"]
+    u, v, _ = oracle.oracle_edge_deletions(off, keys, 7, len(keys) // 10)
+    S = len(off) - 1
+    src = np.repeat(np.arange(S, dtype=np.int64), np.diff(off.astype(np.int64)))
+    have = set((src * S + keys.astype(np.int64)).tolist())
+    comp = u.astype(np.int64) * S + v.astype(np.int64)
+    assert all(c in have for c in comp.tolist())
+    assert set(comp.tolist()) == set((v.astype(np.int64) * S + u.astype(np.int64)).tolist())
+    assert (np.diff(comp) > 0).all()          # sorted, unique
