@@ -173,7 +173,7 @@ def run_reference(args):
     # How many pairs qualify at all?  The C oracle (OpenMP, shortfall-safe) answers that before the
     # reference runs: with fewer than K of them the reference's OpenMP merge reads an empty vector
     # (inc/predict.hxx:424,452-453; observed segfault), so its sequential templates are timed instead.
-    _, _, _, st = O.oracle_predict(offn, keysn, "JC", args.degree, max_edges=1)
+    _, _, _, st = O.oracle_predict(offn, keysn, "JC", args.degree, max_edges=1, threads=threads)   # torchrun sets OMP_NUM_THREADS=1
     use_omp = st["kept"] >= K
     if O.ref_available():
         kind = "reference"
