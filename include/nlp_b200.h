@@ -202,6 +202,28 @@ typedef struct {
 /* Evaluate the handle's last result (nlp_predict or nlp_merge) against the held-back edges.    */
 int nlp_evaluate(nlp_handle* h, nlp_evaluation* out);
 
+/* ---- batch generation on the device ------------------------------------
+ * Before every sweep of predictions main.cxx removes random edges from the graph (runBatches,
+ * main.cxx:165-168): generateEdgeDeletions (inc/batch.hxx:99-112: batch_size times, up to five
+ * tries of "random vertex u in [1, span), then a random entry of row u"; the graph is not changed
+ * while the batch is drawn) followed by tidyBatchUpdateU (inc/batch.hxx:200-208: sort by (u, v),
+ * unique).  nlp_generate_deletions draws the same batch from the resident graph for
+ * std::default_random_engine(seed) -- the same edges, draw for draw (the generator is a Lehmer
+ * sequence, so every position of the stream is computed on its own; csrc/batch.cuh).
+ * *count = directed pairs (both directions of every removed edge, sorted by (u, v), unique);
+ * *words = engine outputs consumed (the stream position the reference's `rnd` is left at).
+ * Uses the candidate buffers: the last prediction result is gone afterwards.                    */
+int nlp_generate_deletions(nlp_handle* h, uint32_t seed, uint64_t batch_size, uint64_t* count,
+                           uint64_t* words);
+
+/* Copy the generated pairs to caller arrays (host or this GPU), min(capacity, count) of them.   */
+int nlp_fetch_deletions(nlp_handle* h, uint32_t* u, uint32_t* v, uint64_t capacity);
+
+/* Device pointers of the generated pairs, e.g. for nlp_set_truth(h, d_u, d_v, count): they are
+ * exactly main.cxx's sorted `deletions0` (main.cxx:206-207).  Valid until the next
+ * nlp_generate_deletions / nlp_destroy.                                                         */
+int nlp_deletions_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d_v, uint64_t* count);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t nlp_launch_count(const nlp_handle* h);
 

@@ -17,7 +17,7 @@ STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH
 
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
            "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_set_reuse", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
-           "nlp_set_truth", "nlp_evaluate", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
+           "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
 class Options(C.Structure):
@@ -87,6 +87,9 @@ def load_library(build_if_missing=True):
     lib.nlp_merge.argtypes = [vp, vp, vp, vp, u64, u64, C.POINTER(C.c_float)]
     lib.nlp_set_truth.argtypes = [vp, vp, vp, u64]
     lib.nlp_evaluate.argtypes = [vp, C.POINTER(Evaluation)]
+    lib.nlp_generate_deletions.argtypes = [vp, u32, u64, C.POINTER(u64), C.POINTER(u64)]
+    lib.nlp_fetch_deletions.argtypes = [vp, vp, vp, u64]
+    lib.nlp_deletions_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     lib.nlp_launch_count.argtypes = [vp]
     lib.nlp_launch_count.restype = u64
     lib.nlp_stream.argtypes = [vp]
@@ -194,6 +197,25 @@ class Predictor:
         e = Evaluation()
         self._check(self.lib.nlp_evaluate(self.h, C.byref(e)))
         return e.as_dict()
+
+    def generate_deletions(self, seed, batch_size, fetch=True):
+        """The reference's random edge removal (inc/batch.hxx:99-112, 200-208) on the resident graph
+        for std::default_random_engine(seed).  Returns (u, v, engine_words) -- the sorted unique
+        directed pairs -- or (count, engine_words) with ``fetch=False`` (pairs stay on the GPU)."""
+        n, words = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.nlp_generate_deletions(self.h, seed, batch_size, C.byref(n), C.byref(words)))
+        n = int(n.value)
+        if not fetch:
+            return n, int(words.value)
+        u = np.empty(n, np.uint32); v = np.empty(n, np.uint32)
+        if n:
+            self._check(self.lib.nlp_fetch_deletions(self.h, u.ctypes.data, v.ctypes.data, n))
+        return u, v, int(words.value)
+
+    def deletions_device(self):
+        pu, pv, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self.lib.nlp_deletions_device(self.h, C.byref(pu), C.byref(pv), C.byref(n)))
+        return pu.value, pv.value, int(n.value)
 
     def launch_count(self):
         return int(self.lib.nlp_launch_count(self.h))

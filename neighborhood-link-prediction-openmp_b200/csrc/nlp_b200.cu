@@ -10,6 +10,7 @@
 #include "select.cuh"
 #include "pairs.cuh"
 #include "evaluate.cuh"
+#include "batch.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -104,6 +105,10 @@ struct nlp_handle {
   cudaEvent_t ev_stg_ready[2] = {nullptr, nullptr}, ev_stg_done[2] = {nullptr, nullptr};
   bool stg_busy[2] = {false, false};
   int stg_next = 0;
+  // nlp_generate_deletions: per-slot tables of the random stream, orbit, result (sorted unique directed pairs)
+  DevBuf bt_d, bt_uat, bt_hit, bt_jump[2], bt_starts, bt_pos, del_u, del_v;
+  uint64_t del_n = 0;
+  bool has_deletions = false;
   // held-back edges for nlp_evaluate: packed (u << 32 | v) keys, ascending
   DevBuf truth_key, truth_tmp, eval_ctr;
   uint64_t truth_n = 0;
@@ -1050,6 +1055,8 @@ int nlp_destroy(nlp_handle* h) {
   release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->counts); release(h->totals); release(h->hist);
   release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
   release(h->truth_key); release(h->truth_tmp); release(h->eval_ctr);
+  release(h->bt_d); release(h->bt_uat); release(h->bt_hit); release(h->bt_jump[0]); release(h->bt_jump[1]);
+  release(h->bt_starts); release(h->bt_pos); release(h->del_u); release(h->del_v);
   if (h->ev_eval0) cudaEventDestroy(h->ev_eval0);
   if (h->ev_eval1) cudaEventDestroy(h->ev_eval1);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -1259,6 +1266,103 @@ int nlp_merge(nlp_handle* h, const uint32_t* d_u, const uint32_t* d_v, const flo
   NLP_CUDA(h, cudaEventSynchronize(h->ev_done));
   if (select_ms) NLP_CUDA(h, cudaEventElapsedTime(select_ms, h->ev_start, h->ev_done));
   h->res_buf = ob; h->res_count = on; h->has_result = true;
+  return NLP_OK;
+}
+
+int nlp_generate_deletions(nlp_handle* h, uint32_t seed, uint64_t batch_size, uint64_t* count, uint64_t* words) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_graph) return fail(h, NLP_ERR_NO_GRAPH, "nlp_generate_deletions: no graph set");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  h->has_deletions = false;
+  h->del_n = 0;
+  if (count) *count = 0;
+  if (words) *words = 0;
+  const uint64_t B = batch_size;
+  const uint32_t S = h->S;
+  if (B == 0 || S <= 1) { h->has_deletions = true; return NLP_OK; }
+  const uint64_t P = 6 * B + 16;                    // a deletion uses at most 4 failed tries + 2 = 6 slots
+  if (P >= 0xfffffff0ull) return fail(h, NLP_ERR_CAPACITY, "nlp_generate_deletions: batch too large");
+  NLP_TRY(ensure(h, h->bt_d, P * 8));
+  NLP_TRY(ensure(h, h->bt_uat, P * 4));
+  NLP_TRY(ensure(h, h->bt_hit, P * 4));
+  NLP_TRY(ensure(h, h->bt_jump[0], P * 4));
+  NLP_TRY(ensure(h, h->bt_jump[1], P * 4));
+  NLP_TRY(ensure(h, h->bt_starts, B * 4));
+  NLP_TRY(ensure(h, h->bt_pos, 2 * B * 8));
+  h->has_result = false;                            // the candidate buffers are reused for the pairs
+  NLP_TRY(ensure_candidates(h, 2 * B));
+  const DevGraph g = dev_graph(h);
+  uint32_t seed0 = seed % 2147483647u;              // linear_congruential_engine::seed
+  if (seed0 == 0) seed0 = 1;
+  const unsigned gp = grid_for(P, 256, h->num_sms * 16), gb = grid_for(B, 256, h->num_sms * 16);
+  k_batch_slots<<<gp, 256, 0, h->stream>>>(g.deg, S, seed0, P, (double*)h->bt_d.p, (uint32_t*)h->bt_uat.p);
+  NLP_LAUNCHED(h);
+  k_batch_next<<<gp, 256, 0, h->stream>>>((const uint32_t*)h->bt_uat.p, P, (uint32_t*)h->bt_hit.p, (uint32_t*)h->bt_jump[0].p);
+  NLP_LAUNCHED(h);
+  NLP_CUDA(h, cudaMemsetAsync(h->bt_starts.p, 0, 4, h->stream));       // the first deletion starts at slot 0
+  int cur = 0;
+  for (uint64_t known = 1; known < B;) {            // orbit of slot 0 by pointer doubling: jump = next^known
+    const uint64_t take = std::min<uint64_t>(known, B - known);
+    k_batch_extend<<<grid_for(take, 256, h->num_sms * 16), 256, 0, h->stream>>>((uint32_t*)h->bt_starts.p, known, take,
+                                                                                  (const uint32_t*)h->bt_jump[cur].p);
+    NLP_LAUNCHED(h);
+    known += take;
+    if (known < B) {
+      k_batch_square<<<gp, 256, 0, h->stream>>>((const uint32_t*)h->bt_jump[cur].p, (uint32_t*)h->bt_jump[cur ^ 1].p, P);
+      NLP_LAUNCHED(h);
+      cur ^= 1;
+    }
+  }
+  k_batch_emit<<<gb, 256, 0, h->stream>>>(g, (const uint32_t*)h->bt_starts.p, B, (const uint32_t*)h->bt_hit.p,
+                                          (const uint32_t*)h->bt_uat.p, (const double*)h->bt_d.p,
+                                          (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p);
+  NLP_LAUNCHED(h);
+  int sb = 0;
+  NLP_TRY(radix_sort_pairs(h, 0, 2 * B, false, &sb));                  // sortEdgesByIdU, inc/batch.hxx:171-178
+  uint32_t* head = (uint32_t*)h->cs[sb].p;                             // the score array is idle here
+  k_batch_heads<<<grid_for(2 * B, 256, h->num_sms * 16), 256, 0, h->stream>>>((const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p,
+                                                                               2 * B, head);
+  NLP_LAUNCHED(h);
+  uint64_t m = 0;
+  NLP_TRY(exclusive_scan<uint32_t>(h, head, 2 * B, (unsigned long long*)h->bt_pos.p, &m));
+  NLP_TRY(ensure(h, h->del_u, m * 4));
+  NLP_TRY(ensure(h, h->del_v, m * 4));
+  k_batch_compact<<<grid_for(2 * B, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+      (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, 2 * B, head, (const unsigned long long*)h->bt_pos.p,
+      (uint32_t*)h->del_u.p, (uint32_t*)h->del_v.p);
+  NLP_LAUNCHED(h);
+  // engine words the batch consumed: two per slot, up to where the deletion after the last would start
+  uint32_t last = 0, last_hit = 0;
+  NLP_CUDA(h, cudaMemcpyAsync(&last, (const uint32_t*)h->bt_starts.p + (B - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(&last_hit, (const uint32_t*)h->bt_hit.p + last, 4, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->del_n = m;
+  h->has_deletions = true;
+  if (count) *count = m;
+  if (words) *words = 2ull * (last_hit != BATCH_NONE ? (uint64_t)last_hit + 2ull : (uint64_t)last + 5ull);
+  return NLP_OK;
+}
+
+int nlp_fetch_deletions(nlp_handle* h, uint32_t* u, uint32_t* v, uint64_t capacity) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_deletions) return fail(h, NLP_ERR_NO_RESULT, "nlp_fetch_deletions: no batch generated");
+  const uint64_t n = std::min<uint64_t>(capacity, h->del_n);
+  if (!n) return NLP_OK;
+  if (!u || !v) return fail(h, NLP_ERR_ARG, "nlp_fetch_deletions: null output");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  NLP_CUDA(h, cudaMemcpyAsync(u, h->del_u.p, n * 4, cudaMemcpyDefault, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(v, h->del_v.p, n * 4, cudaMemcpyDefault, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLP_OK;
+}
+
+int nlp_deletions_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d_v, uint64_t* count) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_deletions) return fail(h, NLP_ERR_NO_RESULT, "nlp_deletions_device: no batch generated");
+  if (d_u) *d_u = (const uint32_t*)h->del_u.p;
+  if (d_v) *d_v = (const uint32_t*)h->del_v.p;
+  if (count) *count = h->del_n;
   return NLP_OK;
 }
 

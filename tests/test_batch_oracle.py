@@ -59,3 +59,33 @@ def test_removed_edges_exist_and_are_symmetric(nlp, oracle):
     assert all(c in have for c in comp.tolist())
     assert set(comp.tolist()) == set((v.astype(np.int64) * S + u.astype(np.int64)).tolist())
     assert (np.diff(comp) > 0).all()          # sorted, unique
+
+
+@pytest.mark.gpu
+def test_device_batch_generation_matches_oracle(nlp, oracle):
+    """nlp_generate_deletions (csrc/batch.cuh) against the sequential oracle: the same removed edges
+    and the same stream position for the same std::default_random_engine seed."""
+    pred = nlp.Predictor(0)
+    try:
+        for name, (off, keys) in graphs(nlp).items():
+            if name == "web20k":
+                continue
+            pred.set_graph(off, keys)
+            for seed in (0, 12345, 4000000000):
+                for B in (0, 1, 2, 17, max(3, len(keys) // 20)):
+                    u, v, words = oracle.oracle_edge_deletions(off, keys, seed, B)
+                    gu, gv, gwords = pred.generate_deletions(seed, B)
+                    assert len(gu) == len(u) and (gu == u).all() and (gv == v).all(), (name, seed, B, len(gu), len(u))
+                    assert gwords == words, (name, seed, B, gwords, words)
+        # the generated list is main.cxx's sorted deletions0: it can be handed to nlp_set_truth as it lies
+        off, keys = graphs(nlp)["rmat12"]
+        pred.set_graph(off, keys)
+        n, _ = pred.generate_deletions(7, 500, fetch=False)
+        du, dv, dn = pred.deletions_device()
+        assert dn == n
+        pred.set_truth_pointers(du, dv, dn)
+        r = pred.predict("JC", 0, max_edges=n // 2)
+        ev = pred.evaluate()
+        assert ev["truth"] == n and ev["predicted"] == 2 * r["count"] and ev["common"] == 0   # existing edges are never predicted
+    finally:
+        pred.close()
