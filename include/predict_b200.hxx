@@ -230,6 +230,45 @@ inline void setFetchEdges(bool on) {
   s.fetch_edges = on;
 }
 
+// ---- batch generation on the GPU (inc/batch.hxx:99-112, 200-208 as called at main.cxx:165-168) ----
+// The same removed edges as
+//   default_random_engine rnd(seed);
+//   auto deletions = generateEdgeDeletions(rnd, x, batchSize, 1, x.span()-1, true);
+//   tidyBatchUpdateU(deletions, insertions, x);
+// draw for draw (nlp_generate_deletions).  `words` receives the number of engine outputs the batch
+// consumed: `rnd.discard(*words)` leaves a host engine where the reference's would be.
+// With `holdBack` the list also becomes the ground truth of evaluateLastPrediction() without
+// leaving the GPU (it is main.cxx's sorted `deletions0`).
+template <class G>
+inline auto generateEdgeDeletionsB200(const G& x, uint32_t seed, size_t batchSize, size_t* words = nullptr, bool holdBack = false) {
+  using K = typename G::key_type;
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  nlp_handle* h = s.handle();
+  if constexpr (std::is_same<G, DeviceGraph>::value) {
+    if (s.resident != &x) throw std::runtime_error("nlp_b200: this DeviceGraph is no longer resident (another graph was uploaded since)");
+  } else {
+    const uint64_t f = detail::pack(x, s.offsets, s.keys);
+    if (!(s.have_fingerprint && s.fingerprint == f && s.resident == nullptr)) {
+      detail::check(h, nlp_set_graph(h, s.offsets.data(), s.keys.data(), (uint32_t)(s.offsets.size() - 1)), "nlp_set_graph");
+      s.fingerprint = f; s.have_fingerprint = true; s.resident = nullptr;
+    }
+  }
+  uint64_t n = 0, w = 0;
+  detail::check(h, nlp_generate_deletions(h, seed, (uint64_t)batchSize, &n, &w), "nlp_generate_deletions");
+  if (words) *words = (size_t)w;
+  if (holdBack) {
+    const uint32_t *du = nullptr, *dv = nullptr;
+    detail::check(h, nlp_deletions_device(h, &du, &dv, &n), "nlp_deletions_device");
+    detail::check(h, nlp_set_truth(h, du, dv, n), "nlp_set_truth");
+  }
+  std::vector<uint32_t> u((size_t)n), v((size_t)n);
+  detail::check(h, nlp_fetch_deletions(h, u.data(), v.data(), n), "nlp_fetch_deletions");
+  std::vector<std::tuple<K, K>> a((size_t)n);
+  for (size_t i = 0; i < (size_t)n; ++i) a[i] = std::make_tuple((K)u[i], (K)v[i]);
+  return a;
+}
+
 inline LinkEvaluation evaluateLastPrediction() {
   detail::Session& s = detail::Session::get();
   std::lock_guard<std::mutex> lock(s.mu);

@@ -62,6 +62,14 @@ def test_shim_compiles_and_fails_loudly_without_gpu(nlp, tmp_path):
     assert "no CUDA device" in p.stderr and "no CPU path" in p.stderr, p.stderr
 
 
+def test_shim_helpers_compile(nlp, tmp_path):
+    """Batch generation / evaluation helpers of the C++ mirror, instantiated for a host graph class
+    and for DeviceGraph (compile only: running them needs a B200)."""
+    src = os.path.join(HOST, "shim_compile_only.cxx")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fopenmp", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "include"),
+                           src, "-o", str(tmp_path / "shim_compile_only.o")])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("K", [-1, 500])
 def test_shim_matches_oracle(nlp, oracle, tmp_path, K):
