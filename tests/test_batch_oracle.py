@@ -49,6 +49,16 @@ def test_slot_parallel_formulation_matches_oracle(nlp, oracle):
                 assert words == pwords, (name, seed, B, words, pwords)
 
 
+def test_slot_parallel_formulation_large_batch(nlp, oracle):
+    """More deletions than the graph has edges (18 pointer-doubling rounds, heavy duplication)."""
+    off, keys = graphs(nlp)["web20k"]
+    B = 200_000
+    u, v, words = oracle.oracle_edge_deletions(off, keys, 99, B)
+    pu, pv, pwords = batch_parallel.edge_deletions_parallel(off, keys, 99, B)
+    assert len(u) == len(pu) and (u == pu).all() and (v == pv).all() and words == pwords
+    assert len(u) < 2 * B                                  # duplicates were collapsed
+
+
 def test_removed_edges_exist_and_are_symmetric(nlp, oracle):
     off, keys = graphs(nlp)["rmat12"]
     u, v, _ = oracle.oracle_edge_deletions(off, keys, 7, len(keys) // 10)
