@@ -39,7 +39,7 @@ WORKLOADS = {
     "rmat22": dict(kind="rmat", scale=22, ef=16, seed=43, frac=0.1,
                    desc="R-MAT scale-22 ef-16 (0.57,0.19,0.19) ids permuted, 0.1|E| removed (BASELINE configs[1])"),
     "rmat20": dict(kind="rmat", scale=20, ef=16, seed=43, frac=0.1, desc="R-MAT scale-20 (smoke size)"),
-    "rmat18": dict(kind="rmat", scale=18, ef=16, seed=42, frac=0.01, desc="R-MAT scale-18, 1e-2|E| removed (configs[0])"),
+    "rmat18": dict(kind="rmat", scale=18, ef=16, seed=42, frac=0.01, permute=False, desc="R-MAT scale-18 (ids as generated), 1e-2|E| removed (configs[0])"),
     "rmat16": dict(kind="rmat", scale=16, ef=16, seed=42, frac=0.1, desc="R-MAT scale-16 (tiny)"),
     # BASELINE configs[2..4]: parity/scale cases, run with --workload (not the default bench line)
     "road24m": dict(kind="road", side=4900, keep=0.6, seed=44, frac=0.1,
@@ -53,28 +53,61 @@ WORKLOADS = {
 }
 MEASURES = ["CN", "JC", "SI", "SC", "HP", "HD", "LHN", "AA", "RA"]
 METRIC = "lhub_predicted_edges_per_s"
+DTYPE = "u32 counts, f32 scores (f64 terms for AA/RA/Salton)"
 
 
-def build_workload(name, device, batch=0):
-    """The graph of workload `name` with its edges removed.  `batch` picks the random removal:
-    the reference draws REPEAT_BATCH = 5 independent removals per fraction (main.cxx:26-28,163)."""
+def make_config(info, degree, measures, S, M):
+    """The workload description -- identical in both arms (the driver compares the dicts);
+    everything run-specific lives in the line's "run" object."""
+    return dict(info, min_degree1=degree, measures=list(measures),
+                l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6))
+
+
+REMOVAL_SEED = 12345      # SURVEY.md section 8c/8d: default_random_engine(12345) for every parity run
+
+
+def build_workload(name, device, batch=0, pred=None):
+    """The graph of workload `name` with its edges removed the way the reference removes them
+    (main.cxx:166-169): generateEdgeDeletions draws `frac * |E| / 2` times "random vertex, then a
+    random entry of its row" from std::default_random_engine(12345 + batch), tidyBatchUpdateU makes
+    the list unique, applyBatchUpdateOmpU deletes both directions.  `batch` picks the random
+    removal: the reference draws REPEAT_BATCH = 5 independent ones per fraction (main.cxx:26-28,163).
+    With a Predictor the draw runs on the GPU (nlp_generate_deletions, draw for draw the reference's
+    sequence); without one (the --impl reference arm) the oracle's restatement of the generator
+    runs on the host -- tests/test_batch_oracle.py pins the two to each other and to the reference.
+    Returns (offsets, keys, K, info, (del_u, del_v)): K = removed undirected edges = the prediction
+    count PREDICT_LINKS asks for (main.cxx:50); del_* = main.cxx's sorted directed `deletions0`."""
     import nlp_b200 as N
     w = WORKLOADS[name]
     t0 = time.time()
     if w["kind"] == "rmat":
-        off, keys = N.graphs.rmat(w["scale"], w["ef"], w["seed"], permute=True, device=device)
+        off, keys = N.graphs.rmat(w["scale"], w["ef"], w["seed"], permute=w.get("permute", True), device=device)
     elif w["kind"] == "road":
         off, keys = N.graphs.road_lattice(w["side"], w["keep"], w["seed"], device=device)
     else:
         off, keys = N.graphs.web_crawl(w["n"], w["avg_out"], seed=w["seed"], device=device)
-    off, keys, rl, rh = N.graphs.remove_edges(off, keys, w["frac"], w["seed"] + 1000 + batch)
-    K = int(rl.numel())
-    del rl, rh
+    S = int(off.numel() - 1)
+    batch_size = int(w["frac"] * int(keys.numel()) / 2)            # size_t(d * x.size() / 2), main.cxx:166
+    seed = REMOVAL_SEED + batch
+    if pred is not None:
+        pred.set_graph_pointers(off.data_ptr(), keys.data_ptr(), S, device=True, keep=(off, keys))
+        n, _ = pred.generate_deletions(seed, batch_size, fetch=False)
+        du = torch.empty(n, dtype=torch.int32, device=device); dv = torch.empty(n, dtype=torch.int32, device=device)
+        if n:
+            pred.fetch_deletions_into(du.data_ptr(), dv.data_ptr(), n)
+    else:
+        from oracle import oracle_py as O
+        offn, keysn = N.graphs.to_numpy(off, keys)
+        u, v, _ = O.oracle_edge_deletions(offn, keysn, seed, batch_size)
+        du = torch.from_numpy(u.astype(np.int32)).to(device); dv = torch.from_numpy(v.astype(np.int32)).to(device)
+        del offn, keysn
+    off, keys = N.graphs.apply_deletions(off, keys, du, dv)
+    K = int(du.numel()) // 2
     if device != "cpu":
         torch.cuda.synchronize()
-    info = {"workload": name, "description": w["desc"], "span": int(off.numel() - 1), "entries": int(keys.numel()),
-            "predict_count_K": K, "build_s": round(time.time() - t0, 2)}
-    return off, keys, K, info
+    info = {"workload": name, "description": w["desc"], "span": S, "entries": int(keys.numel()),
+            "predict_count_K": K, "removal": "reference sampler (inc/batch.hxx:99-112), default_random_engine(%d)" % seed}
+    return off, keys, K, info, (du, dv), round(time.time() - t0, 2)
 
 
 class ClockSampler:
@@ -165,9 +198,10 @@ def run_reference(args):
         return 0
     from oracle import oracle_py as O
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    off, keys, K, info = build_workload(args.workload, dev)
+    off, keys, K, info, _, build_s = build_workload(args.workload, dev)
     import nlp_b200 as N
     offn, keysn = N.graphs.to_numpy(off, keys)
+    S, M = int(off.numel() - 1), int(keys.numel())
     del off, keys
     threads = os.cpu_count() or 1
     # How many pairs qualify at all?  The C oracle (OpenMP, shortfall-safe) answers that before the
@@ -190,9 +224,8 @@ def run_reference(args):
     per_measure = max(w1, 1e-3)
     nm = int(max(1, min(len(MEASURES), 150.0 / (per_measure * total_steps))))
     order = ["JC", "AA", "CN", "SC", "RA", "SI", "HP", "HD", "LHN"]
-    sample = [m for m in MEASURES if m in order[:nm]]
-    if args.measures:
-        sample = [m for m in args.measures.split(",") if m]
+    all_measures = [m for m in args.measures.split(",") if m] if args.measures else MEASURES
+    sample = [m for m in all_measures if m in order[:nm]] or all_measures[:1]
     for _ in range(args.warmup):
         reference_step(R, K, args.degree, sample, threads, omp=use_omp)
     edges = 0; ref_ms = 0.0; wall = 0.0
@@ -203,9 +236,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 counts, f32 scores",
-        "data": "synthetic",
-        "config": dict(info, min_degree1=args.degree, measures=sample, l2="inputs larger than L2"),
+        "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
+        "dtype": DTYPE, "data": "synthetic",
+        "config": make_config(info, args.degree, all_measures, S, M),
+        "run": {"build_s": build_s, "measures_run": sample, "host_threads": threads},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": threads, "kind": kind,
                          "sample": "%d of 9 measures per step (%s), full graph, reference's own `time` field, %s"
                                    % (len(sample), ",".join(sample),
@@ -243,13 +277,13 @@ def run_b200(args):
         shard = "batches" if len(all_measures) > 1 else "sources"
     if world == 1:
         shard = "none"
-    off, keys, K, info = build_workload(args.workload, dev, batch=rank if shard == "batches" else 0)
+    pred = N.Predictor(local)
+    off, keys, K, info, _, build_s = build_workload(args.workload, dev, batch=rank if shard == "batches" else 0, pred=pred)
     S = int(off.numel() - 1); M = int(keys.numel())
     # host copies in pinned memory (e2e leg) -- int64/int32 tensors carry the uint64/uint32 bits
     do_e2e = not args.no_e2e
     if do_e2e:
         h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
-    pred = N.Predictor(local)
     if shard == "sources":
         pred.set_partition(rank, world)
     stream = torch.cuda.ExternalStream(pred.lib.nlp_stream(pred.h), device=dev)
@@ -407,60 +441,99 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from `ncu --set full` (see profiles/README.md)
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload + ":" + str(D), {}).get(dom[0])
-    achieved = dom[2] / (dom[1] / 1e3) / 1e9 if dom[1] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "share_of_step": dom[1] / max(1e-9, sum(phase)),
-                "algorithmic_bytes_per_step": dom[2] / args.steps}
-    # whole step against the reference algorithm's bytes (SURVEY.md section 8d formula)
-    total_alg = nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world) + 4 * W + 4 * C + 12 * Kout
-    step_frac = total_alg / (ms / 1e3) / 1e9 / peak
+    kernel_gbs = dom[2] / (dom[1] / 1e3) / 1e9 if dom[1] > 0 else 0.0
+    # The roofline SURVEY.md section 8(d) defines: the reference ALGORITHM's bytes
+    #   B_alg = 8(S+1) + 4M + 4M  (offsets, first-hop adjacency, one degree word per first-hop entry)
+    #         + 4 W(D)            (one key per enumerated wedge)
+    #         + 4 C               (deg(v) per scored candidate)          + 12 K_out (result)
+    #         [+ 4 M_elig for the float measures: the term per eligible first-hop entry]
+    # per prediction (W, C, K_out and M_elig are the kernels' own counters), summed over the
+    # predictions of the timed region, over the device time of that region, against the measured
+    # HBM copy bandwidth.  `kernel_*` is the dominant phase against the traffic this implementation
+    # chose to move through it (the figure round 1 called `frac`).
+    flt_elig = sum(r["eligible_first_hop"] for r, m in zip(results, measures * args.steps) if m in ("AA", "RA"))
+    total_alg = nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world) + 4 * W + 4 * C + 12 * Kout + 4 * flt_elig
+    achieved = total_alg / (ms / 1e3) / 1e9
+    step_frac = achieved / peak
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": step_frac,
+                "traffic": traffic, "peak_source": peak_src,
+                "scope": "whole step: SURVEY.md 8(d) algorithmic bytes of all predictions / device time of the step",
+                "algorithmic_bytes_per_step": total_alg / args.steps,
+                "kernel": dom[0], "kernel_gbs": kernel_gbs, "kernel_frac": kernel_gbs / peak,
+                "kernel_share_of_step": dom[1] / max(1e-9, sum(phase)),
+                "kernel_own_bytes_per_step": dom[2] / args.steps}
 
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample -------
+    # ---- parity: the full (u, v, score bits) lists of the sample against the C oracle ------------
     cpu = None
+    parity = {"status": "skipped", "detail": "--no-cpu-baseline / --no-verify"}
     try:
         from oracle import oracle_py as O
+        threads = os.cpu_count() or 1
+        sample = [m for m in ("JC", "AA") if m in measures] or measures[:1]
+        offn = keysn = None
+        if not (args.no_cpu_baseline and args.no_verify):
+            offn, keysn = N.graphs.to_numpy(off, keys)
         if args.no_cpu_baseline:
             cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "reference", "sample": "skipped (--no-cpu-baseline)"}
         elif O.ref_available():
-            offn, keysn = N.graphs.to_numpy(off, keys)
             R = O.RefGraph(offn, keysn)
-            threads = os.cpu_count() or 1
-            sample = [m for m in ("JC", "AA") if m in measures] or measures[:1]
             enough = all(r["count"] == K for r in results)     # fewer candidates than K: OpenMP merge undefined
-            if not enough:
-                threads = 1
-            e, rms, w = reference_step(R, K, D, sample, threads, omp=enough)
-            if e == sum(r["count"] for r, m in zip(results, measures) if m in sample):
-                cpu = {"value": e / (rms / 1e3), "unit": "edges/s", "cores": threads, "kind": "reference",
-                       "sample": "one pass of %s (%d of %d measures) on the full graph, reference %s templates, "
-                                 "reference's own `time` field (%.0f ms wall)" % ("+".join(sample), len(sample), len(measures),
-                                                                                  "OpenMP" if enough else "SEQUENTIAL (fewer candidates than K: OpenMP merge undefined)", w * 1e3)}
-            else:
-                cpu = {"value": None, "unit": "edges/s", "cores": threads, "kind": "reference",
-                       "sample": "reference returned a different number of edges than the GPU path"}
+            rthreads = threads if enough else 1
+            e, rms, w = reference_step(R, K, D, sample, rthreads, omp=enough)
+            cpu = {"value": e / (rms / 1e3), "unit": "edges/s", "cores": rthreads, "kind": "reference",
+                   "sample": "one pass of %s (%d of %d measures) on the full graph, reference %s templates, "
+                             "reference's own `time` field (%.0f ms wall)" % ("+".join(sample), len(sample), len(measures),
+                                                                              "OpenMP" if enough else "SEQUENTIAL (fewer candidates than K: OpenMP merge undefined)", w * 1e3),
+                   "edges": e}
             R.close()
         else:
             t0 = time.perf_counter()
-            offn, keysn = N.graphs.to_numpy(off, keys)
-            u, v, s, st = O.oracle_predict(offn, keysn, "JC", D, max_edges=K)
+            u, v, s_, st = O.oracle_predict(offn, keysn, "JC", D, max_edges=K)
             w = time.perf_counter() - t0
-            cpu = {"value": len(u) / w, "unit": "edges/s", "cores": os.cpu_count() or 1, "kind": "port",
+            cpu = {"value": len(u) / w, "unit": "edges/s", "cores": threads, "kind": "port",
                    "sample": "one JC pass of the C oracle (OpenMP) on the full graph"}
+        if not args.no_verify:
+            # The reference breaks score ties by heap accident (inc/predict.hxx:332), so its list is
+            # canonicalised by the oracle: the plain-C restatement of the same loop (pinned against the
+            # compiled reference, tests/test_oracle_vs_reference.py) with the (score desc, u, v) order.
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import parity as PT
+            bad, rows = [], 0
+            for m in sample:
+                r = pred.predict(m, D, max_edges=K)
+                got = pred.fetch(r["count"])
+                wu, wv, ws, st = O.oracle_predict(offn, keysn, m, D, max_edges=K, threads=threads)
+                err = PT.compare(got, (wu, wv, ws), "%s D=%d K=%d" % (m, D, K))
+                if err is None:
+                    for k in ("first_hop", "eligible_first_hop", "wedges", "candidates", "kept"):
+                        if r[k] != st[k]:
+                            err = "%s: counter %s = %d, oracle %d" % (m, k, r[k], st[k])
+                            break
+                rows += len(wu)
+                if err:
+                    bad.append(err)
+            parity = {"status": "bit-exact" if not bad else "MISMATCH", "measures": sample, "rows_compared": rows,
+                      "against": "oracle/nlp_oracle.c (C restatement of inc/predict.hxx:214-265, canonical tie order), full (u, v, score bits) lists + wedge/candidate counters",
+                      "detail": bad}
     except Exception as ex:   # noqa: BLE001
-        cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+        if cpu is None:
+            cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+        else:
+            parity = {"status": "failed", "detail": repr(ex)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak" if shard in ("none", "batches") else "strong",
-        "vs_baseline": None, "dtype": "u32 counts, f32 scores (f64 terms for AA/RA/Salton)", "data": "synthetic",
-        "config": dict(info, min_degree1=D, l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6),
-                       measures=all_measures,
-                       parallelism={"none": "1 GPU",
-                                    "batches": "%d batches (independent random removals of the same graph, main.cxx:163), one whole step per GPU, CSR replicated, no collective" % world,
-                                    "measures": "the %d predictions of a step dealt to %d GPUs (independent units, no collective), CSR replicated" % (len(all_measures), world),
-                                    "sources": "sources of every prediction partitioned over %d GPUs, CSR replicated, one all-gather + on-device merge" % world}[shard]),
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": make_config(info, D, all_measures, S, M),
+        "run": {"build_s": build_s, "shard": shard,
+                "parallelism": {"none": "1 GPU",
+                                "batches": "%d batches (independent random removals of the same graph, main.cxx:163), one whole step per GPU, CSR replicated, no collective" % world,
+                                "measures": "the %d predictions of a step dealt to %d GPUs (independent units, no collective), CSR replicated" % (len(all_measures), world),
+                                "sources": "sources of every prediction partitioned over %d GPUs, CSR replicated, one all-gather + on-device merge" % world}[shard]},
+        "parity": parity,
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
@@ -494,6 +567,7 @@ def main():
                          "or the sources of each prediction partitioned (all-gather merge)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run on the host cores")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-list parity check against the C oracle")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -212,6 +212,10 @@ class Predictor:
             self._check(self.lib.nlp_fetch_deletions(self.h, u.ctypes.data, v.ctypes.data, n))
         return u, v, int(words.value)
 
+    def fetch_deletions_into(self, u_ptr, v_ptr, capacity):
+        """Copy the generated deletions into caller memory (host or device pointers)."""
+        self._check(self.lib.nlp_fetch_deletions(self.h, u_ptr, v_ptr, capacity))
+
     def deletions_device(self):
         pu, pv, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
         self._check(self.lib.nlp_deletions_device(self.h, C.byref(pu), C.byref(pv), C.byref(n)))

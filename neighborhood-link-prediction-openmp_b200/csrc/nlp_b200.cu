@@ -63,9 +63,6 @@ struct nlp_handle {
   std::map<uint64_t, std::pair<uint64_t, uint64_t>> pair_sizes;
   int path_mode = NLP_PATH_AUTO;
   int coop_mode = 1;                         // 0: per-warp wedge streaming in k_hash / k_dense (count measures)
-  int cluster_mode = 0;                      // 0: single-CTA k_range only (default: remote shared-memory atomics
-                                             // measured 1.3x/2x/3.3x slower at cluster size 2/4/8, R-MAT 20 IHub),
-                                             // 1: auto, n > 1: force clusters of n CTAs
   int range_half = 1;                        // k_range: half-word counters for sources with deg < 2^15 (NLP_B200_RANGE_HALF=0: off)
   uint32_t range_div = 4;                    // weight of the per-row window cost in the k_range / k_dense rule (frontier.cuh)
   int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
@@ -494,20 +491,11 @@ int launch_dense(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
 // Count measures: hub-heavy sources on windowed shared-memory counters (k_range).
 constexpr uint32_t RANGE_COUNTERS = 52 * 1024;      // 208 KB of u32 counters per block (+13 KB static)
 
-// CTAs per cluster for the range path: 1 while a source needs few windows anyway, else 8
-// (portable cluster size; windows 8x wider, passes 8x fewer).
-inline uint32_t range_cluster_size(const nlp_handle* h) {
-  if (h->cluster_mode == 0) return 1;
-  if (h->cluster_mode > 1) return (uint32_t)h->cluster_mode;
-  return ((uint64_t)h->S + RANGE_COUNTERS - 1) / RANGE_COUNTERS > 8 ? 8u : 1u;
-}
-
 template <bool ADMIT>
 int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t n, uint32_t* deferred) {
   if (!n) return NLP_OK;
   const size_t smem = (size_t)RANGE_COUNTERS * 4;
-  const uint32_t cs = range_cluster_size(h);
-  if (cs <= 1) {
+  {
     NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
     // per block: row cursor + row end for every first-hop entry of its current source
@@ -519,27 +507,7 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
                                                              (unsigned long long*)h->range_cursors.p, stride,
                                                              (uint32_t*)h->range_touched.p);
     NLP_LAUNCHED(h);
-    return NLP_OK;
   }
-  auto kern = k_range_cluster<ADMIT>;
-  NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (cs > 8) NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(RANGE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cfg.gridDim = dim3(cs);
-  int max_clusters = 0;
-  NLP_CUDA(h, cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-  if (max_clusters < 1) return fail(h, NLP_ERR_CUDA, "k_range_cluster: no cluster of this size fits the device");
-  const unsigned nclusters = (unsigned)std::min<uint64_t>(n, (uint64_t)max_clusters);
-  cfg.gridDim = dim3(nclusters * cs);
-  uint32_t C = RANGE_COUNTERS;
-  int bin = 6;
-  NLP_CUDA(h, cudaLaunchKernelEx(&cfg, kern, p, list, n, bin, deferred, C));
-  NLP_LAUNCHED(h);
   return NLP_OK;
 }
 
@@ -738,7 +706,7 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
 // multiplicity is measured once per graph, the first time the range path is about to be used.
 int half_word_limit(nlp_handle* h, bool range_on, uint32_t* limit) {
   *limit = 0;
-  if (!range_on || !h->range_half || range_cluster_size(h) > 1) return NLP_OK;
+  if (!range_on || !h->range_half) return NLP_OK;
   if (h->maxmult == 0) {
     NLP_TRY(ensure(h, h->sym_flag, 32));
     NLP_CUDA(h, cudaMemsetAsync((char*)h->sym_flag.p + 24, 0, 8, h->stream));
@@ -810,7 +778,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   for (int b = 0; b < NBINS; ++b) bl.list[b] = (uint32_t*)h->list[b].p;
   // count measures may send hub-heavy sources to the windowed shared-memory counters (k_range);
   // the float measures need the ordered single-warp accumulation of k_dense
-  const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS * range_cluster_size(h) : 0u;
+  const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS : 0u;
   uint32_t half_deg = 0;
   NLP_TRY(half_word_limit(h, range_c != 0u, &half_deg));
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
@@ -992,7 +960,6 @@ int nlp_create(nlp_handle** out, int device) {
   if (const char* e = getenv("NLP_B200_RANGE_HALF")) h->range_half = atoi(e);
   if (const char* e = getenv("NLP_B200_RANGE_DIV")) h->range_div = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
-  if (const char* e = getenv("NLP_B200_CLUSTER")) h->cluster_mode = atoi(e);
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string("nlp_create: ") + what + ": " + cudaGetErrorString(err);
     delete h;

@@ -887,137 +887,4 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
   tally.flush(p.ctr);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Cluster-per-vertex range path: the same windowed counters, but one source is processed by a
-// thread-block CLUSTER whose CTAs each hold C counters of one contiguous window of CS * C
-// vertices (distributed shared memory).  Every CTA streams its share of the first-hop batches and
-// sends each wedge to the CTA that owns v with a remote shared-memory atomic; exclusion and
-// scoring run on the owner.  Windows are CS times wider, so a source needs CS times fewer passes
-// (each pass costs two binary searches per first-hop row), and a hub source gets CS SMs.
-namespace cg = cooperative_groups;
-
-__device__ __forceinline__ void range_batch_cluster(const Params& p, bool has, uint32_t w, uint32_t vlo, uint32_t vhi,
-                                                    uint32_t C, uint32_t* const* peer_cnt,
-                                                    uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
-  const uint32_t* __restrict__ keys = p.g.keys;
-  uint64_t wb = 0;
-  uint32_t dw = 0;
-  if (has) {
-    wb = __ldg(p.g.off + w);
-    dw = (uint32_t)(__ldg(p.g.off + w + 1) - wb);
-    if (dw > 16u) {                                   // sorted row: cut to the cluster's window
-      const uint32_t a = lower_bound_row(keys, wb, dw, vlo);
-      const uint32_t b = a + lower_bound_row(keys, wb + a, dw - a, vhi);
-      wb += a; dw = b - a;
-    }
-  }
-  s_wb[threadIdx.x] = wb;
-  block_scan_u32(dw, s_inc, s_wsum);
-  const uint32_t tot = s_inc[RANGE_THREADS - 1];
-  for (uint32_t idx = threadIdx.x; idx < tot; idx += RANGE_THREADS) {
-    uint32_t lo = 0, hi = RANGE_THREADS - 1;          // smallest j with s_inc[j] > idx
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (s_inc[mid] <= idx) lo = mid + 1; else hi = mid;
-    }
-    const uint32_t before = lo ? s_inc[lo - 1] : 0u;
-    const uint32_t v = __ldg(keys + s_wb[lo] + (idx - before));
-    if (v >= vlo && v < vhi) {
-      const uint32_t x = v - vlo, owner = x / C;
-      atomicAdd(peer_cnt[owner] + (x - owner * C), 1u);             // inc/predict.hxx:156-158, via DSMEM
-    }
-  }
-  __syncthreads();
-}
-
-template <bool ADMIT>
-__global__ void __launch_bounds__(RANGE_THREADS, 1) k_range_cluster(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
-                                                                     uint32_t* __restrict__ deferred, uint32_t C) {
-  extern __shared__ uint32_t cnt[];                   // this CTA's C counters
-  __shared__ unsigned long long s_wb[RANGE_THREADS];
-  __shared__ uint32_t s_inc[RANGE_THREADS];
-  __shared__ uint32_t s_wsum[32];
-  __shared__ uint32_t* s_peer[16];
-  __shared__ uint32_t s_src[4];                       // rank 0 publishes {queue index, go, need}
-  __shared__ unsigned int s_emitted;
-  cg::cluster_group cluster = cg::this_cluster();
-  const uint32_t CS = cluster.num_blocks(), rank = cluster.block_rank();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const uint32_t* __restrict__ keys = p.g.keys;
-  Tally tally;
-  for (uint32_t i = tid; i < C; i += blockDim.x) cnt[i] = 0u;
-  if (tid < (int)CS) s_peer[tid] = cluster.map_shared_rank(cnt, tid);
-  if (tid == 0) s_emitted = 0;
-  const uint32_t* src0 = cluster.map_shared_rank(s_src, 0);
-  cluster.sync();
-  const uint64_t W = (uint64_t)CS * C;                // vertices per cluster window
-  for (;;) {
-    if (rank == 0 && tid == 0) {
-      const uint32_t qi = (uint32_t)atomicAdd(&p.ctr->queue[bin], 1ull);
-      uint32_t go = 1, need = 0;
-      if (ADMIT && qi < n) go = admit_source(p, __ldg(list + qi), bin, deferred, &need) ? 1u : 0u;
-      s_src[0] = qi; s_src[1] = go; s_src[2] = need;
-    }
-    cluster.sync();
-    const uint32_t qi = src0[0], go = src0[1], need = src0[2];
-    cluster.sync();                                   // rank 0 may overwrite s_src from here on
-    if (qi >= n) break;
-    if (!go) continue;
-    const uint32_t u = __ldg(list + qi);
-    const uint64_t ub = __ldg(p.g.off + u);
-    const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
-    const FirstHop f = first_hop(p, u, ub, du);
-    uint32_t emitted = 0;
-    for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += W) {
-      const uint32_t vlo = (uint32_t)lo64;
-      const uint32_t vhi = (uint32_t)(lo64 + W < p.g.S ? lo64 + W : p.g.S);
-      // every CTA takes RANGE_THREADS / CS consecutive first-hop entries of each batch (so even a
-      // source with a few hundred entries keeps all CTAs busy); all its threads stream the wedges
-      const uint32_t share = RANGE_THREADS / CS;
-      for (uint32_t c = 0; c < f.npieces; ++c) {
-        const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
-        const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
-        for (uint32_t base = rank * share; base < pc; base += RANGE_THREADS) {
-          const uint32_t i = base + tid;
-          const bool has = (uint32_t)tid < share && i < pc;
-          range_batch_cluster(p, has, has ? __ldg(pb + i) : 0u, vlo, vhi, C, s_peer, s_inc, s_wb, s_wsum);
-        }
-      }
-      cluster.sync();                                 // all remote atomics of this window have landed
-      // this CTA's part of the window
-      const uint64_t mlo64 = lo64 + (uint64_t)rank * C;
-      const uint32_t mlo = (uint32_t)(mlo64 < vhi ? mlo64 : vhi);
-      const uint32_t mhi = (uint32_t)(mlo64 + C < vhi ? mlo64 + C : vhi);
-      if (mhi > mlo) {   // exclusion of N(u) (inc/predict.hxx:307)
-        const uint32_t a = lower_bound_row(keys, ub, du, mlo);
-        const uint32_t b = a + lower_bound_row(keys, ub + a, du - a, mhi);
-        for (uint32_t i = a + tid; i < b; i += blockDim.x) {
-          const uint32_t x = __ldg(keys + ub + i) - mlo;
-          if (cnt[x] != 0u) cnt[x] = RANGE_ZEROED;
-        }
-      }
-      __syncthreads();
-      const uint32_t len = mhi - mlo;
-      for (uint32_t sb = (uint32_t)warp * 32u; sb < len; sb += (uint32_t)nw * 32u) {
-        const uint32_t i = sb + lane;
-        uint32_t c = 0;
-        if (i < len) { c = cnt[i]; if (c) cnt[i] = 0u; }
-        if (__any_sync(NLP_FULL, c != 0u))
-          emitted += score_and_emit(p, c != 0u, u, du, mlo + i, c & ~RANGE_ZEROED, 0.0f, tally);
-      }
-      cluster.sync();                                 // nobody adds into counters that are still being scored
-    }
-    if (ADMIT) {
-      if (lane == 0 && emitted) atomicAdd(&s_emitted, emitted);
-      __syncthreads();
-      if (tid == 0) {
-        atomicAdd(&p.ctr->reserved, (unsigned long long)s_emitted - (rank == 0 ? (unsigned long long)need : 0ull));
-        s_emitted = 0;
-      }
-      __syncthreads();
-    }
-  }
-  tally.flush(p.ctr);
-}
-
 }  // namespace nlp

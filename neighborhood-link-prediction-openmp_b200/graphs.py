@@ -215,6 +215,31 @@ def duplicate_symmetric(offsets, keys, every=5, copies=2):
     return off2, keys2
 
 
+def apply_deletions(offsets, keys, del_u, del_v):
+    """Remove the directed entries (del_u[i], del_v[i]) from a CSR, ONE stored copy per request, the
+    way the reference's applyBatchUpdateOmpU does (inc/batch.hxx:239-247: removeEdge + update; a
+    duplicated entry of a multiset row survives its own removal, _algorithm.hxx:132-139).  The
+    pairs must be unique (tidyBatchUpdateU, inc/batch.hxx:200-208); pairs that are not stored are
+    ignored.  torch reference of ``nlp_apply_deletions`` (used by tests and to build workloads)."""
+    S = offsets.numel() - 1
+    dev = keys.device
+    deg = offsets[1:] - offsets[:-1]
+    src = torch.repeat_interleave(torch.arange(S, device=dev, dtype=torch.int64), deg)
+    comp = src * S + keys.to(torch.int64)                     # ascending: rows ascending, rows sorted
+    want = del_u.to(device=dev, dtype=torch.int64) * S + del_v.to(device=dev, dtype=torch.int64)
+    pos = torch.searchsorted(comp, want)                       # first stored copy of every request
+    pos = torch.clamp(pos, max=max(comp.numel() - 1, 0))
+    hit = pos[comp[pos] == want] if comp.numel() else pos[:0]
+    keep = torch.ones(comp.numel(), dtype=torch.bool, device=dev)
+    keep[hit] = False
+    del comp
+    keys2 = keys[keep]
+    deg2 = torch.bincount(src[keep], minlength=S)
+    off2 = torch.zeros(S + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg2, 0, out=off2[1:])
+    return off2, keys2
+
+
 def to_numpy(offsets, keys):
     import numpy as np
     return (offsets.cpu().numpy().astype(np.uint64), keys.cpu().numpy().astype(np.uint32))

@@ -314,3 +314,52 @@ def test_reuse_across_measures(pred, oracle, nlp):
         assert r["phase_ms"][2] > 0.02
     finally:
         pred.set_reuse(False)
+
+
+def test_repeat_semantics(pred, oracle, nlp):
+    """repeat > 1 (inc/predict.hxx:426-430): the scoring phase runs `repeat` times, scoringTime is
+    the MEAN over the repeats, the merge runs once, time = scoringTime + merge; the result is the
+    same as with repeat = 1 -- on both LHub paths and on the IHub kernels."""
+    off, keys = _graph(nlp, "rmat12")
+    pred.set_graph(off, keys)
+    try:
+        for m, D, path in (("JC", 4, PAIR_PATH), ("AA", 16, PAIR_PATH), ("JC", 4, SOURCE_PATH), ("CN", 0, SOURCE_PATH), ("RA", 0, SOURCE_PATH)):
+            pred.set_path(path)
+            r1 = pred.predict(m, D, max_edges=4000, repeat=1)
+            a = pred.fetch(r1["count"])
+            r3 = pred.predict(m, D, max_edges=4000, repeat=3)
+            b = pred.fetch(r3["count"])
+            assert parity.compare(b, a, "repeat=3 vs 1 %s D=%d" % (m, D)) is None
+            want = oracle.oracle_predict(off, keys, m, D, max_edges=4000)[:3]
+            assert parity.compare(b, want, "repeat=3 %s D=%d" % (m, D)) is None
+            for c in ("wedges", "candidates", "kept", "first_hop", "eligible_first_hop"):
+                assert r3[c] == r1[c], (m, D, c, r3[c], r1[c])      # counters are per repeat, not summed
+            assert r3["scoring_ms"] > 0 and r3["time_ms"] >= r3["scoring_ms"]
+            assert abs(r3["time_ms"] - (r3["scoring_ms"] + r3["select_ms"])) < 1e-3
+    finally:
+        pred.set_path(0)
+
+
+def test_lhub_float_long_rows_pruned_buffer(oracle, nlp):
+    """LHub float measures (ordered accumulation), first-hop rows longer than 2048 entries (cut into
+    chunks by the frontier) and the pruned candidate buffer (passes > 1), all at once, on the
+    source-centric kernels; and the same requests on the default path."""
+    g = nlp.graphs
+    off, keys = g.to_numpy(*g.rmat(15, 16, 37))
+    deg = np.diff(off.astype(np.int64))
+    assert deg.max() > 2048, deg.max()
+    K = 3000
+    S = len(off) - 1
+    p = nlp.Predictor(0)
+    try:
+        p.set_graph(off, keys)
+        for path in (SOURCE_PATH, 0):
+            p.set_path(path)
+            p.set_scratch_limit((K + S + 4096 + 60000) * 24 * 10 // 8 + (64 << 20) if path == SOURCE_PATH else 0)
+            for m, D in (("AA", 64), ("RA", 1024), ("AA", 1024), ("JC", 1024)):
+                err, r, st = parity.check_case(p, oracle, off, keys, m, D, K, tag="lhub-float-long-pruned path%d" % path)
+                assert err is None, err
+                if path == SOURCE_PATH and D == 1024:
+                    assert r["passes"] > 1, r
+    finally:
+        p.close()
