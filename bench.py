@@ -384,7 +384,7 @@ def run_b200(args):
     # the other measures of the step reuse the sorted wedge records.  Reported separately; the
     # headline `value` above never reuses anything.
     sweep = None
-    if results and results[0]["path"] == 2 and shard != "sources":
+    if results and results[0]["path"] in (2, 3) and shard != "sources" and args.sweep_reuse:
         def one_step_reuse():
             pred.set_reuse(True)
             return one_step()
@@ -404,18 +404,27 @@ def run_b200(args):
     # ---- roofline of the dominant phase --------------------------------------------------------
     path = results[0]["path"]
     if path == 2:
+        names = ["bucket: plan lookup (built once per graph and D)", "bucket: k_bucket (gather + shared-memory sort + reduce + score)",
+                 "bucket: big sources (k_pair_emit + global radix sort + k_pair_reduce + k_big_place)", "-", "-", "-", "-",
+                 "select+sort (radix top-K)"]
+    elif path == 3:
         names = ["pair: eligible rows + item descriptors + scans", "pair: k_pair_emit (wedge records)",
                  "pair: radix sort by (u,v) (k_tilehist+k_rowscan+k_scatter per digit)", "pair: k_pair_reduce (run count + exclusion + score)",
                  "-", "-", "-", "select+sort (radix top-K)"]
-    else:
-        names = ["frontier(k_elig+k_work+k_bin)", "hub-heavy sources (k_range + k_dense)", "k_hash(16K)", "k_hash(4K)", "k_hash(1K)",
-                 "k_tiny<32>", "k_tiny<8>", "select+sort (radix top-K)"]
     phase = [sum(r["phase_ms"][i] for r in results) for i in range(8)]
     nrun = len(results)
     peak, peak_src = peaks()
     W = sum(r["wedges"] for r in results); C = sum(r["candidates"] for r in results)
     E = sum(r["emitted"] for r in results); Kout = sum(r["count"] for r in results)
     if path == 2:
+        # own traffic of the bucket path: item descriptors (28 B per eligible
+        # first-hop entry), one key per wedge record gathered, 4 B of aligned score per record, 8 B per kept pair
+        P = sum(r["pair_records"] for r in results)
+        elig = sum(r["eligible_first_hop"] for r in results)
+        cands = [(names[1], phase[1], 28 * elig + 4 * P + 4 * P + 8 * E),
+                 (names[2], phase[2], 0.0),
+                 (names[7], phase[7], 4 * 4 * P + 12 * E + 12 * Kout)]
+    elif path == 3:
         # per-phase algorithmic bytes of the pair path
         idbits = max(1, (S - 1).bit_length())
         digits = 2 * ((idbits + 7) // 8)
@@ -545,7 +554,7 @@ def run_b200(args):
         "phase_ms_per_step": {n: p / args.steps for n, p in zip(names, phase)},
         "wall_ms_per_step": wall * 1e3 / args.steps,
         "bins": results[0]["bin_sources"][:7],
-        "path": {1: "source-centric", 2: "pair"}.get(path, path),
+        "path": {1: "source-centric", 2: "bucket (pair)", 3: "pair, global sort"}.get(path, path),
     }
     print(json.dumps(line))
     if world > 1:
@@ -567,6 +576,7 @@ def main():
                          "or the sources of each prediction partitioned (all-gather merge)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run on the host cores")
+    ap.add_argument("--sweep-reuse", action="store_true", help="also time the step with nlp_set_reuse (sorted-record store of the global-sort pair path)")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-list parity check against the C oracle")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -105,7 +105,7 @@ typedef struct {
  *                    eligible row w emits its (u, v>u) pairs, the pairs are radix-sorted and
  *                    run-length reduced.  Falls back to NLP_PATH_SOURCE when not admissible.
  *   NLP_PATH_AUTO    NLP_PATH_PAIR when admissible, else NLP_PATH_SOURCE (default).             */
-typedef enum { NLP_PATH_AUTO = 0, NLP_PATH_SOURCE = 1, NLP_PATH_PAIR = 2 } nlp_path;
+typedef enum { NLP_PATH_AUTO = 0, NLP_PATH_SOURCE = 1, NLP_PATH_PAIR = 2, NLP_PATH_PAIR_SORT = 3 } nlp_path;
 
 /* Create a predictor bound to CUDA device `device` (one process per GPU). */
 int nlp_create(nlp_handle** out, int device);

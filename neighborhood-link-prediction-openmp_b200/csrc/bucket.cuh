@@ -1,0 +1,441 @@
+// LHub bucket path (NLP_PATH_PAIR): the w-centric wedge enumeration of pairs.cuh, regrouped BY
+// SOURCE so that counting needs no global sort at all.
+//
+// The reference counts, for every source u, the entries v > u of the rows of its eligible
+// first-hop neighbours w (inc/predict.hxx:298-304, 153-160).  On a graph with symmetric rows the
+// eligible first-hop entries of u are exactly the entries "u" of the eligible rows w, so they can
+// be listed from w's side (only rows with deg <= D are read -- the reference's dominant LHub cost,
+// the hub test on all |E| first-hop entries of inc/predict.hxx:301, disappears) and then grouped
+// by u once per (graph, D).  That grouping is a pure function of the resident graph and the
+// threshold: it is the PLAN, built on the device the first time a threshold is used and kept
+// until the graph changes.
+//
+//   plan (once per graph and D; k_plan_*):
+//     item      = one eligible first-hop entry (u, w) that has at least one wedge with v > u:
+//                 cnt = #entries of row w above u, ptr = index of the first of them, dw = deg(w)
+//     items are sorted by u (stable: ascending w inside a source, the reference's accumulation
+//     order), so every source owns a contiguous run of items and a contiguous range of wedge
+//     records; roff[source] = first record slot of the source in the record-aligned output.
+//     small sources (<= CAP/2 records) are cut into BUCKETS: windows of CAP/2 records in the
+//     running record count, every source belongs to the window it starts in, so a bucket holds at
+//     most CAP records and at most CAP/2 sources.  The few big sources take the global sort of
+//     pairs.cuh (k_pair_emit -> radix sort -> k_pair_reduce) and are copied into their slots.
+//
+//   per prediction (k_bucket, one thread block per bucket):
+//     gather    the bucket's wedge records (v, local source index[, deg w]) straight from the CSR
+//               rows into shared memory -- they never exist in HBM
+//     sort      stable LSD radix sort in shared memory by (local source, v), 8-bit digits, ranks by
+//               warp-private digit masks (the k_scatter scheme of select.cuh)
+//     reduce    run length = common-neighbour count (or the ordered float fold of AA / RA: the
+//               stable sort kept ascending w), existing-edge exclusion by binary search in row u,
+//               fused scoring (inc/predict.hxx:306-311)
+//     output    record-aligned like k_pair_reduce: score bits at the slot of a run's first record,
+//               NLP_NO_SCORE elsewhere, so the kept pairs lie in ascending (u, v) order and the
+//               ordered top-K of select.cuh only has to sort by score.
+#pragma once
+#include "common.cuh"
+#include "select.cuh"
+#include "wedge.cuh"
+
+namespace nlp {
+
+enum { BK_THREADS = 256, BK_WARPS = 8 };
+constexpr uint32_t BK_CAP_COUNT = 8192;   // records per bucket, count measures (6 B per record x 2 buffers)
+constexpr uint32_t BK_CAP_FLT = 4096;     // float measures carry deg(w) (10 B per record x 2 buffers)
+constexpr uint32_t BK_BIG_NONE = 0xffffffffu;
+
+// ---- plan ------------------------------------------------------------------------------------
+// One thread per row w.  items[w] = entries of an eligible row that have a later, larger entry
+// (rows are sorted multisets: everything below the last key).  Also the graph-only counters of
+// a prediction: first-hop entries, eligible first-hop entries (= sum of deg(w) over eligible w,
+// by symmetry), wedges W(D) = sum of deg(w)^2 (inc/predict.hxx:155).
+__global__ void __launch_bounds__(256) k_plan_rows(DevGraph g, uint32_t D, uint32_t* __restrict__ items, Counters* ctr) {
+  unsigned long long t_first = 0, t_elig = 0, t_wedges = 0;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < g.S; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t d = g.deg[w];
+    t_first += d;
+    uint32_t it = 0;
+    if (d >= 1u && d <= D) {
+      t_elig += d;
+      t_wedges += (unsigned long long)d * d;
+      if (d >= 2u) {
+        const uint64_t wb = __ldg(g.off + w);
+        const uint32_t last = __ldg(g.keys + wb + d - 1);
+        uint32_t j = d - 1;
+        while (j > 0 && __ldg(g.keys + wb + j - 1) == last) --j;
+        it = j;
+      }
+    }
+    items[w] = it;
+  }
+  #pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) {
+    t_first  += __shfl_xor_sync(NLP_FULL, t_first, k);
+    t_elig   += __shfl_xor_sync(NLP_FULL, t_elig, k);
+    t_wedges += __shfl_xor_sync(NLP_FULL, t_wedges, k);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (t_first)  atomicAdd(&ctr->first_hop, t_first);
+    if (t_elig)   atomicAdd(&ctr->eligible_first_hop, t_elig);
+    if (t_wedges) atomicAdd(&ctr->wedges, t_wedges);
+  }
+}
+
+// One thread per eligible row: descriptors of its items, in (w, position) order, plus the
+// (u, item index) pairs the sort by u works on.
+__global__ void __launch_bounds__(256) k_plan_items(DevGraph g, const uint32_t* __restrict__ items,
+                                                    const unsigned long long* __restrict__ item_off,
+                                                    uint32_t* __restrict__ su, uint32_t* __restrict__ sidx,
+                                                    uint32_t* __restrict__ it_cnt, uint32_t* __restrict__ it_dw,
+                                                    unsigned long long* __restrict__ it_ptr) {
+  const uint32_t* __restrict__ keys = g.keys;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < g.S; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t n = items[w];
+    if (!n) continue;
+    const uint32_t d = g.deg[w];
+    const unsigned long long base = item_off[w];
+    const uint64_t wb = __ldg(g.off + w);
+    uint32_t j = 0;                                  // first entry > keys[wb + i]
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t u = __ldg(keys + wb + i);
+      if (j <= i) j = i + 1;
+      while (j < d && __ldg(keys + wb + j) == u) ++j;
+      su[base + i] = u; sidx[base + i] = (uint32_t)(base + i);
+      it_cnt[base + i] = d - j; it_dw[base + i] = d; it_ptr[base + i] = wb + j;
+    }
+  }
+}
+
+// After the stable sort by u: wedge count of every item in sorted order, and the flag "first item
+// of its source".
+__global__ void __launch_bounds__(256) k_plan_heads(const uint32_t* __restrict__ su, const uint32_t* __restrict__ sidx,
+                                                    const uint32_t* __restrict__ it_cnt, uint64_t E,
+                                                    uint32_t* __restrict__ g_cnt, uint32_t* __restrict__ head) {
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < E; j += (uint64_t)gridDim.x * blockDim.x) {
+    g_cnt[j] = it_cnt[sidx[j]];
+    head[j] = (j == 0 || su[j - 1] != su[j]) ? 1u : 0u;
+  }
+}
+
+// Per source (at its first item): first record slot.  src_roff has nsrc + 1 entries.
+__global__ void __launch_bounds__(256) k_plan_sources(const uint32_t* __restrict__ head, const unsigned long long* __restrict__ hs,
+                                                      const unsigned long long* __restrict__ rc, uint64_t E, uint64_t nsrc,
+                                                      uint64_t P, unsigned long long* __restrict__ src_roff) {
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < E; j += (uint64_t)gridDim.x * blockDim.x)
+    if (head[j]) src_roff[hs[j]] = rc[j];
+  if (blockIdx.x == 0 && threadIdx.x == 0) src_roff[nsrc] = P;
+}
+
+// Per item: does its source fit a bucket (records <= half)?  Flags for the three compactions.
+__global__ void __launch_bounds__(256) k_plan_class(const uint32_t* __restrict__ head, const unsigned long long* __restrict__ hs,
+                                                    const unsigned long long* __restrict__ src_roff, const uint32_t* __restrict__ g_cnt,
+                                                    uint64_t E, uint32_t half, uint32_t* __restrict__ f_item,
+                                                    uint32_t* __restrict__ f_cnt, uint32_t* __restrict__ f_src) {
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < E; j += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = hs[j] + head[j] - 1ull;
+    const bool small = src_roff[k + 1] - src_roff[k] <= (unsigned long long)half;
+    f_item[j] = small ? 1u : 0u;
+    f_cnt[j] = small ? g_cnt[j] : 0u;
+    if (head[j]) f_src[k] = small ? 1u : 0u;
+  }
+}
+
+struct BucketPlanDev {
+  // small sources, ascending u; ns + 1 entries where noted
+  const uint32_t* sm_u;                    // [ns]
+  const uint32_t* sm_item;                 // [ns + 1] first item (index into the s_* arrays)
+  const unsigned long long* sm_soff;       // [ns + 1] first record in the bucket (small-only) record space
+  const unsigned long long* sm_roff;       // [ns]     first record slot in the aligned output
+  // items of the small sources, source-major, ascending w inside a source
+  const uint32_t* s_cnt;                   // [Es]
+  const uint32_t* s_dw;                    // [Es]
+  const unsigned long long* s_ptr;         // [Es]
+  const uint32_t* s_src;                   // [Es] index of the item's source in sm_*
+  const unsigned long long* s_loff;        // [Es] first record of the item in the bucket record space
+  uint32_t ns;
+  uint32_t half;                           // bucket window = half records; CAP = 2 * half
+};
+
+struct PlanScatterOut {
+  uint32_t* sm_u; uint32_t* sm_item; unsigned long long* sm_soff; unsigned long long* sm_roff;
+  uint32_t* s_cnt; uint32_t* s_dw; unsigned long long* s_ptr; uint32_t* s_src; unsigned long long* s_loff;
+  uint32_t* b_u; uint32_t* b_cnt; uint32_t* b_dw; unsigned long long* b_ptr; unsigned long long* b_off;
+  unsigned long long* bg_first;            // [nbig + 1] first record of a big source in the big record space
+  unsigned long long* bg_roff;             // [nbig]     its first slot in the aligned output
+  uint32_t* bg_item;                       // [nbig + 1] its first item in the b_* arrays
+};
+
+// Split the sorted items into the small-source arrays and the big-source arrays.
+__global__ void __launch_bounds__(256) k_plan_scatter(const uint32_t* __restrict__ su, const uint32_t* __restrict__ sidx,
+                                                      const uint32_t* __restrict__ it_dw, const unsigned long long* __restrict__ it_ptr,
+                                                      const uint32_t* __restrict__ g_cnt, const uint32_t* __restrict__ head,
+                                                      const unsigned long long* __restrict__ hs, const unsigned long long* __restrict__ rc,
+                                                      const uint32_t* __restrict__ f_item, const unsigned long long* __restrict__ si,
+                                                      const unsigned long long* __restrict__ sr, const unsigned long long* __restrict__ ks,
+                                                      uint64_t E, uint64_t Es, uint64_t Ps, uint64_t ns, uint64_t nbig, uint64_t P,
+                                                      PlanScatterOut o) {
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < E; j += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t idx = sidx[j], u = su[j], cnt = g_cnt[j];
+    const bool hd = head[j] != 0u;
+    const unsigned long long k = hs[j] + (hd ? 1ull : 0ull) - 1ull;
+    if (f_item[j]) {
+      const unsigned long long t = si[j], kk = ks[k];
+      o.s_cnt[t] = cnt; o.s_dw[t] = it_dw[idx]; o.s_ptr[t] = it_ptr[idx]; o.s_src[t] = (uint32_t)kk; o.s_loff[t] = sr[j];
+      if (hd) { o.sm_u[kk] = u; o.sm_item[kk] = (uint32_t)t; o.sm_soff[kk] = sr[j]; o.sm_roff[kk] = rc[j]; }
+    } else {
+      const unsigned long long t = j - si[j], kb = k - ks[k], boff = rc[j] - sr[j];
+      o.b_u[t] = u; o.b_cnt[t] = cnt; o.b_dw[t] = it_dw[idx]; o.b_ptr[t] = it_ptr[idx]; o.b_off[t] = boff;
+      if (hd) { o.bg_first[kb] = boff; o.bg_roff[kb] = rc[j]; o.bg_item[kb] = (uint32_t)t; }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    o.sm_item[ns] = (uint32_t)Es; o.sm_soff[ns] = Ps;
+    o.bg_first[nbig] = P - Ps; o.bg_item[nbig] = (uint32_t)(E - Es);
+  }
+}
+
+// ---- per prediction ----------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t bucket_smem_bytes(bool flt, uint32_t cap) {
+  // key[2][cap] u32, tag[2][cap] u16, (pay[2][cap] u32), hist[8][256], mask[8][256], scan scratch
+  return cap * 4u * 2u + cap * 2u * 2u + (flt ? cap * 4u * 2u : 0u) + BK_WARPS * 256u * 4u * 2u + 64u;
+}
+
+// first index i in [0, n] with a[i] >= x (a ascending, n entries)
+__device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* __restrict__ a, uint32_t n, unsigned long long x) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One stable LSD pass over the n records in shared memory (warp w ranks records
+// [w * 32 * rounds, (w + 1) * 32 * rounds): warp-major order = record order).
+template <bool FLT, int MAXR>
+__device__ __forceinline__ void bucket_sort_pass(const uint32_t* __restrict__ kin, const uint16_t* __restrict__ tin, const uint32_t* __restrict__ pin,
+                                                 uint32_t* __restrict__ kout, uint16_t* __restrict__ tout, uint32_t* __restrict__ pout,
+                                                 uint32_t n, uint32_t rounds, bool by_tag, int shift,
+                                                 uint32_t (*s_hist)[256], uint32_t (*s_mask)[256], uint32_t* s_warp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i = tid; i < BK_WARPS * 256; i += BK_THREADS) { (&s_hist[0][0])[i] = 0; (&s_mask[0][0])[i] = 0; }
+  __syncthreads();
+  uint32_t pre[MAXR];
+  uint32_t* my_mask = s_mask[warp];
+  #pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    if ((uint32_t)r < rounds) {                      // block-uniform
+      const uint32_t idx = (uint32_t)warp * (32u * rounds) + (uint32_t)r * 32u + lane;
+      const bool valid = idx < n;
+      uint32_t d = 0;
+      if (valid) d = by_tag ? (((uint32_t)tin[idx] >> shift) & 255u) : ((kin[idx] >> shift) & 255u);
+      if (valid) atomicOr(my_mask + d, 1u << lane);
+      __syncwarp();
+      const unsigned m = valid ? *reinterpret_cast<volatile uint32_t*>(my_mask + d) : 0u;
+      const uint32_t before = valid ? s_hist[warp][d] : 0u;
+      pre[r] = (d << 16) | (before + __popc(m & lt));
+      __syncwarp();
+      if (valid && (__ffs(m) - 1) == lane) { s_hist[warp][d] = before + __popc(m); my_mask[d] = 0u; }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  {   // thread t owns digit t: exclusive scan over (digit, warp)
+    uint32_t c[BK_WARPS], total = 0;
+    #pragma unroll
+    for (int w = 0; w < BK_WARPS; ++w) { c[w] = s_hist[w][tid]; total += c[w]; }
+    uint32_t run = sort_block_exclusive(total, s_warp);
+    #pragma unroll
+    for (int w = 0; w < BK_WARPS; ++w) { s_hist[w][tid] = run; run += c[w]; }
+  }
+  __syncthreads();
+  #pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    if ((uint32_t)r < rounds) {
+      const uint32_t idx = (uint32_t)warp * (32u * rounds) + (uint32_t)r * 32u + lane;
+      if (idx < n) {
+        const uint32_t pos = s_hist[warp][pre[r] >> 16] + (pre[r] & 0xffffu);
+        kout[pos] = kin[idx]; tout[pos] = tin[idx];
+        if (FLT) pout[pos] = pin[idx];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// One thread block per bucket (window `first_bucket + blockIdx.x` of the bucket record space).
+template <bool FLT>
+__global__ void __launch_bounds__(BK_THREADS, 2)
+k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
+         uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_s) {
+  constexpr uint32_t CAP = FLT ? BK_CAP_FLT : BK_CAP_COUNT;
+  constexpr int MAXR = CAP / BK_THREADS;
+  static_assert(BK_WARPS == SORT_WARPS && BK_THREADS == SORT_THREADS, "sort_block_exclusive is shared with select.cuh");
+  extern __shared__ __align__(16) uint32_t bsm[];
+  uint32_t* key0 = bsm;
+  uint32_t* key1 = key0 + CAP;
+  uint32_t* pay0 = key1 + CAP;                                     // FLT only
+  uint32_t* pay1 = pay0 + (FLT ? CAP : 0);
+  uint16_t* tag0 = reinterpret_cast<uint16_t*>(pay1 + (FLT ? CAP : 0));
+  uint16_t* tag1 = tag0 + CAP;
+  uint32_t (*s_hist)[256] = reinterpret_cast<uint32_t (*)[256]>(tag1 + CAP);
+  uint32_t (*s_mask)[256] = s_hist + BK_WARPS;
+  uint32_t* s_warp = &s_mask[0][0] + BK_WARPS * 256;               // [8] scan scratch, then [8..11] k0, k1
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t* __restrict__ keys = p.g.keys;
+  Tally tally;
+
+  // ---- the bucket: small sources [k0, k1) that start inside the window --------------------------
+  const unsigned long long wlo = (first_bucket + blockIdx.x) * (unsigned long long)pl.half;
+  if (tid == 0)  s_warp[8] = lower_bound_u64(pl.sm_soff, pl.ns + 1u, wlo);
+  if (tid == 32) s_warp[9] = lower_bound_u64(pl.sm_soff, pl.ns + 1u, wlo + pl.half);
+  __syncthreads();
+  const uint32_t k0 = s_warp[8], k1 = min(s_warp[9], pl.ns);
+  if (k0 >= k1) { tally.flush(p.ctr); return; }                    // block-uniform
+  const uint32_t i0 = __ldg(pl.sm_item + k0), i1 = __ldg(pl.sm_item + k1);
+  const unsigned long long base = __ldg(pl.sm_soff + k0);
+  const uint32_t n = (uint32_t)(__ldg(pl.sm_soff + k1) - base);    // <= CAP by construction
+  const uint32_t ns = k1 - k0;
+  if (n > CAP || ns > CAP / 2u) {                                  // cannot happen with a consistent plan
+    if (tid == 0) atomicAdd(&p.ctr->overflow, 1ull);
+    tally.flush(p.ctr);
+    return;
+  }
+
+  // ---- gather: warp per 32 items, wedges packed back to back (as k_pair_emit, into shared memory)
+  for (uint32_t tile = warp; tile * 32u < i1 - i0; tile += BK_WARPS) {
+    const uint32_t e = i0 + tile * 32u + lane;
+    uint32_t cnt = 0, tg = 0, dw = 0;
+    unsigned long long ptr = 0, loff = 0;
+    if (e < i1) {
+      cnt = __ldg(pl.s_cnt + e); ptr = __ldg(pl.s_ptr + e); tg = __ldg(pl.s_src + e) - k0; loff = __ldg(pl.s_loff + e);
+      if (FLT) dw = __ldg(pl.s_dw + e);
+    }
+    const uint32_t out0 = (uint32_t)(__shfl_sync(NLP_FULL, loff, 0) - base);
+    uint32_t inc = cnt;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+      if (lane >= d) inc += t;
+    }
+    const uint32_t tot = __shfl_sync(NLP_FULL, inc, 31);
+    for (uint32_t sb = 0; sb < tot; sb += 32u) {
+      const uint32_t idx = sb + lane;
+      int j = 0;                                      // smallest j with inc[j] > idx
+      #pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
+        if (x <= idx) j += step;
+      }
+      const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
+      const uint32_t cntj = __shfl_sync(NLP_FULL, cnt, j);
+      const uint32_t tgj  = __shfl_sync(NLP_FULL, tg, j);
+      const unsigned long long ptrj = __shfl_sync(NLP_FULL, ptr, j);
+      uint32_t dwj = 0;
+      if (FLT) dwj = __shfl_sync(NLP_FULL, dw, j);
+      if (idx < tot) {
+        const uint32_t v = __ldg(keys + ptrj + (idx - (incj - cntj)));
+        const uint32_t o = out0 + idx;
+        if (o < CAP) {
+          key0[o] = v; tag0[o] = (uint16_t)tgj;
+          if (FLT) pay0[o] = dwj;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- stable LSD radix sort by (local source, v) ---------------------------------------------
+  const uint32_t rounds = (n + BK_THREADS - 1) / BK_THREADS;
+  uint32_t *ka = key0, *kb = key1, *pa = pay0, *pb = pay1;
+  uint16_t *ta = tag0, *tb = tag1;
+  for (int ps = 0; ps < key_passes; ++ps) {
+    bucket_sort_pass<FLT, MAXR>(ka, ta, pa, kb, tb, pb, n, rounds, false, ps * 8, s_hist, s_mask, s_warp);
+    uint32_t* t1 = ka; ka = kb; kb = t1; uint16_t* t2 = ta; ta = tb; tb = t2; t1 = pa; pa = pb; pb = t1;
+  }
+  if (ns > 1u) {
+    bucket_sort_pass<FLT, MAXR>(ka, ta, pa, kb, tb, pb, n, rounds, true, 0, s_hist, s_mask, s_warp);
+    uint32_t* t1 = ka; ka = kb; kb = t1; uint16_t* t2 = ta; ta = tb; tb = t2; t1 = pa; pa = pb; pb = t1;
+    if (ns > 256u) {
+      bucket_sort_pass<FLT, MAXR>(ka, ta, pa, kb, tb, pb, n, rounds, true, 8, s_hist, s_mask, s_warp);
+      t1 = ka; ka = kb; kb = t1; t2 = ta; ta = tb; tb = t2; t1 = pa; pa = pb; pb = t1;
+    }
+  }
+  // (ka, ta, pa) hold the sorted records; the other key / tag buffers are free now and take the
+  // per-source caches: source vertex, and (aligned slot of the source's first record) - (its
+  // local index) as two 32-bit halves.  ns <= CAP / 2.
+  uint32_t* c_u = kb;                                              // [CAP / 2]
+  uint32_t* c_dlo = kb + CAP / 2;                                  // [CAP / 2]
+  uint32_t* c_dhi = reinterpret_cast<uint32_t*>(tb);               // [CAP / 2] (CAP u16 = CAP / 2 u32)
+  for (uint32_t i = tid; i < ns; i += BK_THREADS) {
+    c_u[i] = __ldg(pl.sm_u + k0 + i);
+    const unsigned long long delta = __ldg(pl.sm_roff + k0 + i) - (__ldg(pl.sm_soff + k0 + i) - base);
+    c_dlo[i] = (uint32_t)delta; c_dhi[i] = (uint32_t)(delta >> 32);
+  }
+  __syncthreads();
+
+  // ---- reduce runs, exclude existing edges, score, record-aligned output ------------------------
+  for (uint32_t r = 0; r < rounds; ++r) {
+    const uint32_t idx = r * BK_THREADS + tid;
+    const bool valid = idx < n;
+    uint32_t v = 0, tg = 0, u = 0, cnt = 0;
+    uint64_t du = 0;
+    float acc = 0.0f;
+    bool head = false;
+    if (valid) {
+      v = ka[idx]; tg = ta[idx];
+      head = idx == 0 || ka[idx - 1] != v || ta[idx - 1] != tg;
+    }
+    if (head) {
+      u = c_u[tg];
+      if (FLT) {   // inc/predict.hxx:788,828: acc = float(double(acc) + term), ascending w
+        uint32_t j = idx;
+        do {
+          acc = __double2float_rn(__dadd_rn((double)acc, flt_term(p, pa[j])));
+          ++j;
+        } while (j < n && ka[j] == v && ta[j] == tg);
+      } else {
+        uint32_t j = idx + 1;
+        while (j < n && ka[j] == v && ta[j] == tg) ++j;
+        cnt = j - idx;
+      }
+      const uint64_t ub = __ldg(p.g.off + u);
+      du = __ldg(p.g.deg + u);
+      // existing edges keep their candidate slot with value 0 (inc/predict.hxx:306-307)
+      if (row_contains(keys, ub, (uint32_t)du, v)) { cnt = 0; acc = 0.0f; }
+    }
+    float score;
+    const bool keep = score_pair(p, head, u, du, v, cnt, acc, tally, &score);
+    if (valid) {
+      const unsigned long long slot = (((unsigned long long)c_dhi[tg] << 32) | c_dlo[tg]) + idx;
+      al_s[slot] = keep ? __float_as_uint(score) : NLP_NO_SCORE;
+      if (keep) { al_u[slot] = u; al_v[slot] = v; }
+    }
+  }
+  tally.flush(p.ctr);
+}
+
+// Big sources: their records were sorted and reduced by the global machinery of pairs.cuh in the
+// candidate buffers (record j of the big record space, local index j - first); copy them into
+// their slots of the aligned output.
+__global__ void __launch_bounds__(256) k_big_place(const uint32_t* __restrict__ pu, const uint32_t* __restrict__ pv,
+                                                   const uint32_t* __restrict__ ps, uint64_t n, uint64_t first,
+                                                   const unsigned long long* __restrict__ bg_first,
+                                                   const unsigned long long* __restrict__ bg_roff, uint32_t kb0, uint32_t kb1,
+                                                   uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_s) {
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long pos = first + j;
+    uint32_t lo = kb0, hi = kb1;                     // last big source with bg_first <= pos
+    while (lo + 1 < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldg(bg_first + mid) <= pos) lo = mid; else hi = mid;
+    }
+    const unsigned long long slot = __ldg(bg_roff + lo) + (pos - __ldg(bg_first + lo));
+    const uint32_t s = ps[j];
+    al_s[slot] = s;
+    if (s != NLP_NO_SCORE) { al_u[slot] = pu[j]; al_v[slot] = pv[j]; }
+  }
+}
+
+}  // namespace nlp

@@ -9,6 +9,7 @@
 #include "wedge.cuh"
 #include "select.cuh"
 #include "pairs.cuh"
+#include "bucket.cuh"
 #include "evaluate.cuh"
 #include "batch.cuh"
 
@@ -95,6 +96,26 @@ struct nlp_handle {
   std::map<uint64_t, PairCache> pair_cache;
   int reuse = 0;
   uint64_t cache_bytes = 0, cache_stamp = 0;
+  // bucket path (bucket.cuh): the per-(D, bucket size) plan -- items grouped by source, bucket and
+  // slot offsets -- is a pure function of the resident graph, built once and kept until the graph
+  // changes; `arena` is one allocation that all its arrays are carved from
+  struct BucketPlan {
+    DevBuf arena;
+    BucketPlanDev dev;
+    PairItems big_items{nullptr, nullptr, nullptr, nullptr};
+    const unsigned long long* b_off = nullptr; const unsigned long long* bg_first = nullptr;
+    const unsigned long long* bg_roff = nullptr; const uint32_t* bg_item = nullptr;
+    uint64_t E = 0, P = 0, Es = 0, Ps = 0, ns = 0, nbig = 0, Eb = 0, Pb = 0;
+    uint64_t first_hop = 0, elig = 0, wedges = 0, stamp = 0;
+    std::vector<unsigned long long> h_bg_first;   // host copies: the big sources are few
+    std::vector<uint32_t> h_bg_item;
+    bool usable = false;                     // false: too large for the scratch budget (source path instead)
+  };
+  std::map<uint64_t, BucketPlan> plans;
+  uint64_t plan_bytes = 0;
+  DevBuf plan_tmp;                           // scratch of a plan build (kept: no allocation churn)
+  DevBuf al_u, al_v, al_s;                   // record-aligned output of the bucket path
+  const uint32_t* pair_ps = nullptr;         // aligned score bits when the records live outside the candidate buffers
   // asynchronous fetch: result -> staging (device copy on the compute stream) -> caller memory
   // (copy stream), double buffered, so the next prediction overlaps the transfer
   cudaStream_t copy_stream = nullptr;
@@ -222,6 +243,12 @@ void clear_pair_cache(nlp_handle* h) {
   h->cache_bytes = 0;
 }
 
+void clear_plans(nlp_handle* h) {
+  for (auto& kv : h->plans) release(kv.second.arena);
+  h->plans.clear();
+  h->plan_bytes = 0;
+}
+
 int finish_graph(nlp_handle* h) {
   const uint32_t S = h->S;
   NLP_TRY(ensure(h, h->deg, (size_t)S * 4));
@@ -264,6 +291,7 @@ int finish_graph(nlp_handle* h) {
   h->sym_state = 0;
   h->pair_sizes.clear();
   clear_pair_cache(h);
+  clear_plans(h);
   NLP_TRY(measure_budget(h));
   h->has_graph = true;
   h->has_result = false;
@@ -398,9 +426,10 @@ int top_k_ordered(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
   const uint32_t* pv = h->pair_pv;
   const uint64_t n = h->pair_n, kept = h->pair_kept;
   const int sbuf = h->pair_score_buf, ob = sbuf ^ 1;
-  *out_buf = ob; *out_n = 0;
+  const bool external = h->pair_ps != nullptr;       // bucket path: records and scores in the aligned arrays
+  *out_buf = external ? 0 : ob; *out_n = 0;
   if (!n || !kept) return NLP_OK;
-  const uint32_t* sbits = (const uint32_t*)h->cs[sbuf].p;
+  const uint32_t* sbits = external ? h->pair_ps : (const uint32_t*)h->cs[sbuf].p;
   int mode = 0;
   if (K < kept) {
     NLP_CUDA(h, cudaMemsetAsync(h->sel.p, 0, sizeof(SelectState), h->stream));
@@ -422,14 +451,16 @@ int top_k_ordered(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
   NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &m));
   // Survivors go to buffer `ob`.  When the records live in candidate buffer `ob` themselves (no
   // cache), its u/v arrays are still being read: write to (cu[sbuf], cv[sbuf], cs[ob]) instead and
-  // swap the two score arrays afterwards, which makes that triple buffer `sbuf`.
+  // swap the two score arrays afterwards, which makes that triple buffer `sbuf`.  External records
+  // (bucket path): survivors simply go to buffer 0.
   int res = ob;
   uint32_t *ou = (uint32_t*)h->cu[ob].p, *ov = (uint32_t*)h->cv[ob].p, *os = (uint32_t*)h->cs[ob].p;
-  if (!h->pair_from_cache) { ou = (uint32_t*)h->cu[sbuf].p; ov = (uint32_t*)h->cv[sbuf].p; res = sbuf; }
+  if (external) { res = 0; ou = (uint32_t*)h->cu[0].p; ov = (uint32_t*)h->cv[0].p; os = (uint32_t*)h->cs[0].p; }
+  else if (!h->pair_from_cache) { ou = (uint32_t*)h->cu[sbuf].p; ov = (uint32_t*)h->cv[sbuf].p; res = sbuf; }
   k_ordered_write<<<ntiles, OC_THREADS, 0, h->stream>>>(pu, pv, sbits, n, (const SelectState*)h->sel.p, mode,
                                                         (const unsigned long long*)h->oc_off.p, ou, ov, os);
   NLP_LAUNCHED(h);
-  if (!h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
+  if (!external && !h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
   NLP_TRY(radix_sort(h, res, m, out_buf, 8));      // score digits only
   *out_n = std::min(m, K);
   return NLP_OK;
@@ -543,6 +574,255 @@ int measure_budget(nlp_handle* h) {
   return NLP_OK;
 }
 
+// Rows symmetric (entry multiplicities mirrored)?  Checked once per graph on the device; the
+// w-centric LHub paths are only admissible then.
+int check_symmetry(nlp_handle* h) {
+  if (h->sym_state != 0) return NLP_OK;
+  const DevGraph g = dev_graph(h);
+  NLP_TRY(ensure(h, h->sym_flag, 32));
+  NLP_CUDA(h, cudaMemsetAsync(h->sym_flag.p, 0, 32, h->stream));
+  if (h->M) {
+    k_symmetry<<<grid_for(h->M, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, h->M, (unsigned int*)h->sym_flag.p,
+                                                                              (unsigned long long*)h->sym_flag.p + 1);
+    NLP_LAUNCHED(h);
+  }
+  unsigned long long sf[3] = {0, 0, 0};              // {asym flag, entries u < w, entries u > w}
+  NLP_CUDA(h, cudaMemcpyAsync(sf, h->sym_flag.p, 24, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  const bool f = (unsigned int)sf[0] != 0u || sf[1] != sf[2];
+  h->sym_state = f ? 2 : 1;
+  // the check is graph preparation, not part of the prediction: restart the clock
+  NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
+  return NLP_OK;
+}
+
+// ---- bucket path (bucket.cuh) ----------------------------------------------------------------
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  template <class T> T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += (n ? n : 1) * sizeof(T);
+    return p;
+  }
+};
+
+// cudaMalloc that reports failure instead of raising an ABI error: the caller falls back to
+// another path (the sticky-free allocation error is cleared).
+bool try_ensure(nlp_handle* h, DevBuf& b, size_t bytes) {
+  (void)h;
+  if (bytes <= b.cap && b.p) return true;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  if (bytes == 0) bytes = 16;
+  if (cudaMalloc(&b.p, bytes) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; b.cap = 0; return false; }
+  b.cap = bytes;
+  return true;
+}
+
+// Build the plan of threshold D for buckets of 2 * half records.  plan.usable stays false when it
+// does not fit the scratch budget (the caller runs another path).
+int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan& plan) {
+  const uint32_t S = h->S;
+  const DevGraph g = dev_graph(h);
+  Counters* hc = h->h_ctr;
+  plan.usable = false;
+  uint64_t budget = 0;
+  NLP_TRY(scratch_budget(h, &budget));
+  NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
+  k_plan_rows<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, D, (uint32_t*)h->work.p, (Counters*)h->ctr.p);
+  NLP_LAUNCHED(h);
+  uint64_t E = 0;
+  NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->work.p, S, (unsigned long long*)h->work64.p, &E));
+  NLP_TRY(read_counters(h));
+  plan.first_hop = hc->first_hop; plan.elig = hc->eligible_first_hop; plan.wedges = hc->wedges;
+  plan.E = E;
+  if (E == 0) { plan.usable = true; return NLP_OK; }            // no wedge with v > u at all
+  if (E >= 0xfffffff0ull || E * 120 > budget / 2) return NLP_OK;
+  NLP_TRY(ensure_candidates(h, E));
+  // scratch of the build, one allocation
+  uint32_t *it_cnt, *it_dw, *g_cnt, *head, *f_item, *f_cnt, *f_src;
+  unsigned long long *it_ptr, *hs, *rc, *si, *sr, *ks, *src_roff;
+  auto carve_tmp = [&](Carver& c) {
+    it_cnt = c.take<uint32_t>(E); it_dw = c.take<uint32_t>(E); it_ptr = c.take<unsigned long long>(E);
+    g_cnt = c.take<uint32_t>(E); head = c.take<uint32_t>(E); hs = c.take<unsigned long long>(E);
+    rc = c.take<unsigned long long>(E); f_item = c.take<uint32_t>(E); f_cnt = c.take<uint32_t>(E);
+    f_src = c.take<uint32_t>(E); si = c.take<unsigned long long>(E); sr = c.take<unsigned long long>(E);
+    ks = c.take<unsigned long long>(E); src_roff = c.take<unsigned long long>(E + 1);
+  };
+  { Carver c(nullptr); carve_tmp(c); if (!try_ensure(h, h->plan_tmp, c.off + 256)) return NLP_OK; }
+  { Carver c(h->plan_tmp.p); carve_tmp(c); }
+  const unsigned gS = grid_for(S, 256, h->num_sms * 8), gE = grid_for(E, 256, h->num_sms * 16);
+  k_plan_items<<<gS, 256, 0, h->stream>>>(g, (const uint32_t*)h->work.p, (const unsigned long long*)h->work64.p,
+                                          (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, it_cnt, it_dw, it_ptr);
+  NLP_LAUNCHED(h);
+  int buf = 0;
+  {   // stable sort of (u, item index) by u: only the digits below bits(S - 1)
+    const uint32_t nblocks = (uint32_t)((E + SORT_TILE - 1) / SORT_TILE);
+    NLP_TRY(ensure(h, h->counts, (size_t)nblocks * 256 * 4));
+    const uint32_t top = S ? S - 1 : 0;
+    for (int pass = 4; pass < 8; ++pass) {
+      if ((top >> ((pass % 4) * 8)) == 0) continue;
+      NLP_TRY(radix_pass(h, buf, E, nblocks, pass, false));
+    }
+  }
+  const uint32_t* su = (const uint32_t*)h->cu[buf].p;
+  const uint32_t* sidx = (const uint32_t*)h->cv[buf].p;
+  k_plan_heads<<<gE, 256, 0, h->stream>>>(su, sidx, it_cnt, E, g_cnt, head);
+  NLP_LAUNCHED(h);
+  uint64_t nsrc = 0, P = 0;
+  NLP_TRY(exclusive_scan<uint32_t>(h, head, E, hs, &nsrc));
+  NLP_TRY(exclusive_scan<uint32_t>(h, g_cnt, E, rc, &P));
+  plan.P = P;
+  if (P >= 0xfffffff0ull) return NLP_OK;
+  k_plan_sources<<<gE, 256, 0, h->stream>>>(head, hs, rc, E, nsrc, P, src_roff);
+  NLP_LAUNCHED(h);
+  k_plan_class<<<gE, 256, 0, h->stream>>>(head, hs, src_roff, g_cnt, E, half, f_item, f_cnt, f_src);
+  NLP_LAUNCHED(h);
+  uint64_t Es = 0, Ps = 0, ns = 0;
+  NLP_TRY(exclusive_scan<uint32_t>(h, f_item, E, si, &Es));
+  NLP_TRY(exclusive_scan<uint32_t>(h, f_cnt, E, sr, &Ps));
+  NLP_TRY(exclusive_scan<uint32_t>(h, f_src, nsrc, ks, &ns));
+  const uint64_t nbig = nsrc - ns, Eb = E - Es, Pb = P - Ps;
+  plan.Es = Es; plan.Ps = Ps; plan.ns = ns; plan.nbig = nbig; plan.Eb = Eb; plan.Pb = Pb;
+  // the plan itself, one allocation
+  PlanScatterOut o;
+  auto carve_plan = [&](Carver& c) {
+    o.sm_u = c.take<uint32_t>(ns); o.sm_item = c.take<uint32_t>(ns + 1);
+    o.sm_soff = c.take<unsigned long long>(ns + 1); o.sm_roff = c.take<unsigned long long>(ns);
+    o.s_cnt = c.take<uint32_t>(Es); o.s_dw = c.take<uint32_t>(Es); o.s_ptr = c.take<unsigned long long>(Es);
+    o.s_src = c.take<uint32_t>(Es); o.s_loff = c.take<unsigned long long>(Es);
+    o.b_u = c.take<uint32_t>(Eb); o.b_cnt = c.take<uint32_t>(Eb); o.b_dw = c.take<uint32_t>(Eb);
+    o.b_ptr = c.take<unsigned long long>(Eb); o.b_off = c.take<unsigned long long>(Eb);
+    o.bg_first = c.take<unsigned long long>(nbig + 1); o.bg_roff = c.take<unsigned long long>(nbig);
+    o.bg_item = c.take<uint32_t>(nbig + 1);
+  };
+  size_t bytes = 0;
+  { Carver c(nullptr); carve_plan(c); bytes = c.off + 256; }
+  // keep the plans of a sweep (main.cxx: 11 thresholds) within a quarter of the budget, oldest first out
+  while (h->plan_bytes + bytes > budget / 4 && !h->plans.empty()) {
+    auto lru = h->plans.end();
+    for (auto i = h->plans.begin(); i != h->plans.end(); ++i)
+      if (&i->second != &plan && (lru == h->plans.end() || i->second.stamp < lru->second.stamp)) lru = i;
+    if (lru == h->plans.end()) break;
+    h->plan_bytes -= lru->second.arena.cap;
+    release(lru->second.arena);
+    h->plans.erase(lru);
+  }
+  if (h->plan_bytes + bytes > budget / 4) return NLP_OK;
+  if (!try_ensure(h, plan.arena, bytes)) return NLP_OK;
+  h->plan_bytes += plan.arena.cap;
+  { Carver c(plan.arena.p); carve_plan(c); }
+  k_plan_scatter<<<gE, 256, 0, h->stream>>>(su, sidx, it_dw, it_ptr, g_cnt, head, hs, rc, f_item, si, sr, ks,
+                                            E, Es, Ps, ns, nbig, P, o);
+  NLP_LAUNCHED(h);
+  plan.dev.sm_u = o.sm_u; plan.dev.sm_item = o.sm_item; plan.dev.sm_soff = o.sm_soff; plan.dev.sm_roff = o.sm_roff;
+  plan.dev.s_cnt = o.s_cnt; plan.dev.s_dw = o.s_dw; plan.dev.s_ptr = o.s_ptr; plan.dev.s_src = o.s_src; plan.dev.s_loff = o.s_loff;
+  plan.dev.ns = (uint32_t)ns; plan.dev.half = half;
+  plan.big_items.u = o.b_u; plan.big_items.cnt = o.b_cnt; plan.big_items.dw = o.b_dw; plan.big_items.ptr = o.b_ptr;
+  plan.b_off = o.b_off; plan.bg_first = o.bg_first; plan.bg_roff = o.bg_roff; plan.bg_item = o.bg_item;
+  plan.h_bg_first.assign(nbig + 1, 0); plan.h_bg_item.assign(nbig + 1, 0);
+  NLP_CUDA(h, cudaMemcpyAsync(plan.h_bg_first.data(), o.bg_first, (nbig + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(plan.h_bg_item.data(), o.bg_item, (nbig + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  plan.usable = true;
+  return NLP_OK;
+}
+
+// LHub bucket path.  *used stays false when the graph's rows are not symmetric or the plan / the
+// aligned output do not fit the scratch budget; the caller then runs the source-centric kernels.
+template <bool FLT>
+int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_buf, uint64_t* out_fill, bool* used) {
+  *used = false;
+  NLP_TRY(check_symmetry(h));
+  if (h->sym_state != 1) return NLP_OK;
+  const uint32_t half = (FLT ? BK_CAP_FLT : BK_CAP_COUNT) / 2u;
+  const uint64_t key = ((uint64_t)opt->min_degree1 << 16) | half;
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    nlp_handle::BucketPlan& np = h->plans[key];
+    const int rc = build_plan(h, opt->min_degree1, half, np);
+    if (rc != NLP_OK) { h->plan_bytes -= std::min<uint64_t>(h->plan_bytes, np.arena.cap); release(np.arena); h->plans.erase(key); return rc; }
+    it = h->plans.find(key);
+  }
+  nlp_handle::BucketPlan& plan = it->second;
+  plan.stamp = ++h->cache_stamp;
+  if (!plan.usable) return NLP_OK;
+  const uint64_t P = plan.P;
+  uint64_t budget = 0;
+  NLP_TRY(scratch_budget(h, &budget));
+  if ((P + 2 * (uint64_t)SORT_TILE) * 36 + h->plan_bytes > budget) return NLP_OK;
+  const uint64_t padded = (P + OC_TILE) / OC_TILE * OC_TILE + 1024;
+  if (!try_ensure(h, h->al_u, padded * 4) || !try_ensure(h, h->al_v, padded * 4) || !try_ensure(h, h->al_s, padded * 4)) return NLP_OK;
+  NLP_TRY(ensure_candidates(h, P));
+  Counters* hc = h->h_ctr;
+  NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
+  NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
+  Params p;
+  memset(&p, 0, sizeof p);
+  p.g = dev_graph(h); p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
+  p.gtable = (const double*)h->gtable.p;
+  p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
+  p.cap = h->cand_cap;
+  h->phases_valid = false;
+  NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
+  NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
+  uint32_t* al_u = (uint32_t*)h->al_u.p; uint32_t* al_v = (uint32_t*)h->al_v.p; uint32_t* al_s = (uint32_t*)h->al_s.p;
+  const uint64_t rank = (uint64_t)h->rank, world = (uint64_t)h->world;
+  if (P && world > 1) NLP_CUDA(h, cudaMemsetAsync(al_s, 0xff, P * 4, h->stream));   // slots of the other ranks: NLP_NO_SCORE
+  // small sources: one block per bucket, this rank's contiguous share of the buckets
+  const uint64_t nb = (plan.Ps + half - 1) / half;
+  const uint64_t b0 = nb * rank / world, b1 = nb * (rank + 1) / world;
+  if (b1 > b0) {
+    const uint32_t top = h->S ? h->S - 1 : 0;
+    int key_passes = 0;
+    while (key_passes < 4 && (top >> (8 * key_passes)) != 0) ++key_passes;
+    auto kern = k_bucket<FLT>;
+    const uint32_t smem = bucket_smem_bytes(FLT, FLT ? BK_CAP_FLT : BK_CAP_COUNT);
+    NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (uint64_t s0 = b0; s0 < b1; s0 += 0x7fffffffull) {          // grid.x limit
+      const unsigned grid = (unsigned)std::min<uint64_t>(b1 - s0, 0x7fffffffull);
+      kern<<<grid, BK_THREADS, smem, h->stream>>>(p, plan.dev, s0, key_passes, al_u, al_v, al_s);
+      NLP_LAUNCHED(h);
+    }
+  }
+  NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
+  // big sources: global sort of their records (pairs.cuh), then into their slots
+  const uint64_t kb0 = plan.nbig * rank / world, kb1 = plan.nbig * (rank + 1) / world;
+  if (kb1 > kb0) {
+    const uint64_t ib0 = plan.h_bg_item[kb0], ib1 = plan.h_bg_item[kb1];
+    const uint64_t r0 = plan.h_bg_first[kb0], r1 = plan.h_bg_first[kb1];
+    const uint64_t Eb = ib1 - ib0, Pb = r1 - r0;
+    PairItems bi = plan.big_items;
+    bi.u += ib0; bi.cnt += ib0; bi.dw += ib0; bi.ptr += ib0;
+    k_pair_emit<FLT><<<grid_for(Eb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+        p.g.keys, Eb, bi, plan.b_off + ib0, (unsigned long long)r0, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+    NLP_LAUNCHED(h);
+    int sb = 0;
+    NLP_TRY(radix_sort_pairs(h, 0, Pb, FLT, &sb));
+    k_pair_reduce<FLT><<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+        p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, Pb, (uint32_t*)h->cs[sb ^ 1].p);
+    NLP_LAUNCHED(h);
+    k_big_place<<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+        (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb ^ 1].p, Pb, r0,
+        plan.bg_first, plan.bg_roff, (uint32_t)kb0, (uint32_t)kb1, al_u, al_v, al_s);
+    NLP_LAUNCHED(h);
+  }
+  for (int i = 2; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
+  h->phases_valid = true;
+  NLP_TRY(read_counters(h));
+  if (hc->overflow) return fail(h, NLP_ERR_CAPACITY, "internal: bucket overflow (inconsistent plan)");
+  res->first_hop = plan.first_hop; res->eligible_first_hop = plan.elig; res->wedges = plan.wedges;
+  res->candidates = hc->candidates; res->kept = hc->kept; res->emitted = hc->kept;
+  res->passes = 1; res->path = NLP_PATH_PAIR; res->pair_records = P;
+  res->bin_sources[0] = plan.ns; res->bin_sources[1] = plan.nbig;
+  h->pair_pending = true; h->pair_from_cache = true; h->pair_n = P; h->pair_kept = hc->kept;
+  h->pair_pu = al_u; h->pair_pv = al_v; h->pair_ps = al_s; h->pair_score_buf = 0;
+  *out_buf = 0; *out_fill = hc->kept; *used = true;
+  return NLP_OK;
+}
+
 // LHub pair path (pairs.cuh).  *used stays false when the graph's rows are not symmetric or the
 // wedge records do not fit the scratch budget; the caller then runs the source-centric kernels.
 template <bool FLT>
@@ -550,22 +830,7 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   *used = false;
   const uint32_t S = h->S;
   const DevGraph g = dev_graph(h);
-  if (h->sym_state == 0) {
-    NLP_TRY(ensure(h, h->sym_flag, 32));
-    NLP_CUDA(h, cudaMemsetAsync(h->sym_flag.p, 0, 32, h->stream));
-    if (h->M) {
-      k_symmetry<<<grid_for(h->M, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, h->M, (unsigned int*)h->sym_flag.p,
-                                                                                (unsigned long long*)h->sym_flag.p + 1);
-      NLP_LAUNCHED(h);
-    }
-    unsigned long long sf[3] = {0, 0, 0};              // {asym flag, entries u < w, entries u > w}
-    NLP_CUDA(h, cudaMemcpyAsync(sf, h->sym_flag.p, 24, cudaMemcpyDeviceToHost, h->stream));
-    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
-    const bool f = (unsigned int)sf[0] != 0u || sf[1] != sf[2];
-    h->sym_state = f ? 2 : 1;
-    // the check is graph preparation, not part of the prediction: restart the clock
-    NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
-  }
+  NLP_TRY(check_symmetry(h));
   if (h->sym_state != 1) return NLP_OK;
   Counters* hc = h->h_ctr;
   NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
@@ -599,8 +864,8 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
       NLP_TRY(read_counters(h));
       res->first_hop = c.first_hop; res->eligible_first_hop = c.elig; res->wedges = c.wedges;
       res->candidates = hc->candidates; res->kept = hc->kept; res->emitted = hc->kept;
-      res->passes = 1; res->path = NLP_PATH_PAIR; res->pair_records = P;
-      h->pair_pending = true; h->pair_from_cache = true; h->pair_n = P; h->pair_kept = hc->kept;
+      res->passes = 1; res->path = NLP_PATH_PAIR_SORT; res->pair_records = P;
+      h->pair_pending = true; h->pair_from_cache = true; h->pair_n = P; h->pair_kept = hc->kept; h->pair_ps = nullptr;
       h->pair_pu = (const uint32_t*)c.u.p; h->pair_pv = (const uint32_t*)c.v.p; h->pair_score_buf = 0;
       *out_buf = 1; *out_fill = hc->kept; *used = true;
       return NLP_OK;
@@ -645,10 +910,10 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   if (P) {
     if (payload)
       k_pair_emit<true><<<grid_for(E, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-          g.keys, E, it, (const unsigned long long*)h->it_off.p, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+          g.keys, E, it, (const unsigned long long*)h->it_off.p, 0ull, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
     else
       k_pair_emit<false><<<grid_for(E, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-          g.keys, E, it, (const unsigned long long*)h->it_off.p, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+          g.keys, E, it, (const unsigned long long*)h->it_off.p, 0ull, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
     NLP_LAUNCHED(h);
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
     NLP_TRY(radix_sort_pairs(h, 0, P, payload, &sb));
@@ -669,9 +934,9 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   res->kept = hc->kept;
   res->emitted = hc->kept;
   res->passes = 1;
-  res->path = NLP_PATH_PAIR;
+  res->path = NLP_PATH_PAIR_SORT;
   res->pair_records = P;
-  h->pair_pending = true; h->pair_from_cache = false; h->pair_n = P; h->pair_kept = hc->kept;
+  h->pair_pending = true; h->pair_from_cache = false; h->pair_n = P; h->pair_kept = hc->kept; h->pair_ps = nullptr;
   h->pair_pu = (const uint32_t*)h->cu[sb].p; h->pair_pv = (const uint32_t*)h->cv[sb].p; h->pair_score_buf = cur;
   if (h->reuse && P) {
     // keep a copy of the sorted records (after the reduce kernel is queued: same stream, so the
@@ -733,7 +998,9 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
 
   if (lhub && h->path_mode != NLP_PATH_SOURCE) {
     bool used = false;
-    NLP_TRY(pair_pass<FLT>(h, opt, res, out_buf, out_fill, &used));
+    // reuse across measures still lives on the sorted-record store of the global-sort path
+    if (h->path_mode == NLP_PATH_PAIR_SORT || h->reuse) NLP_TRY(pair_pass<FLT>(h, opt, res, out_buf, out_fill, &used));
+    else NLP_TRY(bucket_pass<FLT>(h, opt, res, out_buf, out_fill, &used));
     if (used) return NLP_OK;
   }
   res->path = NLP_PATH_SOURCE;
@@ -1006,6 +1273,8 @@ int nlp_destroy(nlp_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   clear_pair_cache(h);
+  clear_plans(h);
+  release(h->plan_tmp); release(h->al_u); release(h->al_v); release(h->al_s);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (int i = 0; i < 2; ++i) {
     release(h->stg_u[i]); release(h->stg_v[i]); release(h->stg_s[i]);
@@ -1084,7 +1353,7 @@ int nlp_set_reuse(nlp_handle* h, int on) {
 
 int nlp_set_path(nlp_handle* h, int path) {
   if (!h) return NLP_ERR_ARG;
-  if (path != NLP_PATH_AUTO && path != NLP_PATH_SOURCE && path != NLP_PATH_PAIR) return fail(h, NLP_ERR_ARG, "nlp_set_path: unknown path");
+  if (path != NLP_PATH_AUTO && path != NLP_PATH_SOURCE && path != NLP_PATH_PAIR && path != NLP_PATH_PAIR_SORT) return fail(h, NLP_ERR_ARG, "nlp_set_path: unknown path");
   h->path_mode = path;
   return NLP_OK;
 }

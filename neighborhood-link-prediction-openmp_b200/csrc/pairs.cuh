@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_pair_items(DevGraph g, const uint32_t* 
 // One warp per 32 consecutive items; record k of the warp's tile lands at pair_off[first item] + k.
 template <bool FLT>
 __global__ void __launch_bounds__(256) k_pair_emit(const uint32_t* __restrict__ keys, uint64_t E, PairItems it,
-                                                   const unsigned long long* __restrict__ pair_off,
+                                                   const unsigned long long* __restrict__ pair_off, unsigned long long base,
                                                    uint32_t* __restrict__ pu, uint32_t* __restrict__ pv, uint32_t* __restrict__ pw) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_pair_emit(const uint32_t* __restrict__ 
     uint32_t cnt = 0, u = 0, dw = 0;
     unsigned long long ptr = 0;
     if (e < E) { cnt = it.cnt[e]; u = it.u[e]; ptr = it.ptr[e]; if (FLT) dw = it.dw[e]; }
-    const unsigned long long out0 = pair_off[tile * 32u];
+    const unsigned long long out0 = pair_off[tile * 32u] - base;   // base: first record of this launch's item range
     uint32_t inc = cnt;
     #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {

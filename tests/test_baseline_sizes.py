@@ -83,7 +83,7 @@ def test_cfg2_rmat22_nine_measures_against_compiled_reference(nlp, oracle):
         o2, k2, du, dv, batch = _removed(nlp, p, off, keys, 0.1)
         del off, keys
         K = du.size // 2
-        assert K > 5_000_000, K
+        assert K > 4_000_000, K      # 6.4 M draws, fewer distinct edges: the sampler picks a vertex first
         o2n, k2n = g.to_numpy(o2, k2)
         S = len(o2n) - 1
         p.set_graph_pointers(o2.data_ptr(), k2.data_ptr(), S, device=True, keep=(o2, k2))

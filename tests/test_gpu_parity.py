@@ -42,7 +42,7 @@ def test_gpu_matches_reference_golden(pred, name):
             assert err is None, "%s %s" % (name, err)
 
 
-SOURCE_PATH, PAIR_PATH = 1, 2
+SOURCE_PATH, PAIR_PATH, PAIR_SORT_PATH = 1, 2, 3     # nlp_path: source-centric kernels, bucket path, global-sort pair path
 
 
 @pytest.mark.parametrize("name", ["rmat12", "rmat14p", "road60", "pp4k", "pp4k_multiset", "pp4k_symdup", "web20k"])
@@ -53,14 +53,14 @@ def test_gpu_matches_oracle(pred, oracle, nlp, name, D):
     pred.set_graph(off, keys)
     K = max(3, len(keys) // 20)
     try:
-        for path in (SOURCE_PATH, PAIR_PATH) if D else (SOURCE_PATH,):
+        for path in (SOURCE_PATH, PAIR_PATH, PAIR_SORT_PATH) if D else (SOURCE_PATH,):
             pred.set_path(path)
             for m in nlp.MEASURES:
                 for k in (K, nlp.UNBOUNDED) if (D != 0 or name != "rmat14p") else (K,):
                     err, r, st = parity.check_case(pred, oracle, off, keys, m, D, k, tag="%s path%d" % (name, path))
                     assert err is None, err
                     # asymmetric multiset rows are not admissible for the pair path: it must fall back
-                    want = SOURCE_PATH if (path == SOURCE_PATH or name == "pp4k_multiset") else PAIR_PATH
+                    want = SOURCE_PATH if (path == SOURCE_PATH or name == "pp4k_multiset") else path
                     assert r["path"] == want, (name, D, m, r["path"])
     finally:
         pred.set_path(0)
@@ -172,7 +172,7 @@ def test_properties_at_scale(pred, nlp):
 
 def test_paths_agree_at_scale(nlp, monkeypatch):
     """Independent code paths must give the same bits at a size no CPU oracle finishes quickly:
-    LHub through the source-centric kernels and through the pair path (R-MAT 20, D = 16), and IHub
+    LHub through the source-centric kernels, the bucket path and the global-sort pair path (R-MAT 20, D = 16), and IHub
     common neighbours / Jaccard with word counters and with half-word counters in k_range
     (R-MAT 18); the wedge counter equals sum of deg^2 (W(0))."""
     import torch
@@ -185,14 +185,15 @@ def test_paths_agree_at_scale(nlp, monkeypatch):
         p.set_graph_pointers(o.data_ptr(), k.data_ptr(), o.numel() - 1, device=True, keep=(o, k))
         for m in ("JC", "AA", "LHN"):
             res = []
-            for path in (SOURCE_PATH, PAIR_PATH):
+            for path in (SOURCE_PATH, PAIR_PATH, PAIR_SORT_PATH):
                 p.set_path(path)
                 r = p.predict(m, 16, max_edges=K)
                 assert r["path"] == path
                 res.append((r, p.fetch(r["count"])))
-            assert parity.compare(res[0][1], res[1][1], "paths %s" % m) is None
-            for c in ("wedges", "candidates", "kept", "eligible_first_hop"):
-                assert res[0][0][c] == res[1][0][c], (m, c)
+            for other in (1, 2):
+                assert parity.compare(res[0][1], res[other][1], "paths %s (source vs %d)" % (m, other + 1)) is None
+                for c in ("wedges", "candidates", "kept", "eligible_first_hop"):
+                    assert res[0][0][c] == res[other][0][c], (m, c, other)
     finally:
         p.close()
     o, k = g.rmat(18, 16, 42, device="cuda")
@@ -300,7 +301,7 @@ def test_reuse_across_measures(pred, oracle, nlp):
             for D in (2, 16):
                 err, r, st = parity.check_case(pred, oracle, off, keys, m, D, K, tag="reuse")
                 assert err is None, err
-                assert r["path"] == PAIR_PATH
+                assert r["path"] == PAIR_SORT_PATH      # the record store belongs to the global-sort pair path
                 if D in seen:     # no emission, no sort: only back-to-back event records (a few microseconds)
                     assert r["phase_ms"][1] < 0.02 and r["phase_ms"][2] < 0.02, r["phase_ms"]
                 elif r["pair_records"] >= 4096:      # D = 2 leaves this graph next to no wedge records
