@@ -405,7 +405,8 @@ def run_b200(args):
     path = results[0]["path"]
     if path == 2:
         names = ["bucket: plan lookup (built once per graph and D)", "bucket: k_bucket (gather + shared-memory sort + reduce + score)",
-                 "bucket: big sources (k_pair_emit + global radix sort + k_pair_reduce + k_big_place)", "-", "-", "-", "-",
+                 "bucket: big sources (k_pair_emit + global radix sort + k_pair_reduce + k_big_place)",
+                 "bucket: k_score (exclusion + scoring, one thread per slot)", "-", "-", "-",
                  "select+sort (radix top-K)"]
     elif path == 3:
         names = ["pair: eligible rows + item descriptors + scans", "pair: k_pair_emit (wedge records)",
@@ -421,8 +422,9 @@ def run_b200(args):
         # first-hop entry), one key per wedge record gathered, 4 B of aligned score per record, 8 B per kept pair
         P = sum(r["pair_records"] for r in results)
         elig = sum(r["eligible_first_hop"] for r in results)
-        cands = [(names[1], phase[1], 28 * elig + 4 * P + 4 * P + 8 * E),
+        cands = [(names[1], phase[1], 28 * elig + 4 * P + 4 * P + 8 * C),
                  (names[2], phase[2], 0.0),
+                 (names[3], phase[3], 4 * P + 8 * C + 4 * P),
                  (names[7], phase[7], 4 * 4 * P + 12 * E + 12 * Kout)]
     elif path == 3:
         # per-phase algorithmic bytes of the pair path

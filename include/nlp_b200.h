@@ -32,7 +32,8 @@ typedef enum {
   NLP_ERR_NO_GRAPH  = 3,   /* nlp_predict before nlp_set_graph                                  */
   NLP_ERR_CAPACITY  = 4,   /* candidate buffer cannot hold an unbounded (max_edges = -1) result  */
   NLP_ERR_NO_RESULT = 5,   /* nlp_fetch before nlp_predict                                      */
-  NLP_ERR_NO_TRUTH  = 6    /* nlp_evaluate before nlp_set_truth                                 */
+  NLP_ERR_NO_TRUTH  = 6,   /* nlp_evaluate before nlp_set_truth                                 */
+  NLP_ERR_COMM      = 7    /* NCCL error, or libnccl.so.2 not loadable                          */
 } nlp_status;
 
 /* Similarity measures, in the order main.cxx:212-220 runs them.
@@ -130,6 +131,30 @@ int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_
  * graph itself is replicated.  Default (0, 1).  Replaces the OpenMP `schedule(dynamic,2048)`
  * split of inc/predict.hxx:287.                                                                */
 int nlp_set_partition(nlp_handle* h, int rank, int world);
+
+/* ---- multi-GPU inside the library ------------------------------------------
+ * One process (and one handle) per GPU of a node, the CSR replicated on every GPU.  With a
+ * communicator, nlp_predict itself merges across the ranks -- this is what replaces the serial
+ * T-way heap merge of inc/predict.hxx:431-460:
+ *   1. every rank scores the sources it owns: the LHub bucket path deals contiguous, wedge-work
+ *      balanced source ranges (prefix sum of the wedge records per source, cut into equal
+ *      parts); the source-centric kernels interleave blocks of 32 ids;
+ *   2. the radix select's digit histograms are summed over the ranks with ncclAllReduce, so all
+ *      ranks agree on the GLOBAL cutoff and each keeps only its candidates above it (~K/N);
+ *   3. ONE ncclAllGather (preceded by an all-gather of the counts) moves the survivors;
+ *   4. every rank runs the same final sort; the result (identical on all ranks, and identical to
+ *      the single-GPU result: the canonical order does not depend on the partition) becomes the
+ *      handle's result.
+ * nlp_comm_unique_id: rank 0 creates the 128-byte id; the application hands it to the other
+ * ranks over whatever it already has (MPI_Bcast, a torch.distributed broadcast, a file).
+ * nlp_comm_init: collective over all ranks; also sets the partition (rank, world).  libnccl.so.2
+ * is loaded on first use (NLP_ERR_COMM when it is absent).                                       */
+#define NLP_COMM_ID_BYTES 128
+int nlp_comm_unique_id(void* id);
+int nlp_comm_init(nlp_handle* h, const void* id, int rank, int world);
+int nlp_comm_destroy(nlp_handle* h);
+/* Payload bytes this rank has received through the all-gathers so far. */
+uint64_t nlp_comm_bytes(const nlp_handle* h);
 
 /* Reuse across predictions on the same graph ("sweep fusion"; default off).
  * The nine measures share their common-neighbour counts, and main.cxx:212-220 asks for all of

@@ -13,10 +13,11 @@ from . import build as _build
 MEASURES = ["CN", "JC", "SI", "SC", "HP", "HD", "LHN", "AA", "RA"]   # main.cxx:212-220 order
 UNBOUNDED = (1 << 64) - 1
 STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH",
-          4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT", 6: "NLP_ERR_NO_TRUTH"}
+          4: "NLP_ERR_CAPACITY", 5: "NLP_ERR_NO_RESULT", 6: "NLP_ERR_NO_TRUTH", 7: "NLP_ERR_COMM"}
 
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
            "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_set_reuse", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
+           "nlp_comm_unique_id", "nlp_comm_init", "nlp_comm_destroy", "nlp_comm_bytes",
            "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
@@ -77,6 +78,11 @@ def load_library(build_if_missing=True):
     lib.nlp_set_graph_device.argtypes = [vp, vp, vp, u32]
     lib.nlp_set_partition.argtypes = [vp, C.c_int, C.c_int]
     lib.nlp_set_scratch_limit.argtypes = [vp, u64]
+    lib.nlp_comm_unique_id.argtypes = [vp]
+    lib.nlp_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.nlp_comm_destroy.argtypes = [vp]
+    lib.nlp_comm_bytes.argtypes = [vp]
+    lib.nlp_comm_bytes.restype = u64
     lib.nlp_set_path.argtypes = [vp, C.c_int]
     lib.nlp_set_reuse.argtypes = [vp, C.c_int]
     lib.nlp_predict.argtypes = [vp, C.POINTER(Options), C.POINTER(Result)]
@@ -133,6 +139,27 @@ class Predictor:
 
     def set_partition(self, rank, world):
         self._check(self.lib.nlp_set_partition(self.h, rank, world))
+
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (rank 0 creates it; hand it to the other ranks yourself)."""
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.nlp_comm_unique_id(buf)
+        if rc != 0:
+            raise NlpError(rc, lib.nlp_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, uid, rank, world):
+        """Collective: join the NCCL communicator of `world` ranks; nlp_predict then merges across
+        the ranks by itself and every rank holds the full result."""
+        self._check(self.lib.nlp_comm_init(self.h, C.c_char_p(bytes(uid)), rank, world))
+
+    def comm_destroy(self):
+        self._check(self.lib.nlp_comm_destroy(self.h))
+
+    def comm_bytes(self):
+        return int(self.lib.nlp_comm_bytes(self.h))
 
     def set_path(self, path):
         """0 = auto, 1 = source-centric kernels, 2 = LHub pair path (when admissible)."""

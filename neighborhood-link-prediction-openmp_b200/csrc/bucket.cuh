@@ -39,10 +39,11 @@
 
 namespace nlp {
 
-enum { BK_THREADS = 256, BK_WARPS = 8 };
+enum { BK_THREADS = 256, BK_WARPS = 8, BK_GATHER = 4 };
 constexpr uint32_t BK_CAP_COUNT = 8192;   // records per bucket, count measures (6 B per record x 2 buffers)
 constexpr uint32_t BK_CAP_FLT = 4096;     // float measures carry deg(w) (10 B per record x 2 buffers)
-constexpr uint32_t BK_BIG_NONE = 0xffffffffu;
+constexpr uint32_t BK_NONE = 0xffffffffu;   // aligned count array: no pair starts at this slot
+constexpr uint32_t BK_DONE = 0xfffffffeu;   // ... the slot's score is already final (big sources)
 
 // ---- plan ------------------------------------------------------------------------------------
 // One thread per row w.  items[w] = entries of an eligible row that have a later, larger entry
@@ -195,9 +196,10 @@ __global__ void __launch_bounds__(256) k_plan_scatter(const uint32_t* __restrict
 }
 
 // ---- per prediction ----------------------------------------------------------------------------
+
 __host__ __device__ constexpr uint32_t bucket_smem_bytes(bool flt, uint32_t cap) {
-  // key[2][cap] u32, tag[2][cap] u16, (pay[2][cap] u32), hist[8][256], mask[8][256], scan scratch
-  return cap * 4u * 2u + cap * 2u * 2u + (flt ? cap * 4u * 2u : 0u) + BK_WARPS * 256u * 4u * 2u + 64u;
+  // key[2][cap] u32, tag[2][cap] u16, (pay[2][cap] u32), mask[8][256] u32, hist[2][8][256] u16, scan scratch
+  return cap * 4u * 2u + cap * 2u * 2u + (flt ? cap * 4u * 2u : 0u) + BK_WARPS * 256u * 4u + 2u * BK_WARPS * 256u * 2u + 64u;
 }
 
 // first index i in [0, n] with a[i] >= x (a ascending, n entries)
@@ -210,19 +212,51 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* __
   return lo;
 }
 
+// Multi-GPU: rank r of `world` owns the buckets [b0, b1) and with them an ascending range of
+// source vertices [ulo, uhi); the big sources inside that range are its too, and its slots of the
+// aligned output are one contiguous range.  out = {kb0, kb1, slot_lo, slot_hi} (single thread).
+__global__ void k_plan_partition(BucketPlanDev pl, const uint32_t* __restrict__ b_u, const uint32_t* __restrict__ bg_item,
+                                 const unsigned long long* __restrict__ bg_roff, uint32_t nbig, unsigned long long P,
+                                 unsigned long long b0, unsigned long long b1, int first, int last,
+                                 unsigned long long* __restrict__ out) {
+  if (blockIdx.x || threadIdx.x) return;
+  const unsigned long long INF = 1ull << 32;
+  const uint32_t k0 = first ? 0u : lower_bound_u64(pl.sm_soff, pl.ns + 1u, b0 * pl.half);
+  const uint32_t k1 = last ? pl.ns : lower_bound_u64(pl.sm_soff, pl.ns + 1u, b1 * pl.half);
+  const unsigned long long ulo = first ? 0ull : (k0 < pl.ns ? (unsigned long long)pl.sm_u[k0] : INF);
+  const unsigned long long uhi = last ? INF : (k1 < pl.ns ? (unsigned long long)pl.sm_u[k1] : INF);
+  unsigned long long kb[2];
+  const unsigned long long bound[2] = {ulo, uhi};
+  for (int t = 0; t < 2; ++t) {                      // first big source with u >= bound
+    uint32_t lo = 0, hi = nbig;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if ((unsigned long long)b_u[bg_item[mid]] < bound[t]) lo = mid + 1; else hi = mid;
+    }
+    kb[t] = lo;
+  }
+  const unsigned long long s0 = k0 < pl.ns ? pl.sm_roff[k0] : P, s1 = k1 < pl.ns ? pl.sm_roff[k1] : P;
+  const unsigned long long g0 = kb[0] < nbig ? bg_roff[kb[0]] : P, g1 = kb[1] < nbig ? bg_roff[kb[1]] : P;
+  out[0] = kb[0]; out[1] = kb[1];
+  out[2] = s0 < g0 ? s0 : g0;
+  out[3] = s1 < g1 ? s1 : g1;
+}
+
 // One stable LSD pass over the n records in shared memory (warp w ranks records
-// [w * 32 * rounds, (w + 1) * 32 * rounds): warp-major order = record order).
+// [w * 32 * rounds, (w + 1) * 32 * rounds): warp-major order = record order).  Ranks inside a warp
+// come from warp-private digit masks (one atomicOr and one load per record, select.cuh); the masks
+// clean themselves, and the (warp, digit) counters of the NEXT pass (`s_next`) are zeroed by the
+// digit owners while they scan this pass's, so a pass costs three block barriers and no clearing loop.
 template <bool FLT, int MAXR>
 __device__ __forceinline__ void bucket_sort_pass(const uint32_t* __restrict__ kin, const uint16_t* __restrict__ tin, const uint32_t* __restrict__ pin,
                                                  uint32_t* __restrict__ kout, uint16_t* __restrict__ tout, uint32_t* __restrict__ pout,
                                                  uint32_t n, uint32_t rounds, bool by_tag, int shift,
-                                                 uint32_t (*s_hist)[256], uint32_t (*s_mask)[256], uint32_t* s_warp) {
+                                                 uint16_t (*s_hist)[256], uint16_t (*s_next)[256], uint32_t (*s_mask)[256], uint32_t* s_warp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  for (int i = tid; i < BK_WARPS * 256; i += BK_THREADS) { (&s_hist[0][0])[i] = 0; (&s_mask[0][0])[i] = 0; }
-  __syncthreads();
   uint32_t pre[MAXR];
   uint32_t* my_mask = s_mask[warp];
+  uint16_t* my_hist = s_hist[warp];
   #pragma unroll
   for (int r = 0; r < MAXR; ++r) {
     if ((uint32_t)r < rounds) {                      // block-uniform
@@ -233,10 +267,10 @@ __device__ __forceinline__ void bucket_sort_pass(const uint32_t* __restrict__ ki
       if (valid) atomicOr(my_mask + d, 1u << lane);
       __syncwarp();
       const unsigned m = valid ? *reinterpret_cast<volatile uint32_t*>(my_mask + d) : 0u;
-      const uint32_t before = valid ? s_hist[warp][d] : 0u;
+      const uint32_t before = valid ? *reinterpret_cast<volatile uint16_t*>(my_hist + d) : 0u;
       pre[r] = (d << 16) | (before + __popc(m & lt));
       __syncwarp();
-      if (valid && (__ffs(m) - 1) == lane) { s_hist[warp][d] = before + __popc(m); my_mask[d] = 0u; }
+      if (valid && (__ffs(m) - 1) == lane) { my_hist[d] = (uint16_t)(before + __popc(m)); my_mask[d] = 0u; }
       __syncwarp();
     }
   }
@@ -244,10 +278,10 @@ __device__ __forceinline__ void bucket_sort_pass(const uint32_t* __restrict__ ki
   {   // thread t owns digit t: exclusive scan over (digit, warp)
     uint32_t c[BK_WARPS], total = 0;
     #pragma unroll
-    for (int w = 0; w < BK_WARPS; ++w) { c[w] = s_hist[w][tid]; total += c[w]; }
+    for (int w = 0; w < BK_WARPS; ++w) { c[w] = s_hist[w][tid]; total += c[w]; s_next[w][tid] = 0; }
     uint32_t run = sort_block_exclusive(total, s_warp);
     #pragma unroll
-    for (int w = 0; w < BK_WARPS; ++w) { s_hist[w][tid] = run; run += c[w]; }
+    for (int w = 0; w < BK_WARPS; ++w) { s_hist[w][tid] = (uint16_t)run; run += c[w]; }
   }
   __syncthreads();
   #pragma unroll
@@ -255,7 +289,7 @@ __device__ __forceinline__ void bucket_sort_pass(const uint32_t* __restrict__ ki
     if ((uint32_t)r < rounds) {
       const uint32_t idx = (uint32_t)warp * (32u * rounds) + (uint32_t)r * 32u + lane;
       if (idx < n) {
-        const uint32_t pos = s_hist[warp][pre[r] >> 16] + (pre[r] & 0xffffu);
+        const uint32_t pos = (uint32_t)s_hist[warp][pre[r] >> 16] + (pre[r] & 0xffffu);
         kout[pos] = kin[idx]; tout[pos] = tin[idx];
         if (FLT) pout[pos] = pin[idx];
       }
@@ -268,7 +302,7 @@ __device__ __forceinline__ void bucket_sort_pass(const uint32_t* __restrict__ ki
 template <bool FLT>
 __global__ void __launch_bounds__(BK_THREADS, 2)
 k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
-         uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_s) {
+         uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_c) {
   constexpr uint32_t CAP = FLT ? BK_CAP_FLT : BK_CAP_COUNT;
   constexpr int MAXR = CAP / BK_THREADS;
   static_assert(BK_WARPS == SORT_WARPS && BK_THREADS == SORT_THREADS, "sort_block_exclusive is shared with select.cuh");
@@ -279,27 +313,27 @@ k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
   uint32_t* pay1 = pay0 + (FLT ? CAP : 0);
   uint16_t* tag0 = reinterpret_cast<uint16_t*>(pay1 + (FLT ? CAP : 0));
   uint16_t* tag1 = tag0 + CAP;
-  uint32_t (*s_hist)[256] = reinterpret_cast<uint32_t (*)[256]>(tag1 + CAP);
-  uint32_t (*s_mask)[256] = s_hist + BK_WARPS;
-  uint32_t* s_warp = &s_mask[0][0] + BK_WARPS * 256;               // [8] scan scratch, then [8..11] k0, k1
+  uint32_t (*s_mask)[256] = reinterpret_cast<uint32_t (*)[256]>(tag1 + CAP);
+  uint16_t (*s_hist0)[256] = reinterpret_cast<uint16_t (*)[256]>(s_mask + BK_WARPS);
+  uint16_t (*s_hist1)[256] = s_hist0 + BK_WARPS;
+  uint32_t* s_warp = reinterpret_cast<uint32_t*>(s_hist1 + BK_WARPS);   // [8] scan scratch, then [8..9] k0, k1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* __restrict__ keys = p.g.keys;
-  Tally tally;
 
   // ---- the bucket: small sources [k0, k1) that start inside the window --------------------------
   const unsigned long long wlo = (first_bucket + blockIdx.x) * (unsigned long long)pl.half;
+  for (int i = tid; i < BK_WARPS * 256; i += BK_THREADS) { (&s_mask[0][0])[i] = 0; (&s_hist0[0][0])[i] = 0; }
   if (tid == 0)  s_warp[8] = lower_bound_u64(pl.sm_soff, pl.ns + 1u, wlo);
   if (tid == 32) s_warp[9] = lower_bound_u64(pl.sm_soff, pl.ns + 1u, wlo + pl.half);
   __syncthreads();
   const uint32_t k0 = s_warp[8], k1 = min(s_warp[9], pl.ns);
-  if (k0 >= k1) { tally.flush(p.ctr); return; }                    // block-uniform
+  if (k0 >= k1) return;                                            // block-uniform
   const uint32_t i0 = __ldg(pl.sm_item + k0), i1 = __ldg(pl.sm_item + k1);
   const unsigned long long base = __ldg(pl.sm_soff + k0);
   const uint32_t n = (uint32_t)(__ldg(pl.sm_soff + k1) - base);    // <= CAP by construction
   const uint32_t ns = k1 - k0;
   if (n > CAP || ns > CAP / 2u) {                                  // cannot happen with a consistent plan
     if (tid == 0) atomicAdd(&p.ctr->overflow, 1ull);
-    tally.flush(p.ctr);
     return;
   }
 
@@ -320,26 +354,31 @@ k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
       if (lane >= d) inc += t;
     }
     const uint32_t tot = __shfl_sync(NLP_FULL, inc, 31);
-    for (uint32_t sb = 0; sb < tot; sb += 32u) {
-      const uint32_t idx = sb + lane;
-      int j = 0;                                      // smallest j with inc[j] > idx
+    for (uint32_t sb = 0; sb < tot; sb += 32u * BK_GATHER) {   // BK_GATHER independent key loads in flight per lane
+      uint32_t v[BK_GATHER], tgs[BK_GATHER], dws[BK_GATHER];
       #pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
-        const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
-        if (x <= idx) j += step;
+      for (int q = 0; q < BK_GATHER; ++q) {
+        const uint32_t idx = sb + q * 32u + lane;
+        int j = 0;                                    // smallest j with inc[j] > idx
+        #pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const uint32_t x = __shfl_sync(NLP_FULL, inc, j + step - 1);
+          if (x <= idx) j += step;
+        }
+        const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
+        const uint32_t cntj = __shfl_sync(NLP_FULL, cnt, j);
+        tgs[q] = __shfl_sync(NLP_FULL, tg, j);
+        const unsigned long long ptrj = __shfl_sync(NLP_FULL, ptr, j);
+        dws[q] = FLT ? __shfl_sync(NLP_FULL, dw, j) : 0u;
+        v[q] = idx < tot ? __ldg(keys + ptrj + (idx - (incj - cntj))) : 0u;
       }
-      const uint32_t incj = __shfl_sync(NLP_FULL, inc, j);
-      const uint32_t cntj = __shfl_sync(NLP_FULL, cnt, j);
-      const uint32_t tgj  = __shfl_sync(NLP_FULL, tg, j);
-      const unsigned long long ptrj = __shfl_sync(NLP_FULL, ptr, j);
-      uint32_t dwj = 0;
-      if (FLT) dwj = __shfl_sync(NLP_FULL, dw, j);
-      if (idx < tot) {
-        const uint32_t v = __ldg(keys + ptrj + (idx - (incj - cntj)));
+      #pragma unroll
+      for (int q = 0; q < BK_GATHER; ++q) {
+        const uint32_t idx = sb + q * 32u + lane;
         const uint32_t o = out0 + idx;
-        if (o < CAP) {
-          key0[o] = v; tag0[o] = (uint16_t)tgj;
-          if (FLT) pay0[o] = dwj;
+        if (idx < tot && o < CAP) {
+          key0[o] = v[q]; tag0[o] = (uint16_t)tgs[q];
+          if (FLT) pay0[o] = dws[q];
         }
       }
     }
@@ -350,17 +389,13 @@ k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
   const uint32_t rounds = (n + BK_THREADS - 1) / BK_THREADS;
   uint32_t *ka = key0, *kb = key1, *pa = pay0, *pb = pay1;
   uint16_t *ta = tag0, *tb = tag1;
-  for (int ps = 0; ps < key_passes; ++ps) {
-    bucket_sort_pass<FLT, MAXR>(ka, ta, pa, kb, tb, pb, n, rounds, false, ps * 8, s_hist, s_mask, s_warp);
+  uint16_t (*ha)[256] = s_hist0, (*hb)[256] = s_hist1;
+  const int tag_passes = ns > 256u ? 2 : (ns > 1u ? 1 : 0);
+  for (int ps = 0; ps < key_passes + tag_passes; ++ps) {
+    const bool by_tag = ps >= key_passes;
+    bucket_sort_pass<FLT, MAXR>(ka, ta, pa, kb, tb, pb, n, rounds, by_tag, (by_tag ? ps - key_passes : ps) * 8, ha, hb, s_mask, s_warp);
     uint32_t* t1 = ka; ka = kb; kb = t1; uint16_t* t2 = ta; ta = tb; tb = t2; t1 = pa; pa = pb; pb = t1;
-  }
-  if (ns > 1u) {
-    bucket_sort_pass<FLT, MAXR>(ka, ta, pa, kb, tb, pb, n, rounds, true, 0, s_hist, s_mask, s_warp);
-    uint32_t* t1 = ka; ka = kb; kb = t1; uint16_t* t2 = ta; ta = tb; tb = t2; t1 = pa; pa = pb; pb = t1;
-    if (ns > 256u) {
-      bucket_sort_pass<FLT, MAXR>(ka, ta, pa, kb, tb, pb, n, rounds, true, 8, s_hist, s_mask, s_warp);
-      t1 = ka; ka = kb; kb = t1; t2 = ta; ta = tb; tb = t2; t1 = pa; pa = pb; pb = t1;
-    }
+    uint16_t (*t3)[256] = ha; ha = hb; hb = t3;
   }
   // (ka, ta, pa) hold the sorted records; the other key / tag buffers are free now and take the
   // per-source caches: source vertex, and (aligned slot of the source's first record) - (its
@@ -375,43 +410,64 @@ k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
   }
   __syncthreads();
 
-  // ---- reduce runs, exclude existing edges, score, record-aligned output ------------------------
+  // ---- reduce runs: record-aligned (u, v, count) at the slot of a run's first record --------------
+  // Exclusion and scoring need a binary search in row u and degree gathers in global memory; with
+  // the few warps a shared-memory-heavy block leaves resident they would be latency bound here,
+  // so they run in k_score with one thread per slot.
   for (uint32_t r = 0; r < rounds; ++r) {
     const uint32_t idx = r * BK_THREADS + tid;
-    const bool valid = idx < n;
-    uint32_t v = 0, tg = 0, u = 0, cnt = 0;
-    uint64_t du = 0;
-    float acc = 0.0f;
-    bool head = false;
-    if (valid) {
-      v = ka[idx]; tg = ta[idx];
-      head = idx == 0 || ka[idx - 1] != v || ta[idx - 1] != tg;
-    }
+    if (idx >= n) break;
+    const uint32_t v = ka[idx], tg = ta[idx];
+    const bool head = idx == 0 || ka[idx - 1] != v || ta[idx - 1] != tg;
+    uint32_t c = BK_NONE;
     if (head) {
-      u = c_u[tg];
       if (FLT) {   // inc/predict.hxx:788,828: acc = float(double(acc) + term), ascending w
+        float acc = 0.0f;
         uint32_t j = idx;
         do {
           acc = __double2float_rn(__dadd_rn((double)acc, flt_term(p, pa[j])));
           ++j;
         } while (j < n && ka[j] == v && ta[j] == tg);
+        c = __float_as_uint(acc);
       } else {
         uint32_t j = idx + 1;
         while (j < n && ka[j] == v && ta[j] == tg) ++j;
-        cnt = j - idx;
+        c = j - idx;
       }
+    }
+    const unsigned long long slot = (((unsigned long long)c_dhi[tg] << 32) | c_dlo[tg]) + idx;
+    al_c[slot] = c;
+    if (head) { al_u[slot] = c_u[tg]; al_v[slot] = v; }
+  }
+}
+
+// One thread per slot of the aligned arrays: existing-edge exclusion by binary search in row u
+// (inc/predict.hxx:306-307: such pairs keep their candidate slot with value 0), fused scoring
+// (inc/predict.hxx:309-311).  al_c: count (or float accumulator bits) at the first record of a
+// run, BK_NONE where there is no pair, BK_DONE where the score is already in al_s (big sources).
+template <bool FLT>
+__global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restrict__ al_u, const uint32_t* __restrict__ al_v,
+                                               const uint32_t* __restrict__ al_c, uint32_t* __restrict__ al_s,
+                                               uint64_t lo, uint64_t hi) {
+  Tally tally;
+  const uint64_t n = hi - lo, n32 = (n + 31u) & ~31ull;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n32; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = lo + t;
+    const uint32_t c = t < n ? al_c[i] : BK_DONE;
+    const bool head = c != BK_NONE && c != BK_DONE;
+    uint32_t u = 0, v = 0, cnt = 0;
+    uint64_t du = 0;
+    float acc = 0.0f;
+    if (head) {
+      u = al_u[i]; v = al_v[i];
+      if (FLT) acc = __uint_as_float(c); else cnt = c;
       const uint64_t ub = __ldg(p.g.off + u);
       du = __ldg(p.g.deg + u);
-      // existing edges keep their candidate slot with value 0 (inc/predict.hxx:306-307)
-      if (row_contains(keys, ub, (uint32_t)du, v)) { cnt = 0; acc = 0.0f; }
+      if (row_contains(p.g.keys, ub, (uint32_t)du, v)) { cnt = 0; acc = 0.0f; }
     }
     float score;
     const bool keep = score_pair(p, head, u, du, v, cnt, acc, tally, &score);
-    if (valid) {
-      const unsigned long long slot = (((unsigned long long)c_dhi[tg] << 32) | c_dlo[tg]) + idx;
-      al_s[slot] = keep ? __float_as_uint(score) : NLP_NO_SCORE;
-      if (keep) { al_u[slot] = u; al_v[slot] = v; }
-    }
+    if (c != BK_DONE) al_s[i] = keep ? __float_as_uint(score) : NLP_NO_SCORE;
   }
   tally.flush(p.ctr);
 }
@@ -423,7 +479,8 @@ __global__ void __launch_bounds__(256) k_big_place(const uint32_t* __restrict__ 
                                                    const uint32_t* __restrict__ ps, uint64_t n, uint64_t first,
                                                    const unsigned long long* __restrict__ bg_first,
                                                    const unsigned long long* __restrict__ bg_roff, uint32_t kb0, uint32_t kb1,
-                                                   uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_s) {
+                                                   uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_s,
+                                                   uint32_t* __restrict__ al_c) {
   for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
     const unsigned long long pos = first + j;
     uint32_t lo = kb0, hi = kb1;                     // last big source with bg_first <= pos
@@ -434,6 +491,7 @@ __global__ void __launch_bounds__(256) k_big_place(const uint32_t* __restrict__ 
     const unsigned long long slot = __ldg(bg_roff + lo) + (pos - __ldg(bg_first + lo));
     const uint32_t s = ps[j];
     al_s[slot] = s;
+    al_c[slot] = BK_DONE;
     if (s != NLP_NO_SCORE) { al_u[slot] = pu[j]; al_v[slot] = pv[j]; }
   }
 }

@@ -13,6 +13,9 @@
 #include "evaluate.cuh"
 #include "batch.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>      // types only: libnccl.so.2 is dlopen'ed by nlp_comm_init
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -109,12 +112,13 @@ struct nlp_handle {
     uint64_t first_hop = 0, elig = 0, wedges = 0, stamp = 0;
     std::vector<unsigned long long> h_bg_first;   // host copies: the big sources are few
     std::vector<uint32_t> h_bg_item;
+    uint64_t part_key = 0, part_kb0 = 0, part_kb1 = 0, part_slo = 0, part_shi = 0;   // this rank's share (cached per rank/world)
     bool usable = false;                     // false: too large for the scratch budget (source path instead)
   };
   std::map<uint64_t, BucketPlan> plans;
   uint64_t plan_bytes = 0;
   DevBuf plan_tmp;                           // scratch of a plan build (kept: no allocation churn)
-  DevBuf al_u, al_v, al_s;                   // record-aligned output of the bucket path
+  DevBuf al_u, al_v, al_s, al_c;             // record-aligned output of the bucket path (pair, score bits, count)
   const uint32_t* pair_ps = nullptr;         // aligned score bits when the records live outside the candidate buffers
   // asynchronous fetch: result -> staging (device copy on the compute stream) -> caller memory
   // (copy stream), double buffered, so the next prediction overlaps the transfer
@@ -136,6 +140,11 @@ struct nlp_handle {
   int res_buf = 0;
   uint64_t res_count = 0;
   bool has_result = false;
+  // multi-GPU: NCCL communicator (nlp_comm_init); with it nlp_predict merges across the ranks itself
+  void* comm = nullptr;
+  bool part_ordered = false;                 // this prediction's partition gave every rank an ascending source range
+  DevBuf gcnt, gsend, grecv;
+  uint64_t gathered_bytes = 0;               // payload bytes received by all-gathers so far
   // config
   int rank = 0, world = 1;
   uint64_t scratch_limit = 0;
@@ -752,9 +761,10 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   const uint64_t P = plan.P;
   uint64_t budget = 0;
   NLP_TRY(scratch_budget(h, &budget));
-  if ((P + 2 * (uint64_t)SORT_TILE) * 36 + h->plan_bytes > budget) return NLP_OK;
+  if ((P + 2 * (uint64_t)SORT_TILE) * 40 + h->plan_bytes > budget) return NLP_OK;
   const uint64_t padded = (P + OC_TILE) / OC_TILE * OC_TILE + 1024;
-  if (!try_ensure(h, h->al_u, padded * 4) || !try_ensure(h, h->al_v, padded * 4) || !try_ensure(h, h->al_s, padded * 4)) return NLP_OK;
+  if (!try_ensure(h, h->al_u, padded * 4) || !try_ensure(h, h->al_v, padded * 4) || !try_ensure(h, h->al_s, padded * 4) ||
+      !try_ensure(h, h->al_c, padded * 4)) return NLP_OK;
   NLP_TRY(ensure_candidates(h, P));
   Counters* hc = h->h_ctr;
   NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
@@ -766,14 +776,32 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   p.ctr = (Counters*)h->ctr.p; p.thr = (const Threshold*)h->thr.p;
   p.cap = h->cand_cap;
   h->phases_valid = false;
-  NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
-  NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
   uint32_t* al_u = (uint32_t*)h->al_u.p; uint32_t* al_v = (uint32_t*)h->al_v.p; uint32_t* al_s = (uint32_t*)h->al_s.p;
+  uint32_t* al_c = (uint32_t*)h->al_c.p;
   const uint64_t rank = (uint64_t)h->rank, world = (uint64_t)h->world;
-  if (P && world > 1) NLP_CUDA(h, cudaMemsetAsync(al_s, 0xff, P * 4, h->stream));   // slots of the other ranks: NLP_NO_SCORE
-  // small sources: one block per bucket, this rank's contiguous share of the buckets
+  // this rank's share: a contiguous range of buckets (equal parts of the prefix sum of the wedge
+  // records per source) = an ascending range of sources, the big sources inside it, and one
+  // contiguous range of slots
   const uint64_t nb = (plan.Ps + half - 1) / half;
   const uint64_t b0 = nb * rank / world, b1 = nb * (rank + 1) / world;
+  uint64_t kb0 = 0, kb1 = plan.nbig, slo = 0, shi = P;
+  if (world > 1) {
+    const uint64_t pkey = (rank << 32) | world;
+    if (plan.part_key != pkey) {
+      NLP_TRY(ensure(h, h->gcnt, (size_t)(world + 8) * 8));
+      unsigned long long out[4] = {0, 0, 0, 0};
+      k_plan_partition<<<1, 1, 0, h->stream>>>(plan.dev, plan.big_items.u, plan.bg_item, plan.bg_roff, (uint32_t)plan.nbig, P,
+                                               b0, b1, rank == 0, rank + 1 == world, (unsigned long long*)h->gcnt.p);
+      NLP_LAUNCHED(h);
+      NLP_CUDA(h, cudaMemcpyAsync(out, h->gcnt.p, 32, cudaMemcpyDeviceToHost, h->stream));
+      NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+      plan.part_key = pkey; plan.part_kb0 = out[0]; plan.part_kb1 = out[1]; plan.part_slo = out[2]; plan.part_shi = out[3];
+    }
+    kb0 = plan.part_kb0; kb1 = plan.part_kb1; slo = plan.part_slo; shi = plan.part_shi;
+  }
+  NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
+  NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
+  // small sources: one block per bucket
   if (b1 > b0) {
     const uint32_t top = h->S ? h->S - 1 : 0;
     int key_passes = 0;
@@ -783,13 +811,12 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
     NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (uint64_t s0 = b0; s0 < b1; s0 += 0x7fffffffull) {          // grid.x limit
       const unsigned grid = (unsigned)std::min<uint64_t>(b1 - s0, 0x7fffffffull);
-      kern<<<grid, BK_THREADS, smem, h->stream>>>(p, plan.dev, s0, key_passes, al_u, al_v, al_s);
+      kern<<<grid, BK_THREADS, smem, h->stream>>>(p, plan.dev, s0, key_passes, al_u, al_v, al_c);
       NLP_LAUNCHED(h);
     }
   }
   NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
   // big sources: global sort of their records (pairs.cuh), then into their slots
-  const uint64_t kb0 = plan.nbig * rank / world, kb1 = plan.nbig * (rank + 1) / world;
   if (kb1 > kb0) {
     const uint64_t ib0 = plan.h_bg_item[kb0], ib1 = plan.h_bg_item[kb1];
     const uint64_t r0 = plan.h_bg_first[kb0], r1 = plan.h_bg_first[kb1];
@@ -806,10 +833,16 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
     NLP_LAUNCHED(h);
     k_big_place<<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
         (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb ^ 1].p, Pb, r0,
-        plan.bg_first, plan.bg_roff, (uint32_t)kb0, (uint32_t)kb1, al_u, al_v, al_s);
+        plan.bg_first, plan.bg_roff, (uint32_t)kb0, (uint32_t)kb1, al_u, al_v, al_s, al_c);
     NLP_LAUNCHED(h);
   }
-  for (int i = 2; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
+  NLP_CUDA(h, cudaEventRecord(h->ev_phase[2], h->stream));
+  // exclusion + scoring of the small sources' pairs, one thread per slot
+  if (shi > slo) {
+    k_score<FLT><<<grid_for(shi - slo, 256, h->num_sms * 16), 256, 0, h->stream>>>(p, al_u, al_v, al_c, al_s, slo, shi);
+    NLP_LAUNCHED(h);
+  }
+  for (int i = 3; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
   h->phases_valid = true;
   NLP_TRY(read_counters(h));
   if (hc->overflow) return fail(h, NLP_ERR_CAPACITY, "internal: bucket overflow (inconsistent plan)");
@@ -817,8 +850,9 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   res->candidates = hc->candidates; res->kept = hc->kept; res->emitted = hc->kept;
   res->passes = 1; res->path = NLP_PATH_PAIR; res->pair_records = P;
   res->bin_sources[0] = plan.ns; res->bin_sources[1] = plan.nbig;
-  h->pair_pending = true; h->pair_from_cache = true; h->pair_n = P; h->pair_kept = hc->kept;
-  h->pair_pu = al_u; h->pair_pv = al_v; h->pair_ps = al_s; h->pair_score_buf = 0;
+  h->pair_pending = true; h->pair_from_cache = true; h->pair_n = shi - slo; h->pair_kept = hc->kept;
+  h->pair_pu = al_u + slo; h->pair_pv = al_v + slo; h->pair_ps = al_s + slo; h->pair_score_buf = 0;
+  h->part_ordered = true;
   *out_buf = 0; *out_fill = hc->kept; *used = true;
   return NLP_OK;
 }
@@ -866,6 +900,7 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
       res->candidates = hc->candidates; res->kept = hc->kept; res->emitted = hc->kept;
       res->passes = 1; res->path = NLP_PATH_PAIR_SORT; res->pair_records = P;
       h->pair_pending = true; h->pair_from_cache = true; h->pair_n = P; h->pair_kept = hc->kept; h->pair_ps = nullptr;
+      h->part_ordered = false;
       h->pair_pu = (const uint32_t*)c.u.p; h->pair_pv = (const uint32_t*)c.v.p; h->pair_score_buf = 0;
       *out_buf = 1; *out_fill = hc->kept; *used = true;
       return NLP_OK;
@@ -937,6 +972,7 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   res->path = NLP_PATH_PAIR_SORT;
   res->pair_records = P;
   h->pair_pending = true; h->pair_from_cache = false; h->pair_n = P; h->pair_kept = hc->kept; h->pair_ps = nullptr;
+  h->part_ordered = false;
   h->pair_pu = (const uint32_t*)h->cu[sb].p; h->pair_pv = (const uint32_t*)h->cv[sb].p; h->pair_score_buf = cur;
   if (h->reuse && P) {
     // keep a copy of the sorted records (after the reduce kernel is queued: same stream, so the
@@ -1005,6 +1041,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   }
   res->path = NLP_PATH_SOURCE;
   h->pair_pending = false;
+  h->part_ordered = false;
   NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
   NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
   const DevGraph g = dev_graph(h);
@@ -1206,6 +1243,207 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   return NLP_OK;
 }
 
+// ---- multi-GPU: NCCL communicator behind the C ABI -----------------------
+// libnccl is dlopen'ed on first use, so the library loads (and every single-GPU entry works)
+// on a box without NCCL; <nccl.h> is only needed for the types.
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string err;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.lib ? &api : nullptr;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) { api.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return nullptr; }
+  auto sym = [&](const char* n) { void* p = dlsym(api.lib, n); if (!p) api.err = std::string("dlsym ") + n; return p; };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.AllGather || !api.GetErrorString) {
+    dlclose(api.lib); api.lib = nullptr; return nullptr;
+  }
+  return &api;
+}
+
+#define NLP_NCCL(h, expr)                                                                      \
+  do {                                                                                         \
+    ncclResult_t r__ = (expr);                                                                 \
+    if (r__ != ncclSuccess) {                                                                  \
+      (h)->err = std::string(#expr) + " (nlp_b200.cu:" + std::to_string(__LINE__) + "): " + nccl_api()->GetErrorString(r__); \
+      return NLP_ERR_COMM;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+inline bool distributed(const nlp_handle* h) { return h->comm != nullptr; }   // also with one rank: same code path
+
+// MSD radix select with the digit histograms summed over the ranks: every rank ends with the
+// same prefix / above / bucket, i.e. the GLOBAL cutoff ("all-reduce of a
+// score histogram to agree the cutoff").  Levels are queued four at a time; `done` is read back.
+int select_narrow(nlp_handle* h, const uint32_t* cu, const uint32_t* cv, const uint32_t* cs, uint64_t n,
+                  uint64_t K, uint32_t max_bits, bool dist) {
+  NLP_CUDA(h, cudaMemsetAsync(h->sel.p, 0, sizeof(SelectState), h->stream));
+  const uint64_t slack = std::max<uint64_t>(K / 8, 65536);
+  NcclApi* api = dist ? nccl_api() : nullptr;
+  bool done = false;
+  while (!done) {
+    for (int lvl = 0; lvl < 4; ++lvl) {
+      k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(cu, cv, cs, n, (SelectState*)h->sel.p);
+      NLP_LAUNCHED(h);
+      if (api) {
+        unsigned long long* hist = (unsigned long long*)((char*)h->sel.p + offsetof(SelectState, hist));
+        NLP_NCCL(h, api->AllReduce(hist, hist, 256, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->stream));
+      }
+      k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K, (unsigned long long)slack, max_bits);
+      NLP_LAUNCHED(h);
+    }
+    NLP_CUDA(h, cudaMemcpyAsync(h->h_sel, h->sel.p, offsetof(SelectState, hist), cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    done = h->h_sel->done != 0;
+  }
+  return NLP_OK;
+}
+
+// Sum of one count per rank (one tiny all-gather + read-back).
+int global_count(nlp_handle* h, uint64_t mine, uint64_t* sum) {
+  NcclApi* api = nccl_api();
+  const int W = h->world;
+  NLP_TRY(ensure(h, h->gcnt, (size_t)(W + 1) * 8));
+  unsigned long long* d_cnt = (unsigned long long*)h->gcnt.p;
+  unsigned long long m = mine;
+  NLP_CUDA(h, cudaMemcpyAsync(d_cnt + W, &m, 8, cudaMemcpyHostToDevice, h->stream));
+  NLP_NCCL(h, api->AllGather(d_cnt + W, d_cnt, 1, ncclUint64, (ncclComm_t)h->comm, h->stream));
+  std::vector<unsigned long long> cnt(W);
+  NLP_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 8, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  *sum = 0;
+  for (int r = 0; r < W; ++r) *sum += cnt[r];
+  return NLP_OK;
+}
+
+// All-gather the m local survivors in candidate buffer `buf` (counts first, then ONE padded
+// payload all-gather); afterwards buffer 0 holds the candidates of all ranks in rank order.
+int gather_candidates(nlp_handle* h, int buf, uint64_t m, uint64_t* total) {
+  NcclApi* api = nccl_api();
+  const int W = h->world;
+  NLP_TRY(ensure(h, h->gcnt, (size_t)(W + 1) * 8));
+  unsigned long long* d_cnt = (unsigned long long*)h->gcnt.p;
+  unsigned long long mine = m;
+  NLP_CUDA(h, cudaMemcpyAsync(d_cnt + W, &mine, 8, cudaMemcpyHostToDevice, h->stream));
+  NLP_NCCL(h, api->AllGather(d_cnt + W, d_cnt, 1, ncclUint64, (ncclComm_t)h->comm, h->stream));
+  std::vector<unsigned long long> cnt(W);
+  NLP_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 8, cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  uint64_t width = 1, sum = 0;
+  for (int r = 0; r < W; ++r) { width = std::max<uint64_t>(width, cnt[r]); sum += cnt[r]; }
+  if (sum >= 0xfffffff0ull) return fail(h, NLP_ERR_CAPACITY, "multi-GPU merge: too many candidates");
+  NLP_TRY(ensure(h, h->gsend, (size_t)width * 12));
+  NLP_TRY(ensure(h, h->grecv, (size_t)width * 12 * W));
+  uint32_t* send = (uint32_t*)h->gsend.p;
+  if (m) {
+    NLP_CUDA(h, cudaMemcpyAsync(send, h->cu[buf].p, m * 4, cudaMemcpyDeviceToDevice, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(send + width, h->cv[buf].p, m * 4, cudaMemcpyDeviceToDevice, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(send + 2 * width, h->cs[buf].p, m * 4, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  NLP_NCCL(h, api->AllGather(send, h->grecv.p, (size_t)width * 3, ncclUint32, (ncclComm_t)h->comm, h->stream));
+  NLP_TRY(ensure_candidates(h, sum));           // may reallocate the candidate buffers: the local survivors are in `send`
+  uint64_t at = 0;
+  for (int r = 0; r < W; ++r) {
+    const uint32_t* src = (const uint32_t*)h->grecv.p + (size_t)r * width * 3;
+    if (cnt[r]) {
+      NLP_CUDA(h, cudaMemcpyAsync((uint32_t*)h->cu[0].p + at, src, cnt[r] * 4, cudaMemcpyDeviceToDevice, h->stream));
+      NLP_CUDA(h, cudaMemcpyAsync((uint32_t*)h->cv[0].p + at, src + width, cnt[r] * 4, cudaMemcpyDeviceToDevice, h->stream));
+      NLP_CUDA(h, cudaMemcpyAsync((uint32_t*)h->cs[0].p + at, src + 2 * width, cnt[r] * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    at += cnt[r];
+  }
+  *total = sum;
+  h->gathered_bytes += (uint64_t)width * 12 * W;
+  return NLP_OK;
+}
+
+// The merge of a multi-GPU prediction (replaces the serial T-way heap merge of
+// inc/predict.hxx:431-460): global cutoff by all-reduced select histograms, local compaction of the
+// survivors, one all-gather, final on-device sort.  Every rank ends with the same result.
+int dist_top_k(nlp_handle* h, int buf, uint64_t fill, uint64_t K, int* out_buf, uint64_t* out_n) {
+  uint64_t m = 0, total = 0;
+  int lb = 0;
+  if (h->pair_pending) {
+    // records (and the kept pairs among them) lie in ascending (u, v) order in the aligned arrays
+    const uint32_t* pu = h->pair_pu; const uint32_t* pv = h->pair_pv;
+    const uint64_t n = h->pair_n;
+    const bool external = h->pair_ps != nullptr;
+    const int sbuf = h->pair_score_buf, ob = sbuf ^ 1;
+    const uint32_t* sbits = external ? h->pair_ps : (const uint32_t*)h->cs[sbuf].p;
+    uint64_t kept_all = 0;
+    NLP_TRY(global_count(h, h->pair_kept, &kept_all));
+    const int mode = K < kept_all ? 1 : 0;          // fewer kept pairs than asked for: everything survives
+    if (mode) NLP_TRY(select_narrow(h, pu, pv, sbits, n, K, 32u, true));
+    const uint32_t ntiles = (uint32_t)((n + OC_TILE - 1) / OC_TILE);
+    if (n) {
+      NLP_TRY(ensure(h, h->oc_counts, (size_t)ntiles * 4));
+      NLP_TRY(ensure(h, h->oc_off, (size_t)ntiles * 8));
+      k_ordered_count<<<ntiles, OC_THREADS, 0, h->stream>>>(sbits, n, (const SelectState*)h->sel.p, mode, (uint32_t*)h->oc_counts.p);
+      NLP_LAUNCHED(h);
+      NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &m));
+      int res = ob;
+      uint32_t *ou = (uint32_t*)h->cu[ob].p, *ov = (uint32_t*)h->cv[ob].p, *os = (uint32_t*)h->cs[ob].p;
+      if (external) { res = 0; ou = (uint32_t*)h->cu[0].p; ov = (uint32_t*)h->cv[0].p; os = (uint32_t*)h->cs[0].p; }
+      else if (!h->pair_from_cache) { ou = (uint32_t*)h->cu[sbuf].p; ov = (uint32_t*)h->cv[sbuf].p; res = sbuf; }
+      k_ordered_write<<<ntiles, OC_THREADS, 0, h->stream>>>(pu, pv, sbits, n, (const SelectState*)h->sel.p, mode,
+                                                            (const unsigned long long*)h->oc_off.p, ou, ov, os);
+      NLP_LAUNCHED(h);
+      if (!external && !h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
+      lb = res;
+    }
+    NLP_TRY(gather_candidates(h, lb, m, &total));
+    if (h->part_ordered) {
+      // ranks own ascending source ranges: the gathered list is in (u, v) order inside every score
+      // class, so a stable sort by score alone is the canonical order
+      NLP_TRY(radix_sort(h, 0, total, out_buf, 8));
+      *out_n = std::min(total, K);
+      return NLP_OK;
+    }
+    return top_k(h, 0, total, K, out_buf, out_n);
+  }
+  // source-centric kernels: `fill` unordered candidates in buffer `buf`
+  uint64_t fill_all = 0;
+  NLP_TRY(global_count(h, fill, &fill_all));
+  lb = buf;
+  m = fill;
+  if (K < fill_all) NLP_TRY(select_narrow(h, (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, fill, K, 96u, true));
+  if (K < fill_all && fill) {
+    const int o = buf ^ 1;
+    NLP_CUDA(h, cudaMemsetAsync(h->cursor2.p, 0, 8, h->stream));
+    k_select_compact<<<grid_for(fill, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(
+        (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, fill,
+        (const SelectState*)h->sel.p, (uint32_t*)h->cu[o].p, (uint32_t*)h->cv[o].p, (uint32_t*)h->cs[o].p,
+        (unsigned long long*)h->cursor2.p);
+    NLP_LAUNCHED(h);
+    unsigned long long got = 0;
+    NLP_CUDA(h, cudaMemcpyAsync(&got, h->cursor2.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    lb = o; m = got;
+  }
+  NLP_TRY(gather_candidates(h, lb, m, &total));
+  return top_k(h, 0, total, K, out_buf, out_n);
+}
+
 }  // namespace
 
 
@@ -1272,9 +1510,11 @@ int nlp_destroy(nlp_handle* h) {
   if (!h) return NLP_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->comm) { nccl_api()->CommDestroy((ncclComm_t)h->comm); h->comm = nullptr; }
+  release(h->gcnt); release(h->gsend); release(h->grecv);
   clear_pair_cache(h);
   clear_plans(h);
-  release(h->plan_tmp); release(h->al_u); release(h->al_v); release(h->al_s);
+  release(h->plan_tmp); release(h->al_u); release(h->al_v); release(h->al_s); release(h->al_c);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (int i = 0; i < 2; ++i) {
     release(h->stg_u[i]); release(h->stg_v[i]); release(h->stg_s[i]);
@@ -1338,9 +1578,52 @@ int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_
 int nlp_set_partition(nlp_handle* h, int rank, int world) {
   if (!h) return NLP_ERR_ARG;
   if (world < 1 || rank < 0 || rank >= world) return fail(h, NLP_ERR_ARG, "nlp_set_partition: need 0 <= rank < world");
+  if (h->comm && (rank != h->rank || world != h->world)) return fail(h, NLP_ERR_ARG, "nlp_set_partition: a communicator is active (nlp_comm_destroy first)");
   h->rank = rank; h->world = world;
   return NLP_OK;
 }
+
+int nlp_comm_unique_id(void* id) {
+  if (!id) return NLP_ERR_ARG;
+  NcclApi* api = nccl_api();
+  if (!api) { g_create_error = "nlp_comm_unique_id: NCCL not available"; return NLP_ERR_COMM; }
+  ncclUniqueId uid;
+  if (api->GetUniqueId(&uid) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return NLP_ERR_COMM; }
+  static_assert(sizeof(uid) == NLP_COMM_ID_BYTES, "ncclUniqueId size");
+  memcpy(id, &uid, sizeof uid);
+  return NLP_OK;
+}
+
+int nlp_comm_init(nlp_handle* h, const void* id, int rank, int world) {
+  if (!h) return NLP_ERR_ARG;
+  if (!id) return fail(h, NLP_ERR_ARG, "nlp_comm_init: null id");
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, NLP_ERR_ARG, "nlp_comm_init: need 0 <= rank < world");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(h, NLP_ERR_COMM, "nlp_comm_init: libnccl.so.2 could not be loaded");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  if (h->comm) { api->CommDestroy((ncclComm_t)h->comm); h->comm = nullptr; }
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  ncclComm_t c = nullptr;
+  NLP_NCCL(h, api->CommInitRank(&c, world, uid, rank));
+  h->comm = c;
+  h->rank = rank; h->world = world;
+  return NLP_OK;
+}
+
+int nlp_comm_destroy(nlp_handle* h) {
+  if (!h) return NLP_ERR_ARG;
+  if (h->comm) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    nccl_api()->CommDestroy((ncclComm_t)h->comm);
+    h->comm = nullptr;
+  }
+  h->rank = 0; h->world = 1;
+  return NLP_OK;
+}
+
+uint64_t nlp_comm_bytes(const nlp_handle* h) { return h ? h->gathered_bytes : 0; }
 
 int nlp_set_reuse(nlp_handle* h, int on) {
   if (!h) return NLP_ERR_ARG;
@@ -1396,8 +1679,9 @@ int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res) {
   }
   int ob = buf;
   uint64_t on = 0;
-  if (h->pair_pending) NLP_TRY(top_k_ordered(h, opt->max_edges, &ob, &on));
-  else                 NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
+  if (distributed(h))       NLP_TRY(dist_top_k(h, buf, fill, opt->max_edges, &ob, &on));
+  else if (h->pair_pending) NLP_TRY(top_k_ordered(h, opt->max_edges, &ob, &on));
+  else                      NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
   NLP_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
   NLP_CUDA(h, cudaEventSynchronize(h->ev_done));
   float sel = 0.f;
