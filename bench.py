@@ -63,6 +63,7 @@ def make_config(info, degree, measures, S, M):
                 l2="inputs larger than L2 (CSR %.0f MB)" % ((8 * (S + 1) + 4 * M) / 1e6))
 
 
+BASE_GRAPH = {}           # the last workload's graph before the removal (the e2e leg applies the batch on the device)
 REMOVAL_SEED = 12345      # default_random_engine(12345) for every parity run
 
 
@@ -101,12 +102,14 @@ def build_workload(name, device, batch=0, pred=None):
         u, v, _ = O.oracle_edge_deletions(offn, keysn, seed, batch_size)
         du = torch.from_numpy(u.astype(np.int32)).to(device); dv = torch.from_numpy(v.astype(np.int32)).to(device)
         del offn, keysn
+    base = (off, keys)
     off, keys = N.graphs.apply_deletions(off, keys, du, dv)
     K = int(du.numel()) // 2
     if device != "cpu":
         torch.cuda.synchronize()
     info = {"workload": name, "description": w["desc"], "span": S, "entries": int(keys.numel()),
             "predict_count_K": K, "removal": "reference sampler (inc/batch.hxx:99-112), default_random_engine(%d)" % seed}
+    BASE_GRAPH["graph"] = base
     return off, keys, K, info, (du, dv), round(time.time() - t0, 2)
 
 
@@ -264,34 +267,47 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = "cuda:%d" % local
     all_measures = [m for m in args.measures.split(",") if m] if args.measures else MEASURES
-    # N > 1, three ways to use the GPUs (CSR replicated in all of them):
-    #  batches  (default)  every rank runs a whole step on ITS OWN batch -- the reference draws
-    #           REPEAT_BATCH independent random removals per fraction (main.cxx:163) and predicts on
-    #           each; independent units, no data-path collective, per-GPU work fixed: weak scaling
+    # N > 1 (CSR replicated on every GPU in all modes):
+    #  comm     (default) the north star's design: the sources of EVERY prediction are partitioned by
+    #           wedge work, the library merges the ranks' candidates itself over its own NCCL
+    #           communicator (nlp_comm_init: all-reduced select histograms for the global cutoff, one
+    #           all-gather, final sort) and every rank ends with the full result: strong scaling
+    #  batches  every rank runs a whole step on ITS OWN batch -- the reference draws REPEAT_BATCH
+    #           independent random removals per fraction (main.cxx:163); independent units, no
+    #           collective: weak scaling.  Also measured (shortly) in comm mode as the "replicas" key.
     #  measures the nine predictions of ONE batch dealt to the ranks (strong scaling, no collective)
-    #  sources  the source vertices of each prediction partitioned (nlp_set_partition), local top-K
-    #           lists merged with one all-gather + on-device select (strong scaling; what a single
-    #           heavy prediction, e.g. IHub, needs)
+    #  sources  round-1 plumbing: nlp_set_partition + torch.distributed all-gather + nlp_merge
     shard = args.shard
     if shard == "auto":
-        shard = "batches" if len(all_measures) > 1 else "sources"
+        shard = "comm"
     if world == 1:
         shard = "none"
     pred = N.Predictor(local)
-    off, keys, K, info, _, build_s = build_workload(args.workload, dev, batch=rank if shard == "batches" else 0, pred=pred)
+    wl = build_workload(args.workload, dev, batch=rank if shard == "batches" else 0, pred=pred)
+    off, keys, K, info, (du, dv), build_s = wl
     S = int(off.numel() - 1); M = int(keys.numel())
-    # host copies in pinned memory (e2e leg) -- int64/int32 tensors carry the uint64/uint32 bits
-    do_e2e = not args.no_e2e
-    if do_e2e:
-        h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
-    if shard == "sources":
+    if shard == "comm":
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(N.Predictor.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, 0)
+        torch.cuda.synchronize()
+        pred.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    elif shard == "sources":
         pred.set_partition(rank, world)
     stream = torch.cuda.ExternalStream(pred.lib.nlp_stream(pred.h), device=dev)
     measures = all_measures[rank::world] if shard == "measures" else all_measures
     D = args.degree
-    if do_e2e:   # two sets of pinned result buffers: transfers are double buffered (nlp_fetch_async)
+    do_e2e = not args.no_e2e
+    base = BASE_GRAPH.get("graph")                 # (off0, keys0) before the removal, still on the device
+    if do_e2e:
+        # host side of a step: the batch update (main.cxx's sorted directed deletions0) in pinned memory,
+        # two sets of pinned result buffers (transfers are double buffered, nlp_fetch_async)
+        h_du = du.cpu().pin_memory(); h_dv = dv.cpu().pin_memory()
         h_out = [[torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()]
                  for _ in range(2)]
+        if args.e2e_upload:
+            h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
 
     def barrier():
         torch.cuda.synchronize()
@@ -299,31 +315,52 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def predict(m):
+        if shard == "sources":
+            r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
+            return r, n
+        r = pred.predict(m, D, max_edges=K)
+        return r, r["count"]
+
     def one_step(collect=None):
         edges = 0
         for m in measures:
-            if shard == "sources":
-                r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
-            else:
-                r = pred.predict(m, D, max_edges=K); n = r["count"]
+            r, n = predict(m)
             edges += n
             if collect is not None:
                 collect.append(r)
         return edges
 
+    def fetch_results(i, n):
+        if shard in ("comm", "sources") and rank != 0:
+            return                                  # every rank holds the full result; rank 0 hands it to the host
+        if shard == "sources":
+            pred.fetch_into(h_out[0][0].data_ptr(), h_out[0][1].data_ptr(), h_out[0][2].data_ptr(), n)
+        else:    # the device -> host transfer of this result overlaps the next prediction
+            o = h_out[i % 2]
+            pred.fetch_async(o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n)
+
     def one_step_e2e():
+        # One batch of the harness, host buffers in, host results out (main.cxx:164-169 + 208-221): bind the
+        # base graph (resident since it was loaded, as main.cxx's x), send this batch's deletions from
+        # pinned host memory, apply them on the device (nlp_apply_deletions), predict, fetch.
+        pred.set_graph_pointers(base[0].data_ptr(), base[1].data_ptr(), S, device=True, keep=base)
+        pred.apply_deletions(pointers=(h_du.data_ptr(), h_dv.data_ptr(), int(h_du.numel())))
+        edges = 0
+        for i, m in enumerate(measures):
+            r, n = predict(m)
+            fetch_results(i, n)
+            edges += n
+        pred.fetch_wait()
+        return edges
+
+    def one_step_upload():
+        # the same with the whole CSR of the batch's graph uploaded from pinned host memory (round 1's e2e)
         pred.set_graph_pointers(h_off.data_ptr(), h_keys.data_ptr(), S, device=False, keep=(h_off, h_keys))
         edges = 0
         for i, m in enumerate(measures):
-            if shard == "sources":
-                r, n, ms = N.distributed.predict_distributed(pred, m, D, K)
-            else:
-                r = pred.predict(m, D, max_edges=K); n = r["count"]
-            if shard == "sources":
-                pred.fetch_into(h_out[0][0].data_ptr(), h_out[0][1].data_ptr(), h_out[0][2].data_ptr(), n)
-            else:    # the device -> host transfer of this result overlaps the next prediction
-                o = h_out[i % 2]
-                pred.fetch_async(o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n)
+            r, n = predict(m)
+            fetch_results(i, n)
             edges += n
         pred.fetch_wait()
         return edges
@@ -359,32 +396,72 @@ def run_b200(args):
     for _ in range(args.warmup):
         one_step()
     launches0 = pred.launch_count()
+    comm0 = pred.comm_bytes()
     edges, ms, wall, results = timed(one_step, args.steps, collect=True)
     launches = pred.launch_count() - launches0
+    comm_bytes = pred.comm_bytes() - comm0
     value = edges / (ms / 1e3)
 
+    # in comm mode: is every rank's result the single-GPU result?  (checked outside the timed region)
+    identical = None
+    job = None
+    if shard == "comm":
+        import hashlib
+
+        def digest(m):
+            r = pred.predict(m, D, max_edges=K)
+            u, v, s_ = pred.fetch(r["count"])
+            return hashlib.sha256(u.tobytes() + v.tobytes() + s_.tobytes()).hexdigest() + ":%d" % r["count"]
+        check = [m for m in ("JC", "CN", "AA") if m in measures] or measures[:1]
+        with_comm = [digest(m) for m in check]
+        pred.comm_destroy()                          # leaves the handle on (0, 1): the whole prediction on this GPU
+        alone = [digest(m) for m in check]
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(N.Predictor.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, 0)
+        torch.cuda.synchronize()
+        pred.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        t = torch.tensor([int(with_comm == alone)], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        identical = bool(int(t[0]))
+    if world > 1:
+        # job-wide counters: the source-centric kernels count per rank, the bucket path's plan counters
+        # (first hop, eligible first hop, wedges) are already those of the whole graph
+        mine = [sum(r["wedges"] for r in results), sum(r["candidates"] for r in results),
+                sum(r["eligible_first_hop"] for r, m in zip(results, measures * args.steps) if m in ("AA", "RA")),
+                sum(r["count"] for r in results)]
+        t = torch.tensor(mine, device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot = [int(x) for x in t.tolist()]
+        global_stats = shard in ("comm", "sources") and results and results[0]["path"] == 2
+        job = {"W": mine[0] if global_stats else tot[0], "C": tot[1], "flt_elig": mine[2] if global_stats else tot[2],
+               "Kout": mine[3] if shard in ("comm", "sources") else tot[3],
+               "nrun": len(results) * (world if shard in ("batches", "measures") else 1)}
+
     # ---- e2e: host buffers in, host results out ----------------------------------------------
+    e2e = None
+    e2e_upload = None
     if do_e2e:
         for _ in range(max(1, min(args.warmup, 2))):
             one_step_e2e()
         e_edges, e_ms, e_wall, _ = timed(one_step_e2e, args.steps)
-        h2d = (S + 1) * 8 + M * 4
-        if shard == "batches":             # every rank moves its own graph: whole-job bytes
-            t = torch.tensor([h2d], device=dev, dtype=torch.int64)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            h2d = int(t[0])
-        elif shard in ("measures", "sources"):
-            h2d *= world
-        e2e = {"value": e_edges / (e_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(e_edges / args.steps) * 12, "ms_per_step": e_ms / args.steps}
-    else:
-        e2e = None
+        copies = 1 if shard in ("none",) else world      # every rank receives the batch
+        e2e = {"value": e_edges / (e_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": 8 * int(h_du.numel()) * copies,
+               "d2h_bytes_per_step": int(e_edges / args.steps) * 12, "ms_per_step": e_ms / args.steps,
+               "step": "bind the resident base graph, H2D of the batch's %d directed deletions from pinned memory, nlp_apply_deletions "
+                       "(CSR rebuilt on the device), %d predictions, every (u, v, score) list fetched to pinned host memory" % (int(h_du.numel()), len(measures))}
+        if args.e2e_upload:
+            for _ in range(max(1, min(args.warmup, 2))):
+                one_step_upload()
+            u_edges, u_ms, u_wall, _ = timed(one_step_upload, args.steps)
+            e2e_upload = {"value": u_edges / (u_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": ((S + 1) * 8 + M * 4) * copies,
+                          "d2h_bytes_per_step": int(u_edges / args.steps) * 12, "ms_per_step": u_ms / args.steps,
+                          "step": "the whole CSR of the batch's graph uploaded from pinned host memory (nlp_set_graph) instead of the batch update"}
+        pred.set_graph_pointers(off.data_ptr(), keys.data_ptr(), S, device=True, keep=(off, keys))
     # ---- extra: the same step with reuse across measures (nlp_set_reuse) -----
-    # The store is emptied at the start of every step, so each step does the full work once and
-    # the other measures of the step reuse the sorted wedge records.  Reported separately; the
-    # headline `value` above never reuses anything.
     sweep = None
-    if results and results[0]["path"] in (2, 3) and shard != "sources" and args.sweep_reuse:
+    if results and results[0]["path"] in (2, 3) and shard == "none" and args.sweep_reuse:
         def one_step_reuse():
             pred.set_reuse(True)
             return one_step()
@@ -394,7 +471,29 @@ def run_b200(args):
         pred.set_reuse(False)
         sweep = {"value": r_edges / (r_ms / 1e3), "unit": "edges/s", "ms_per_step": r_ms / args.steps,
                  "note": "sorted wedge records shared by the measures of a step; store emptied every step"}
+    # ---- extra (comm mode): N independent replicas, one whole step per GPU on the same batch ----------
+    replicas = None
+    if shard == "comm" and not args.no_replicas:
+        pred.comm_destroy()
+        for _ in range(2):
+            one_step()
+        barrier()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        rep_edges = 0
+        for _ in range(args.steps):
+            rep_edges += one_step()
+        ev1.record(stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        replicas = {"value": rep_edges * world / (float(t[0]) / 1e3), "unit": "edges/s", "ms_per_step": float(t[0]) / args.steps,
+                    "note": "%d independent replicas (one whole step per GPU, no collective): weak scaling, for comparison" % world}
     clocks = sampler.stop() if rank == 0 else None     # sampled over warm-up + all timed regions
+    if shard == "comm":
+        pred.comm_destroy()             # rank 0 goes on alone (parity check against the oracle)
+    elif shard == "sources":
+        pred.set_partition(0, 1)
 
     if rank != 0:
         if world > 1:
@@ -463,12 +562,14 @@ def run_b200(args):
     # HBM copy bandwidth.  `kernel_*` is the dominant phase against the traffic this implementation
     # chose to move through it (the figure round 1 called `frac`).
     flt_elig = sum(r["eligible_first_hop"] for r, m in zip(results, measures * args.steps) if m in ("AA", "RA"))
-    total_alg = nrun * (8 * (S + 1) + 4 * M + 4 * M) / max(1, world) + 4 * W + 4 * C + 12 * Kout + 4 * flt_elig
+    jW, jC, jF, jK, jn = (job["W"], job["C"], job["flt_elig"], job["Kout"], job["nrun"]) if job else (W, C, flt_elig, Kout, nrun)
+    total_alg = jn * (8 * (S + 1) + 4 * M + 4 * M) + 4 * jW + 4 * jC + 12 * jK + 4 * jF       # the whole job
     achieved = total_alg / (ms / 1e3) / 1e9
-    step_frac = achieved / peak
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": step_frac,
+    peak_job = peak * world
+    step_frac = achieved / peak_job
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_job, "unit": "GB/s", "frac": step_frac,
                 "traffic": traffic, "peak_source": peak_src,
-                "scope": "whole step: SURVEY.md 8(d) algorithmic bytes of all predictions / device time of the step",
+                "scope": "whole step: SURVEY.md 8(d) algorithmic bytes of all predictions of the job / device time of the step / (GPUs x measured HBM copy bandwidth)",
                 "algorithmic_bytes_per_step": total_alg / args.steps,
                 "kernel": dom[0], "kernel_gbs": kernel_gbs, "kernel_frac": kernel_gbs / peak,
                 "kernel_share_of_step": dom[1] / max(1e-9, sum(phase)),
@@ -537,10 +638,15 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak" if shard in ("none", "batches") else "strong",
+        "identical_to_single_gpu": identical,
+        "comm_bytes_per_step": comm_bytes / args.steps if world > 1 else 0,
+        "replicas": replicas,
+        "e2e_upload": e2e_upload,
         "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": make_config(info, D, all_measures, S, M),
         "run": {"build_s": build_s, "shard": shard,
                 "parallelism": {"none": "1 GPU",
+                                "comm": "sources of every prediction partitioned by wedge work over %d GPUs (contiguous source ranges of equal wedge-record count; CSR replicated), merged inside the library over NCCL: all-reduced select histograms (global cutoff), one all-gather of the survivors, final on-device sort; every rank holds the result" % world,
                                 "batches": "%d batches (independent random removals of the same graph, main.cxx:163), one whole step per GPU, CSR replicated, no collective" % world,
                                 "measures": "the %d predictions of a step dealt to %d GPUs (independent units, no collective), CSR replicated" % (len(all_measures), world),
                                 "sources": "sources of every prediction partitioned over %d GPUs, CSR replicated, one all-gather + on-device merge" % world}[shard]},
@@ -551,7 +657,7 @@ def run_b200(args):
         "sweep_reuse": sweep,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "wedges_per_s": W / (sum(r["scoring_ms"] for r in results) / 1e3),
+        "wedges_per_s": jW / (sum(r["scoring_ms"] for r in results) / 1e3),
         "step_hbm_frac": step_frac,
         "phase_ms_per_step": {n: p / args.steps for n, p in zip(names, phase)},
         "wall_ms_per_step": wall * 1e3 / args.steps,
@@ -573,9 +679,12 @@ def main():
     ap.add_argument("--workload", default="rmat22", choices=sorted(WORKLOADS))
     ap.add_argument("--degree", type=int, default=16, help="MINDEGREE1 of the LHub runs (0 = IHub)")
     ap.add_argument("--measures", default="", help="comma list (default: all nine)")
-    ap.add_argument("--shard", default="auto", choices=["auto", "batches", "measures", "sources"],
-                    help="N > 1: one batch per rank (weak scaling, default), the predictions of one batch dealt to the ranks, "
-                         "or the sources of each prediction partitioned (all-gather merge)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "comm", "batches", "measures", "sources"],
+                    help="N > 1: comm (default) = sources of every prediction partitioned by wedge work, merged inside the library "
+                         "over its NCCL communicator; batches = one batch per rank (weak scaling); measures = the predictions of one "
+                         "batch dealt to the ranks; sources = round-1 plumbing (torch.distributed all-gather + nlp_merge)")
+    ap.add_argument("--no-replicas", action="store_true", help="comm mode: skip the extra independent-replicas measurement")
+    ap.add_argument("--e2e-upload", action="store_true", help="also time the e2e step with the whole CSR uploaded per step (round 1's e2e)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run on the host cores")
     ap.add_argument("--sweep-reuse", action="store_true", help="also time the step with nlp_set_reuse (sorted-record store of the global-sort pair path)")

@@ -249,6 +249,23 @@ int nlp_fetch_deletions(nlp_handle* h, uint32_t* u, uint32_t* v, uint64_t capaci
  * nlp_generate_deletions / nlp_destroy.                                                         */
 int nlp_deletions_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d_v, uint64_t* count);
 
+/* ---- apply a batch of deletions on the device (second half) -----------------
+ * runBatches applies the tidied batch to a copy of the graph before the sweep of predictions
+ * (applyBatchUpdateOmpU, inc/batch.hxx:239-247, main.cxx:164,169): removeEdge(u, v) for every
+ * directed pair, then update().  nlp_apply_deletions does that to the RESIDENT graph without a host
+ * round trip of the CSR: the first stored copy of every requested pair is marked by binary search,
+ * the new degrees are scanned into new offsets and the keys are compacted.  n directed pairs
+ * (host or this GPU's pointers -- e.g. nlp_deletions_device's), unique as tidyBatchUpdateU leaves
+ * them; pairs that are not stored are ignored.  The result becomes the handle's graph (in memory
+ * the handle owns: arrays lent with nlp_set_graph_device are not written, so the base graph can be
+ * bound again for the next batch).  Uses the candidate buffers: the last result is gone.         */
+int nlp_apply_deletions(nlp_handle* h, const uint32_t* del_u, const uint32_t* del_v, uint64_t n);
+
+/* Size of the resident graph, and a copy of its CSR (offsets[span + 1], keys[entries]; host or
+ * this GPU's pointers; either may be NULL).                                                      */
+int nlp_graph_size(nlp_handle* h, uint32_t* span, uint64_t* entries);
+int nlp_fetch_graph(nlp_handle* h, uint64_t* offsets, uint32_t* keys);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t nlp_launch_count(const nlp_handle* h);
 

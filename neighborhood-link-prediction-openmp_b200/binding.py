@@ -18,7 +18,7 @@ STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
            "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_set_reuse", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
            "nlp_comm_unique_id", "nlp_comm_init", "nlp_comm_destroy", "nlp_comm_bytes",
-           "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
+           "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_apply_deletions", "nlp_graph_size", "nlp_fetch_graph", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
 class Options(C.Structure):
@@ -96,6 +96,9 @@ def load_library(build_if_missing=True):
     lib.nlp_generate_deletions.argtypes = [vp, u32, u64, C.POINTER(u64), C.POINTER(u64)]
     lib.nlp_fetch_deletions.argtypes = [vp, vp, vp, u64]
     lib.nlp_deletions_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    lib.nlp_apply_deletions.argtypes = [vp, vp, vp, u64]
+    lib.nlp_graph_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u64)]
+    lib.nlp_fetch_graph.argtypes = [vp, vp, vp]
     lib.nlp_launch_count.argtypes = [vp]
     lib.nlp_launch_count.restype = u64
     lib.nlp_stream.argtypes = [vp]
@@ -247,6 +250,30 @@ class Predictor:
         pu, pv, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
         self._check(self.lib.nlp_deletions_device(self.h, C.byref(pu), C.byref(pv), C.byref(n)))
         return pu.value, pv.value, int(n.value)
+
+    def apply_deletions(self, u=None, v=None, pointers=None):
+        """Remove directed pairs from the resident graph on the device (nlp_apply_deletions).
+        numpy arrays, or ``pointers=(u_ptr, v_ptr, n)`` (host or device); with neither, the batch
+        nlp_generate_deletions left on the GPU is applied."""
+        if pointers is None and u is None:
+            pointers = self.deletions_device()
+        if pointers is not None:
+            self._check(self.lib.nlp_apply_deletions(self.h, pointers[0], pointers[1], pointers[2]))
+            return
+        u = np.ascontiguousarray(u, dtype=np.uint32); v = np.ascontiguousarray(v, dtype=np.uint32)
+        self._check(self.lib.nlp_apply_deletions(self.h, u.ctypes.data if u.size else None, v.ctypes.data if v.size else None, u.size))
+
+    def graph_size(self):
+        s, m = C.c_uint32(0), C.c_uint64(0)
+        self._check(self.lib.nlp_graph_size(self.h, C.byref(s), C.byref(m)))
+        return int(s.value), int(m.value)
+
+    def fetch_graph(self):
+        """Host copy of the resident CSR (numpy uint64 offsets, uint32 keys)."""
+        S, M = self.graph_size()
+        off = np.empty(S + 1, np.uint64); keys = np.empty(M, np.uint32)
+        self._check(self.lib.nlp_fetch_graph(self.h, off.ctypes.data, keys.ctypes.data if M else None))
+        return off, keys
 
     def launch_count(self):
         return int(self.lib.nlp_launch_count(self.h))

@@ -120,4 +120,86 @@ __global__ void __launch_bounds__(256) k_batch_compact(const uint32_t* __restric
     if (head[i]) { ou[pos[i]] = pu[i]; ov[pos[i]] = pv[i]; }
 }
 
+
+// ---- apply a batch of deletions to the resident CSR (inc/batch.hxx:239-247, main.cxx:169) --------
+// applyBatchUpdateOmpU calls removeEdge(u, v) for every pair of the (unique) list and updates the
+// graph; one stored copy goes per request (a duplicated entry of a multiset row survives its own
+// removal, _algorithm.hxx:132-139).  Here: mark the first stored copy of every request by binary
+// search in row u (one bit per entry), count the marks per row, scan the new degrees into the
+// new offsets, and compact the keys tile by tile.
+enum { DEL_THREADS = 256, DEL_PER_THREAD = 8, DEL_TILE = DEL_THREADS * DEL_PER_THREAD };
+
+__global__ void __launch_bounds__(256) k_del_mark(DevGraph g, const uint32_t* __restrict__ du, const uint32_t* __restrict__ dv,
+                                                  uint64_t n, uint32_t* __restrict__ bits, uint32_t* __restrict__ marks) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = du[i], v = dv[i];
+    if (u >= g.S) continue;
+    const uint64_t ub = __ldg(g.off + u);
+    const uint32_t d = __ldg(g.deg + u);
+    uint32_t lo = 0, hi = d;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(g.keys + ub + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= d || __ldg(g.keys + ub + lo) != v) continue;            // not stored: ignored, as removeEdge does
+    const uint64_t e = ub + lo;
+    const uint32_t bit = 1u << (e & 31u);
+    const uint32_t old = atomicOr(bits + (e >> 5), bit);
+    if (!(old & bit)) atomicAdd(marks + u, 1u);                       // a repeated request removes nothing more
+  }
+}
+
+__global__ void __launch_bounds__(256) k_del_newdeg(const uint32_t* __restrict__ deg, uint32_t* __restrict__ marks, uint32_t S) {
+  for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < S; u += (uint64_t)gridDim.x * blockDim.x)
+    marks[u] = deg[u] - marks[u];
+}
+
+// kept entries per tile; a thread owns 8 consecutive entries = one byte of the bit array
+__global__ void __launch_bounds__(DEL_THREADS) k_del_count(const uint8_t* __restrict__ bits, uint64_t M, uint32_t* __restrict__ tile_counts) {
+  __shared__ uint32_t s_warp[DEL_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * DEL_TILE + (uint64_t)threadIdx.x * DEL_PER_THREAD;
+  uint32_t c = 0;
+  if (base < M) {
+    const uint32_t left = (uint32_t)(M - base < DEL_PER_THREAD ? M - base : DEL_PER_THREAD);
+    const uint32_t gone = bits[base >> 3] & ((1u << left) - 1u);
+    c = left - __popc(gone);
+  }
+  c = __reduce_add_sync(NLP_FULL, c);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    #pragma unroll
+    for (int w = 0; w < DEL_THREADS / 32; ++w) t += s_warp[w];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(DEL_THREADS) k_del_write(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ bits, uint64_t M,
+                                                            const unsigned long long* __restrict__ tile_off, uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_warp[DEL_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t base = (uint64_t)blockIdx.x * DEL_TILE + (uint64_t)threadIdx.x * DEL_PER_THREAD;
+  uint32_t left = 0, gone = 0, c = 0;
+  if (base < M) {
+    left = (uint32_t)(M - base < DEL_PER_THREAD ? M - base : DEL_PER_THREAD);
+    gone = bits[base >> 3] & ((1u << left) - 1u);
+    c = left - __popc(gone);
+  }
+  uint32_t inc = c;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t before = 0;
+  #pragma unroll
+  for (int w = 0; w < DEL_THREADS / 32; ++w) before += w < warp ? s_warp[w] : 0u;
+  unsigned long long pos = tile_off[blockIdx.x] + before + inc - c;
+  for (uint32_t k = 0; k < left; ++k)
+    if (!((gone >> k) & 1u)) out[pos++] = keys[base + k];
+}
+
 }  // namespace nlp

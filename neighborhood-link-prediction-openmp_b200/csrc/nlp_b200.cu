@@ -48,7 +48,8 @@ struct nlp_handle {
   // graph
   const uint64_t* d_off = nullptr;
   const uint32_t* d_keys = nullptr;
-  DevBuf own_off, own_keys;
+  DevBuf own_off, own_keys, spare_off, spare_keys;   // spare: destination of nlp_apply_deletions when the graph is the handle's own
+  DevBuf del_bits;
   uint32_t S = 0;
   uint64_t M = 0;
   uint32_t maxdeg = 0;
@@ -1521,7 +1522,7 @@ int nlp_destroy(nlp_handle* h) {
     if (h->ev_stg_ready[i]) cudaEventDestroy(h->ev_stg_ready[i]);
     if (h->ev_stg_done[i]) cudaEventDestroy(h->ev_stg_done[i]);
   }
-  release(h->own_off); release(h->own_keys); release(h->deg); release(h->work); release(h->work64); release(h->elig); release(h->maxdeg_dev);
+  release(h->own_off); release(h->own_keys); release(h->spare_off); release(h->spare_keys); release(h->del_bits); release(h->deg); release(h->work); release(h->work64); release(h->elig); release(h->maxdeg_dev);
   release(h->chunk_base); release(h->chunk_src); release(h->chunk_cnt); release(h->ecount); release(h->ekeys);
   release(h->scan_tiles); release(h->scan_total);
   release(h->it_u); release(h->it_cnt); release(h->it_dw); release(h->it_ptr); release(h->it_off); release(h->sym_flag);
@@ -1861,6 +1862,81 @@ int nlp_generate_deletions(nlp_handle* h, uint32_t seed, uint64_t batch_size, ui
   h->has_deletions = true;
   if (count) *count = m;
   if (words) *words = 2ull * (last_hit != BATCH_NONE ? (uint64_t)last_hit + 2ull : (uint64_t)last + 5ull);
+  return NLP_OK;
+}
+
+int nlp_apply_deletions(nlp_handle* h, const uint32_t* del_u, const uint32_t* del_v, uint64_t n) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_graph) return fail(h, NLP_ERR_NO_GRAPH, "nlp_apply_deletions: no graph set");
+  if (n && (!del_u || !del_v)) return fail(h, NLP_ERR_ARG, "nlp_apply_deletions: null input");
+  if (n >= 0xfffffff0ull) return fail(h, NLP_ERR_CAPACITY, "nlp_apply_deletions: batch too large");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  const uint32_t S = h->S;
+  const uint64_t M = h->M;
+  const DevGraph g = dev_graph(h);
+  h->has_result = false;                               // the candidate buffers stage the request list
+  NLP_TRY(ensure_candidates(h, n));
+  uint32_t* du = (uint32_t*)h->cu[0].p; uint32_t* dv = (uint32_t*)h->cv[0].p;
+  if (n) {
+    NLP_CUDA(h, cudaMemcpyAsync(du, del_u, n * 4, cudaMemcpyDefault, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(dv, del_v, n * 4, cudaMemcpyDefault, h->stream));
+  }
+  const uint64_t nwords = (M + 31) / 32 + 2;
+  NLP_TRY(ensure(h, h->del_bits, nwords * 4));
+  NLP_CUDA(h, cudaMemsetAsync(h->del_bits.p, 0, nwords * 4, h->stream));
+  uint32_t* marks = (uint32_t*)h->work.p;              // [S]: marks per row, then the new degrees
+  NLP_CUDA(h, cudaMemsetAsync(marks, 0, (size_t)S * 4, h->stream));
+  if (n) {
+    k_del_mark<<<grid_for(n, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, du, dv, n, (uint32_t*)h->del_bits.p, marks);
+    NLP_LAUNCHED(h);
+  }
+  // the new CSR goes to buffers this handle owns; a borrowed graph (nlp_set_graph_device) is left untouched
+  const bool cur_is_own = h->d_off == (const uint64_t*)h->own_off.p && h->own_off.p != nullptr;
+  DevBuf& n_off = cur_is_own ? h->spare_off : h->own_off;
+  DevBuf& n_keys = cur_is_own ? h->spare_keys : h->own_keys;
+  NLP_TRY(ensure(h, n_off, ((size_t)S + 1) * 8));
+  NLP_TRY(ensure(h, n_keys, (size_t)M * 4));
+  uint64_t M2 = 0;
+  if (S) {
+    k_del_newdeg<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g.deg, marks, S);
+    NLP_LAUNCHED(h);
+    NLP_TRY(exclusive_scan<uint32_t>(h, marks, S, (unsigned long long*)n_off.p, &M2));
+  }
+  NLP_CUDA(h, cudaMemcpyAsync((unsigned long long*)n_off.p + S, &M2, 8, cudaMemcpyHostToDevice, h->stream));
+  if (M) {
+    const uint32_t ntiles = (uint32_t)((M + DEL_TILE - 1) / DEL_TILE);
+    NLP_TRY(ensure(h, h->oc_counts, (size_t)ntiles * 4));
+    NLP_TRY(ensure(h, h->oc_off, (size_t)ntiles * 8));
+    k_del_count<<<ntiles, DEL_THREADS, 0, h->stream>>>((const uint8_t*)h->del_bits.p, M, (uint32_t*)h->oc_counts.p);
+    NLP_LAUNCHED(h);
+    NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, nullptr));
+    k_del_write<<<ntiles, DEL_THREADS, 0, h->stream>>>(g.keys, (const uint8_t*)h->del_bits.p, M,
+                                                       (const unsigned long long*)h->oc_off.p, (uint32_t*)n_keys.p);
+    NLP_LAUNCHED(h);
+  }
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));       // &M2 above is a stack address
+  if (cur_is_own) { std::swap(h->own_off, h->spare_off); std::swap(h->own_keys, h->spare_keys); }
+  h->d_off = (const uint64_t*)h->own_off.p;
+  h->d_keys = (const uint32_t*)h->own_keys.p;
+  h->has_graph = false;
+  return finish_graph(h);
+}
+
+int nlp_graph_size(nlp_handle* h, uint32_t* span, uint64_t* entries) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_graph) return fail(h, NLP_ERR_NO_GRAPH, "nlp_graph_size: no graph set");
+  if (span) *span = h->S;
+  if (entries) *entries = h->M;
+  return NLP_OK;
+}
+
+int nlp_fetch_graph(nlp_handle* h, uint64_t* offsets, uint32_t* keys) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_graph) return fail(h, NLP_ERR_NO_GRAPH, "nlp_fetch_graph: no graph set");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  if (offsets) NLP_CUDA(h, cudaMemcpyAsync(offsets, h->d_off, ((size_t)h->S + 1) * 8, cudaMemcpyDefault, h->stream));
+  if (keys && h->M) NLP_CUDA(h, cudaMemcpyAsync(keys, h->d_keys, (size_t)h->M * 4, cudaMemcpyDefault, h->stream));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
   return NLP_OK;
 }
 

@@ -138,6 +138,23 @@ def ref_edge_deletions(offsets, keys, seed, batch_size):
     return u[:n].copy(), v[:n].copy()
 
 
+def ref_apply_deletions(offsets, keys, del_u, del_v):
+    """The reference's own applyBatchUpdateOmpU (inc/batch.hxx:239-247) on a DiGraph built from the
+    CSR; returns the CSR of the graph afterwards."""
+    lib = C.CDLL(os.path.join(_HERE, "_ref", "libnlpref_batch.so"))
+    lib.nlpref_apply_deletions.restype = C.c_int64
+    lib.nlpref_apply_deletions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                           C.c_void_p, C.c_void_p]
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    du = np.ascontiguousarray(del_u, dtype=np.uint32); dv = np.ascontiguousarray(del_v, dtype=np.uint32)
+    o2 = np.empty_like(offsets); k2 = np.empty(max(keys.size, 1), np.uint32)
+    n = lib.nlpref_apply_deletions(offsets.ctypes.data, keys.ctypes.data if keys.size else None, offsets.shape[0] - 1,
+                                   du.ctypes.data if du.size else None, dv.ctypes.data if dv.size else None, du.size,
+                                   o2.ctypes.data, k2.ctypes.data)
+    return o2, k2[:n].copy()
+
+
 def ref_available():
     return os.path.exists(os.path.join(_HERE, "_ref", "libnlpref.so"))
 

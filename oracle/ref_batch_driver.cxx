@@ -35,4 +35,30 @@ int64_t nlpref_edge_deletions(const uint64_t* offsets, const uint32_t* keys, uin
   return (int64_t)deletions.size();
 }
 
+// The reference's applyBatchUpdateOmpU (inc/batch.hxx:239-247, as runBatches calls it at
+// main.cxx:169) on a DiGraph built from the CSR: removes the directed pairs (del_u[i], del_v[i]),
+// then dumps the graph back as CSR.  out_keys needs room for the input's M entries; returns the
+// number of entries left (out_offsets[span]).
+int64_t nlpref_apply_deletions(const uint64_t* offsets, const uint32_t* keys, uint32_t span,
+                               const uint32_t* del_u, const uint32_t* del_v, uint64_t ndel,
+                               uint64_t* out_offsets, uint32_t* out_keys) {
+  using K = uint32_t;
+  DiGraph<K, None, None> y;
+  for (uint32_t u = 1; u < span; ++u) y.addVertex(u);
+  for (uint32_t u = 0; u < span; ++u)
+    for (uint64_t e = offsets[u]; e < offsets[u + 1]; ++e) y.addEdge(u, keys[e]);
+  updateOmpU(y);
+  vector<tuple<K, K>> deletions, insertions;
+  deletions.reserve(ndel);
+  for (uint64_t i = 0; i < ndel; ++i) deletions.push_back(make_tuple(del_u[i], del_v[i]));
+  applyBatchUpdateOmpU(y, deletions, insertions);
+  uint64_t at = 0;
+  for (uint32_t u = 0; u < span; ++u) {
+    out_offsets[u] = at;
+    if (y.hasVertex(u)) y.forEachEdgeKey(u, [&](K v) { out_keys[at++] = v; });
+  }
+  out_offsets[span] = at;
+  return (int64_t)at;
+}
+
 }  // extern "C"

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import batch_parallel
+import parity
 
 HAVE_REF = os.path.isdir("/root/reference") or os.path.exists(
     os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libnlpref_batch.so"))
@@ -97,5 +98,65 @@ def test_device_batch_generation_matches_oracle(nlp, oracle):
         r = pred.predict("JC", 0, max_edges=n // 2)
         ev = pred.evaluate()
         assert ev["truth"] == n and ev["predicted"] == 2 * r["count"] and ev["common"] == 0   # existing edges are never predicted
+    finally:
+        pred.close()
+
+
+@pytest.mark.gpu
+def test_device_apply_deletions_matches_reference(nlp, oracle):
+    """nlp_apply_deletions (mark by binary search, rescan offsets, compact keys) against the
+    reference's own applyBatchUpdateOmpU (oracle/_ref, simple graphs) and against the torch
+    restatement (also multiset rows: one stored copy goes per request); the rebuilt graph then
+    predicts like a freshly uploaded one.  Graph lent with nlp_set_graph_device stays untouched."""
+    import torch
+    g = nlp.graphs
+    pred = nlp.Predictor(0)
+    try:
+        cases = dict(graphs(nlp))
+        o, k = g.duplicate_symmetric(*g.planted_partition(3000, 40, 8, 2, 77), every=3, copies=2)
+        cases["pp3k_symdup"] = g.to_numpy(o, k)
+        for name, (off, keys) in cases.items():
+            B = max(3, len(keys) // 20)
+            for mode in ("host", "device"):
+                if mode == "host":
+                    pred.set_graph(off, keys)
+                else:
+                    d_off = torch.from_numpy(off.astype(np.int64)).cuda(); d_keys = torch.from_numpy(keys.astype(np.int32)).cuda()
+                    pred.set_graph_pointers(d_off.data_ptr(), d_keys.data_ptr(), len(off) - 1, device=True, keep=(d_off, d_keys))
+                du, dv, _ = pred.generate_deletions(12345, B)
+                if mode == "host":
+                    pred.apply_deletions(du, dv)
+                else:
+                    pred.apply_deletions()                      # the batch still on the GPU
+                o2, k2 = pred.fetch_graph()
+                to, tk = g.apply_deletions(torch.from_numpy(off.astype(np.int64)), torch.from_numpy(keys.astype(np.int32)),
+                                           torch.from_numpy(du.astype(np.int64)), torch.from_numpy(dv.astype(np.int64)))
+                to, tk = g.to_numpy(to, tk)
+                assert np.array_equal(o2, to) and np.array_equal(k2, tk), (name, mode)
+                if name != "pp3k_symdup" and oracle.ref_batch_available():
+                    ro, rk = oracle.ref_apply_deletions(off, keys, du, dv)
+                    assert np.array_equal(o2, ro) and np.array_equal(k2, rk), (name, mode, "reference applyBatchUpdateOmpU")
+                if mode == "device":
+                    assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), off) and np.array_equal(d_keys.cpu().numpy().view(np.uint32), keys)
+                K = max(1, len(du) // 2)
+                for m, D in (("JC", 4), ("AA", 16), ("CN", 0)):
+                    r = pred.predict(m, D, max_edges=K)
+                    got = pred.fetch(r["count"])
+                    want = oracle.oracle_predict(o2, k2, m, D, max_edges=K)[:3]
+                    assert parity.compare(got, want, "after apply %s %s %s D=%d" % (name, mode, m, D)) is None
+        # a second batch on top of the first (the handle's own graph is the source now), repeated requests, absent pairs
+        off, keys = cases["rmat12"]
+        pred.set_graph(off, keys)
+        du, dv, _ = pred.generate_deletions(1, 400)
+        pred.apply_deletions(du, dv)
+        o2, k2 = pred.fetch_graph()
+        du2, dv2, _ = pred.generate_deletions(2, 400)
+        du2 = np.concatenate([du2, du2[:10], np.array([1, 5], np.uint32)]); dv2 = np.concatenate([dv2, dv2[:10], np.array([1, 4000], np.uint32)])
+        pred.apply_deletions(du2, dv2)
+        o3, k3 = pred.fetch_graph()
+        to, tk = g.apply_deletions(torch.from_numpy(o2.astype(np.int64)), torch.from_numpy(k2.astype(np.int32)),
+                                   torch.from_numpy(du2.astype(np.int64)), torch.from_numpy(dv2.astype(np.int64)))
+        to, tk = g.to_numpy(to, tk)
+        assert np.array_equal(o3, to) and np.array_equal(k3, tk)
     finally:
         pred.close()
