@@ -448,7 +448,12 @@ k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
 template <bool FLT>
 __global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restrict__ al_u, const uint32_t* __restrict__ al_v,
                                                const uint32_t* __restrict__ al_c, uint32_t* __restrict__ al_s,
-                                               uint64_t lo, uint64_t hi) {
+                                               uint64_t lo, uint64_t hi, Select11* sel) {
+  // first level of the top-K select (select.cuh, Select11): histogram of the top 11 bits of every
+  // kept score, accumulated here so that the select does not have to read the scores again
+  __shared__ uint32_t s_h[2048];
+  for (int i = threadIdx.x; i < 2048; i += 256) s_h[i] = 0;
+  __syncthreads();
   Tally tally;
   const uint64_t n = hi - lo, n32 = (n + 31u) & ~31ull;
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n32; t += (uint64_t)gridDim.x * blockDim.x) {
@@ -467,9 +472,15 @@ __global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restr
     }
     float score;
     const bool keep = score_pair(p, head, u, du, v, cnt, acc, tally, &score);
-    if (c != BK_DONE) al_s[i] = keep ? __float_as_uint(score) : NLP_NO_SCORE;
+    uint32_t sb = keep ? __float_as_uint(score) : NLP_NO_SCORE;
+    if (c != BK_DONE) al_s[i] = sb;
+    else if (t < n) sb = al_s[i];                      // big source: scored by k_pair_reduce already
+    if (sb != NLP_NO_SCORE) atomicAdd(&s_h[desc_key(sb) >> 21], 1u);
   }
   tally.flush(p.ctr);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 256)
+    if (s_h[i]) atomicAdd(&sel->hist[i], (unsigned long long)s_h[i]);
 }
 
 // Big sources: their records were sorted and reduced by the global machinery of pairs.cuh in the

@@ -85,7 +85,9 @@ struct nlp_handle {
   // dense spill tables
   DevBuf tables, touched, range_cursors, range_touched;
   // select / sort scratch
-  DevBuf counts, totals, hist, sel, cursor2;
+  DevBuf counts, totals, hist, sel, cursor2, sel11;
+  Select11* h_sel11 = nullptr;         // pinned (header + digit histograms)
+  bool sel11_l0 = false;               // the scoring kernel already accumulated the first select histogram
   DevBuf oc_counts, oc_off;                  // ordered compaction (pair path top-K)
   // pair path: records sorted by (u, v) at (pair_pu, pair_pv), aligned scores in cs[pair_score_buf]
   bool pair_pending = false;
@@ -124,6 +126,9 @@ struct nlp_handle {
   // asynchronous fetch: result -> staging (device copy on the compute stream) -> caller memory
   // (copy stream), double buffered, so the next prediction overlaps the transfer
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // big-source detour of the bucket path, concurrent with k_bucket
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<DevBuf> arena_pool;            // plan arenas of earlier graphs, reused (no cudaMalloc / cudaFree per batch)
   DevBuf stg_u[2], stg_v[2], stg_s[2];
   cudaEvent_t ev_stg_ready[2] = {nullptr, nullptr}, ev_stg_done[2] = {nullptr, nullptr};
   bool stg_busy[2] = {false, false};
@@ -253,8 +258,46 @@ void clear_pair_cache(nlp_handle* h) {
   h->cache_bytes = 0;
 }
 
+// The arenas of dropped plans are kept for the plans of the next graph: a batch of the harness
+// rebuilds its plans on a graph of nearly the same size, and cudaFree / cudaMalloc of hundreds of
+// megabytes costs milliseconds (sometimes hundreds) each.
+void retire_arena(nlp_handle* h, DevBuf& a) {
+  if (!a.p) return;
+  if (h->arena_pool.size() >= 8) {                   // bounded: drop the smallest
+    size_t k = 0;
+    for (size_t i = 1; i < h->arena_pool.size(); ++i) if (h->arena_pool[i].cap < h->arena_pool[k].cap) k = i;
+    if (h->arena_pool[k].cap < a.cap) std::swap(h->arena_pool[k], a);
+    release(a);
+    return;
+  }
+  h->arena_pool.push_back(a);
+  a.p = nullptr; a.cap = 0;
+}
+
+bool take_arena(nlp_handle* h, DevBuf& a, size_t bytes) {
+  size_t best = h->arena_pool.size();
+  for (size_t i = 0; i < h->arena_pool.size(); ++i)
+    if (h->arena_pool[i].cap >= bytes && (best == h->arena_pool.size() || h->arena_pool[i].cap < h->arena_pool[best].cap)) best = i;
+  if (best < h->arena_pool.size()) {
+    a = h->arena_pool[best];
+    h->arena_pool.erase(h->arena_pool.begin() + best);
+    return true;
+  }
+  const size_t want = bytes + bytes / 16;            // a little headroom for the next, slightly different graph
+  if (cudaMalloc(&a.p, want) != cudaSuccess) {
+    cudaGetLastError();
+    for (auto& b : h->arena_pool) release(b);        // give the pooled memory back and try once more
+    h->arena_pool.clear();
+    if (cudaMalloc(&a.p, bytes) != cudaSuccess) { cudaGetLastError(); a.p = nullptr; a.cap = 0; return false; }
+    a.cap = bytes;
+    return true;
+  }
+  a.cap = want;
+  return true;
+}
+
 void clear_plans(nlp_handle* h) {
-  for (auto& kv : h->plans) release(kv.second.arena);
+  for (auto& kv : h->plans) retire_arena(h, kv.second.arena);
   h->plans.clear();
   h->plan_bytes = 0;
 }
@@ -425,54 +468,6 @@ int top_k(nlp_handle* h, int buf, uint64_t n, uint64_t K, int* out_buf, uint64_t
   }
   NLP_TRY(radix_sort(h, buf, n, out_buf));
   *out_n = std::min(n, K);
-  return NLP_OK;
-}
-
-// Pair path: the records in buffer `sb` are sorted by (u, v), cs[sb ^ 1] holds the aligned score
-// bits (NLP_NO_SCORE = nothing).  Select on the score alone, copy the survivors out in order,
-// stable-sort them by score: ties stay in ascending (u, v) order = canonical order.
-int top_k_ordered(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
-  const uint32_t* pu = h->pair_pu;
-  const uint32_t* pv = h->pair_pv;
-  const uint64_t n = h->pair_n, kept = h->pair_kept;
-  const int sbuf = h->pair_score_buf, ob = sbuf ^ 1;
-  const bool external = h->pair_ps != nullptr;       // bucket path: records and scores in the aligned arrays
-  *out_buf = external ? 0 : ob; *out_n = 0;
-  if (!n || !kept) return NLP_OK;
-  const uint32_t* sbits = external ? h->pair_ps : (const uint32_t*)h->cs[sbuf].p;
-  int mode = 0;
-  if (K < kept) {
-    NLP_CUDA(h, cudaMemsetAsync(h->sel.p, 0, sizeof(SelectState), h->stream));
-    const uint64_t slack = std::max<uint64_t>(K / 8, 65536);
-    for (int lvl = 0; lvl < 4; ++lvl) {            // at most 32 score bits: all levels queued, the state stays on the device
-      k_select_hist<<<grid_for(n, 256 * 8, h->num_sms * 8), 256, 0, h->stream>>>(pu, pv, sbits, n, (SelectState*)h->sel.p);
-      NLP_LAUNCHED(h);
-      k_select_step<<<1, 1, 0, h->stream>>>((SelectState*)h->sel.p, (unsigned long long)K, (unsigned long long)slack, 32u);
-      NLP_LAUNCHED(h);
-    }
-    mode = 1;   // K < kept <= n: at least one level ran; k_ordered_* read the exact state on the device
-  }
-  const uint32_t ntiles = (uint32_t)((n + OC_TILE - 1) / OC_TILE);
-  NLP_TRY(ensure(h, h->oc_counts, (size_t)ntiles * 4));
-  NLP_TRY(ensure(h, h->oc_off, (size_t)ntiles * 8));
-  k_ordered_count<<<ntiles, OC_THREADS, 0, h->stream>>>(sbits, n, (const SelectState*)h->sel.p, mode, (uint32_t*)h->oc_counts.p);
-  NLP_LAUNCHED(h);
-  uint64_t m = 0;
-  NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &m));
-  // Survivors go to buffer `ob`.  When the records live in candidate buffer `ob` themselves (no
-  // cache), its u/v arrays are still being read: write to (cu[sbuf], cv[sbuf], cs[ob]) instead and
-  // swap the two score arrays afterwards, which makes that triple buffer `sbuf`.  External records
-  // (bucket path): survivors simply go to buffer 0.
-  int res = ob;
-  uint32_t *ou = (uint32_t*)h->cu[ob].p, *ov = (uint32_t*)h->cv[ob].p, *os = (uint32_t*)h->cs[ob].p;
-  if (external) { res = 0; ou = (uint32_t*)h->cu[0].p; ov = (uint32_t*)h->cv[0].p; os = (uint32_t*)h->cs[0].p; }
-  else if (!h->pair_from_cache) { ou = (uint32_t*)h->cu[sbuf].p; ov = (uint32_t*)h->cv[sbuf].p; res = sbuf; }
-  k_ordered_write<<<ntiles, OC_THREADS, 0, h->stream>>>(pu, pv, sbits, n, (const SelectState*)h->sel.p, mode,
-                                                        (const unsigned long long*)h->oc_off.p, ou, ov, os);
-  NLP_LAUNCHED(h);
-  if (!external && !h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
-  NLP_TRY(radix_sort(h, res, m, out_buf, 8));      // score digits only
-  *out_n = std::min(m, K);
   return NLP_OK;
 }
 
@@ -717,11 +712,11 @@ int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan&
       if (&i->second != &plan && (lru == h->plans.end() || i->second.stamp < lru->second.stamp)) lru = i;
     if (lru == h->plans.end()) break;
     h->plan_bytes -= lru->second.arena.cap;
-    release(lru->second.arena);
+    retire_arena(h, lru->second.arena);
     h->plans.erase(lru);
   }
   if (h->plan_bytes + bytes > budget / 4) return NLP_OK;
-  if (!try_ensure(h, plan.arena, bytes)) return NLP_OK;
+  if (!take_arena(h, plan.arena, bytes)) return NLP_OK;
   h->plan_bytes += plan.arena.cap;
   { Carver c(plan.arena.p); carve_plan(c); }
   k_plan_scatter<<<gE, 256, 0, h->stream>>>(su, sidx, it_dw, it_ptr, g_cnt, head, hs, rc, f_item, si, sr, ks,
@@ -740,6 +735,33 @@ int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan&
   return NLP_OK;
 }
 
+// Big sources of a plan (more records than half a bucket): wedge records to the candidate buffers,
+// global stable radix sort by (u, v), run reduce + exclusion + scoring (pairs.cuh), results into
+// their slots of the aligned output.  Launches on h->stream.
+template <bool FLT>
+int big_detour(nlp_handle* h, const nlp_handle::BucketPlan& plan, const Params& p, uint64_t kb0, uint64_t kb1,
+               uint32_t* al_u, uint32_t* al_v, uint32_t* al_s, uint32_t* al_c) {
+  const uint64_t ib0 = plan.h_bg_item[kb0], ib1 = plan.h_bg_item[kb1];
+  const uint64_t r0 = plan.h_bg_first[kb0], r1 = plan.h_bg_first[kb1];
+  const uint64_t Eb = ib1 - ib0, Pb = r1 - r0;
+  if (!Pb) return NLP_OK;
+  PairItems bi = plan.big_items;
+  bi.u += ib0; bi.cnt += ib0; bi.dw += ib0; bi.ptr += ib0;
+  k_pair_emit<FLT><<<grid_for(Eb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+      p.g.keys, Eb, bi, plan.b_off + ib0, (unsigned long long)r0, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+  NLP_LAUNCHED(h);
+  int sb = 0;
+  NLP_TRY(radix_sort_pairs(h, 0, Pb, FLT, &sb));
+  k_pair_reduce<FLT><<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+      p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, Pb, (uint32_t*)h->cs[sb ^ 1].p);
+  NLP_LAUNCHED(h);
+  k_big_place<<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+      (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb ^ 1].p, Pb, r0,
+      plan.bg_first, plan.bg_roff, (uint32_t)kb0, (uint32_t)kb1, al_u, al_v, al_s, al_c);
+  NLP_LAUNCHED(h);
+  return NLP_OK;
+}
+
 // LHub bucket path.  *used stays false when the graph's rows are not symmetric or the plan / the
 // aligned output do not fit the scratch budget; the caller then runs the source-centric kernels.
 template <bool FLT>
@@ -753,7 +775,7 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   if (it == h->plans.end()) {
     nlp_handle::BucketPlan& np = h->plans[key];
     const int rc = build_plan(h, opt->min_degree1, half, np);
-    if (rc != NLP_OK) { h->plan_bytes -= std::min<uint64_t>(h->plan_bytes, np.arena.cap); release(np.arena); h->plans.erase(key); return rc; }
+    if (rc != NLP_OK) { h->plan_bytes -= std::min<uint64_t>(h->plan_bytes, np.arena.cap); retire_arena(h, np.arena); h->plans.erase(key); return rc; }
     it = h->plans.find(key);
   }
   nlp_handle::BucketPlan& plan = it->second;
@@ -802,6 +824,18 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   }
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
+  // big sources: global sort of their records (pairs.cuh), then into their slots -- issued on a
+  // second stream BEFORE k_bucket, so the two run side by side (disjoint buffers; k_score waits for both)
+  const bool detour = kb1 > kb0;
+  if (detour) {
+    NLP_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    NLP_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    std::swap(h->stream, h->stream2);              // the helpers launch on h->stream
+    int rc = big_detour<FLT>(h, plan, p, kb0, kb1, al_u, al_v, al_s, al_c);
+    if (rc == NLP_OK && cudaEventRecord(h->ev_join, h->stream) != cudaSuccess) rc = fail(h, NLP_ERR_CUDA, "cudaEventRecord(ev_join)");
+    std::swap(h->stream, h->stream2);
+    NLP_TRY(rc);
+  }
   // small sources: one block per bucket
   if (b1 > b0) {
     const uint32_t top = h->S ? h->S - 1 : 0;
@@ -817,32 +851,16 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
     }
   }
   NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
-  // big sources: global sort of their records (pairs.cuh), then into their slots
-  if (kb1 > kb0) {
-    const uint64_t ib0 = plan.h_bg_item[kb0], ib1 = plan.h_bg_item[kb1];
-    const uint64_t r0 = plan.h_bg_first[kb0], r1 = plan.h_bg_first[kb1];
-    const uint64_t Eb = ib1 - ib0, Pb = r1 - r0;
-    PairItems bi = plan.big_items;
-    bi.u += ib0; bi.cnt += ib0; bi.dw += ib0; bi.ptr += ib0;
-    k_pair_emit<FLT><<<grid_for(Eb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-        p.g.keys, Eb, bi, plan.b_off + ib0, (unsigned long long)r0, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
-    NLP_LAUNCHED(h);
-    int sb = 0;
-    NLP_TRY(radix_sort_pairs(h, 0, Pb, FLT, &sb));
-    k_pair_reduce<FLT><<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-        p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, Pb, (uint32_t*)h->cs[sb ^ 1].p);
-    NLP_LAUNCHED(h);
-    k_big_place<<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-        (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb ^ 1].p, Pb, r0,
-        plan.bg_first, plan.bg_roff, (uint32_t)kb0, (uint32_t)kb1, al_u, al_v, al_s, al_c);
-    NLP_LAUNCHED(h);
-  }
+  if (detour) NLP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   NLP_CUDA(h, cudaEventRecord(h->ev_phase[2], h->stream));
-  // exclusion + scoring of the small sources' pairs, one thread per slot
+  // exclusion + scoring of the small sources' pairs, one thread per slot; also the first
+  // histogram of the top-K select (Select11)
+  NLP_CUDA(h, cudaMemsetAsync(h->sel11.p, 0, sizeof(Select11), h->stream));
   if (shi > slo) {
-    k_score<FLT><<<grid_for(shi - slo, 256, h->num_sms * 16), 256, 0, h->stream>>>(p, al_u, al_v, al_c, al_s, slo, shi);
+    k_score<FLT><<<grid_for(shi - slo, 256, h->num_sms * 16), 256, 0, h->stream>>>(p, al_u, al_v, al_c, al_s, slo, shi, (Select11*)h->sel11.p);
     NLP_LAUNCHED(h);
   }
+  h->sel11_l0 = true;
   for (int i = 3; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
   h->phases_valid = true;
   NLP_TRY(read_counters(h));
@@ -1378,55 +1396,122 @@ int gather_candidates(nlp_handle* h, int buf, uint64_t m, uint64_t* total) {
   return NLP_OK;
 }
 
-// The merge of a multi-GPU prediction (replaces the serial T-way heap merge of
-// inc/predict.hxx:431-460): global cutoff by all-reduced select histograms, local compaction of the
-// survivors, one all-gather, final on-device sort.  Every rank ends with the same result.
-int dist_top_k(nlp_handle* h, int buf, uint64_t fill, uint64_t K, int* out_buf, uint64_t* out_n) {
-  uint64_t m = 0, total = 0;
-  int lb = 0;
-  if (h->pair_pending) {
-    // records (and the kept pairs among them) lie in ascending (u, v) order in the aligned arrays
-    const uint32_t* pu = h->pair_pu; const uint32_t* pv = h->pair_pv;
-    const uint64_t n = h->pair_n;
-    const bool external = h->pair_ps != nullptr;
-    const int sbuf = h->pair_score_buf, ob = sbuf ^ 1;
-    const uint32_t* sbits = external ? h->pair_ps : (const uint32_t*)h->cs[sbuf].p;
-    uint64_t kept_all = 0;
-    NLP_TRY(global_count(h, h->pair_kept, &kept_all));
-    const int mode = K < kept_all ? 1 : 0;          // fewer kept pairs than asked for: everything survives
-    if (mode) NLP_TRY(select_narrow(h, pu, pv, sbits, n, K, 32u, true));
-    const uint32_t ntiles = (uint32_t)((n + OC_TILE - 1) / OC_TILE);
-    if (n) {
-      NLP_TRY(ensure(h, h->oc_counts, (size_t)ntiles * 4));
-      NLP_TRY(ensure(h, h->oc_off, (size_t)ntiles * 8));
-      k_ordered_count<<<ntiles, OC_THREADS, 0, h->stream>>>(sbits, n, (const SelectState*)h->sel.p, mode, (uint32_t*)h->oc_counts.p);
-      NLP_LAUNCHED(h);
-      NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &m));
-      int res = ob;
-      uint32_t *ou = (uint32_t*)h->cu[ob].p, *ov = (uint32_t*)h->cv[ob].p, *os = (uint32_t*)h->cs[ob].p;
-      if (external) { res = 0; ou = (uint32_t*)h->cu[0].p; ov = (uint32_t*)h->cv[0].p; os = (uint32_t*)h->cs[0].p; }
-      else if (!h->pair_from_cache) { ou = (uint32_t*)h->cu[sbuf].p; ov = (uint32_t*)h->cv[sbuf].p; res = sbuf; }
-      k_ordered_write<<<ntiles, OC_THREADS, 0, h->stream>>>(pu, pv, sbits, n, (const SelectState*)h->sel.p, mode,
-                                                            (const unsigned long long*)h->oc_off.p, ou, ov, os);
-      NLP_LAUNCHED(h);
-      if (!external && !h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
-      lb = res;
-    }
-    NLP_TRY(gather_candidates(h, lb, m, &total));
-    if (h->part_ordered) {
-      // ranks own ascending source ranges: the gathered list is in (u, v) order inside every score
-      // class, so a stable sort by score alone is the canonical order
-      NLP_TRY(radix_sort(h, 0, total, out_buf, 8));
-      *out_n = std::min(total, K);
-      return NLP_OK;
-    }
-    return top_k(h, 0, total, K, out_buf, out_n);
+// Stable sort of buffer `buf` by the score digits that are not constant (known from digit
+// histograms the caller already has: `constant` bit d set = digit d of desc_key(score) is the same
+// for every entry).
+int radix_sort_score(nlp_handle* h, int buf, uint64_t n, unsigned constant, int* out_buf) {
+  *out_buf = buf;
+  if (n < 2) return NLP_OK;
+  const uint32_t nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  NLP_TRY(ensure(h, h->counts, (size_t)nblocks * 256 * 4));
+  for (int d = 0; d < 4; ++d) {
+    if ((constant >> d) & 1u) continue;
+    NLP_TRY(radix_pass(h, buf, n, nblocks, 8 + d, true));
   }
-  // source-centric kernels: `fill` unordered candidates in buffer `buf`
-  uint64_t fill_all = 0;
+  *out_buf = buf;
+  return NLP_OK;
+}
+
+// Top-K of the w-centric LHub paths, one GPU or several.  The kept pairs lie in ascending (u, v)
+// order in record-aligned arrays (pair_pu / pair_pv / score bits): exact radix select on the score
+// (Select11; with a communicator the histograms are all-reduced, so every rank finds the GLOBAL
+// cutoff), in-order compaction of exactly the survivors (better than the K-th score, plus the first
+// `need` of its tie class in (u, v) order), [one all-gather,] stable sort by score.  Replaces the
+// per-thread heaps and the serial T-way merge of inc/predict.hxx:313-336, 431-460.
+int ordered_top_k(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
+  const uint32_t* pu = h->pair_pu;
+  const uint32_t* pv = h->pair_pv;
+  const uint64_t n = h->pair_n;
+  const int sbuf = h->pair_score_buf, ob = sbuf ^ 1;
+  const bool external = h->pair_ps != nullptr;       // bucket path: records and scores in the aligned arrays
+  const uint32_t* sbits = external ? h->pair_ps : (const uint32_t*)h->cs[sbuf].p;
+  const bool dist = distributed(h);
+  NcclApi* api = dist ? nccl_api() : nullptr;
+  Select11* st = (Select11*)h->sel11.p;
+  const bool l0 = h->sel11_l0;
+  h->sel11_l0 = false;
+  *out_buf = external ? 0 : ob; *out_n = 0;
+  if (!dist && (!n || !h->pair_kept)) return NLP_OK;
+  const unsigned gsel = grid_for(n, 256 * 8, h->num_sms * 8);
+  if (!l0) NLP_CUDA(h, cudaMemsetAsync(st, 0, sizeof(Select11), h->stream));
+  for (int lvl = 0; lvl < 3; ++lvl) {
+    if (n && !(lvl == 0 && l0)) {
+      k_sel11_hist<<<gsel, 256, 0, h->stream>>>(sbits, n, st);
+      NLP_LAUNCHED(h);
+    }
+    if (api) NLP_NCCL(h, api->AllReduce(st->hist, st->hist, 2048, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->stream));
+    k_sel11_step<<<1, 256, 0, h->stream>>>(st, (unsigned long long)K);
+    NLP_LAUNCHED(h);
+  }
+  const uint32_t ntiles = (uint32_t)((n + OC_TILE - 1) / OC_TILE);
+  if (n) {
+    NLP_TRY(ensure(h, h->oc_counts, (size_t)ntiles * 8));
+    NLP_TRY(ensure(h, h->oc_off, (size_t)ntiles * 8));
+    k_ordered_count2<<<ntiles, OC_THREADS, 0, h->stream>>>(sbits, n, st, (unsigned long long*)h->oc_counts.p);
+    NLP_LAUNCHED(h);
+  }
+  if (api) NLP_NCCL(h, api->AllReduce(&st->dhist[0][0], &st->dhist[0][0], 1024, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(h->h_sel11, st, sizeof(Select11), cudaMemcpyDeviceToHost, h->stream));
+  uint64_t packed = 0;
+  if (n) NLP_TRY(exclusive_scan<unsigned long long>(h, (const unsigned long long*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &packed));
+  else NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  const uint64_t better = packed >> 32, tie = packed & 0xffffffffull;
+  const uint64_t need = h->h_sel11->need;
+  uint64_t need_r = std::min(need, tie), sup = better + tie;     // sup: entries the digit histograms were taken over
+  if (dist) {
+    // (better, tie) of every rank: ranks with ascending source ranges take the tie class in rank order
+    const int W = h->world;
+    NLP_TRY(ensure(h, h->gcnt, (size_t)(2 * W + 2) * 8));
+    unsigned long long* d_cnt = (unsigned long long*)h->gcnt.p;
+    unsigned long long mine[2] = {better, tie};
+    NLP_CUDA(h, cudaMemcpyAsync(d_cnt + 2 * W, mine, 16, cudaMemcpyHostToDevice, h->stream));
+    NLP_NCCL(h, api->AllGather(d_cnt + 2 * W, d_cnt, 2, ncclUint64, (ncclComm_t)h->comm, h->stream));
+    std::vector<unsigned long long> all(2 * W);
+    NLP_CUDA(h, cudaMemcpyAsync(all.data(), d_cnt, (size_t)W * 16, cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    uint64_t tie_before = 0;
+    sup = 0;
+    for (int r = 0; r < W; ++r) { if (r < h->rank) tie_before += all[2 * r + 1]; sup += all[2 * r] + all[2 * r + 1]; }
+    if (h->part_ordered) need_r = need > tie_before ? std::min<uint64_t>(need - tie_before, tie) : 0;
+  }
+  const uint64_t m = better + need_r;
+  // Survivors go to buffer `ob`.  When the records live in candidate buffer `ob` themselves (no
+  // cache), its u/v arrays are still being read: write to (cu[sbuf], cv[sbuf], cs[ob]) instead and
+  // swap the two score arrays afterwards, which makes that triple buffer `sbuf`.  External records
+  // (bucket path): survivors simply go to buffer 0.
+  int res = ob;
+  if (n) {
+    uint32_t *ou = (uint32_t*)h->cu[ob].p, *ov = (uint32_t*)h->cv[ob].p, *os = (uint32_t*)h->cs[ob].p;
+    if (external) { res = 0; ou = (uint32_t*)h->cu[0].p; ov = (uint32_t*)h->cv[0].p; os = (uint32_t*)h->cs[0].p; }
+    else if (!h->pair_from_cache) { ou = (uint32_t*)h->cu[sbuf].p; ov = (uint32_t*)h->cv[sbuf].p; res = sbuf; }
+    k_ordered_write2<<<ntiles, OC_THREADS, 0, h->stream>>>(pu, pv, sbits, n, st, (unsigned long long)need_r,
+                                                           (const unsigned long long*)h->oc_off.p, ou, ov, os);
+    NLP_LAUNCHED(h);
+    if (!external && !h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
+  } else if (external) res = 0;
+  unsigned constant = 0;
+  for (int d = 0; d < 4; ++d)
+    for (int b = 0; b < 256; ++b)
+      if (sup && h->h_sel11->dhist[d][b] == sup) { constant |= 1u << d; break; }
+  uint64_t total = m;
+  if (dist) {
+    NLP_TRY(gather_candidates(h, res, m, &total));
+    res = 0;
+    if (!h->part_ordered) return top_k(h, 0, total, K, out_buf, out_n);
+  }
+  NLP_TRY(radix_sort_score(h, res, total, constant, out_buf));
+  *out_n = std::min(total, K);
+  return NLP_OK;
+}
+
+// The merge of a multi-GPU prediction on the source-centric kernels (replaces the serial T-way heap
+// merge of inc/predict.hxx:431-460): `fill` unordered candidates in buffer `buf`; global cutoff by
+// all-reduced select histograms on the 96-bit key, local compaction of the survivors, one
+// all-gather, final on-device select + sort.  Every rank ends with the same result.
+int dist_top_k(nlp_handle* h, int buf, uint64_t fill, uint64_t K, int* out_buf, uint64_t* out_n) {
+  uint64_t m = fill, total = 0, fill_all = 0;
+  int lb = buf;
   NLP_TRY(global_count(h, fill, &fill_all));
-  lb = buf;
-  m = fill;
   if (K < fill_all) NLP_TRY(select_narrow(h, (const uint32_t*)h->cu[buf].p, (const uint32_t*)h->cv[buf].p, (const uint32_t*)h->cs[buf].p, fill, K, 96u, true));
   if (K < fill_all && fill) {
     const int o = buf ^ 1;
@@ -1492,10 +1577,14 @@ int nlp_create(nlp_handle** out, int device) {
   if ((e = cudaMallocHost((void**)&h->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_hist, 12 * 256 * 8)) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_sel, sizeof(SelectState))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost((void**)&h->h_sel11, sizeof(Select11))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   int rc = NLP_OK;
   if ((rc = ensure(h, h->ctr, sizeof(Counters), true)) || (rc = ensure(h, h->thr, sizeof(Threshold), true)) ||
       (rc = ensure(h, h->totals, 256 * 4)) || (rc = ensure(h, h->hist, 12 * 256 * 8)) ||
-      (rc = ensure(h, h->sel, sizeof(SelectState), true)) || (rc = ensure(h, h->cursor2, 16, true))) {
+      (rc = ensure(h, h->sel, sizeof(SelectState), true)) || (rc = ensure(h, h->cursor2, 16, true)) ||
+      (rc = ensure(h, h->sel11, sizeof(Select11), true))) {
     g_create_error = h->err;
     delete h;
     return rc;
@@ -1539,6 +1628,13 @@ int nlp_destroy(nlp_handle* h) {
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->h_hist) cudaFreeHost(h->h_hist);
   if (h->h_sel) cudaFreeHost(h->h_sel);
+  if (h->h_sel11) cudaFreeHost(h->h_sel11);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  release(h->sel11);
+  for (auto& b : h->arena_pool) release(b);
+  h->arena_pool.clear();
   for (int i = 0; i < 7; ++i) cudaEventDestroy(h->ev_phase[i]);
   cudaEventDestroy(h->ev_start); cudaEventDestroy(h->ev_frontier); cudaEventDestroy(h->ev_scored); cudaEventDestroy(h->ev_done);
   cudaStreamDestroy(h->stream);
@@ -1680,9 +1776,9 @@ int nlp_predict(nlp_handle* h, const nlp_options* opt, nlp_result* res) {
   }
   int ob = buf;
   uint64_t on = 0;
-  if (distributed(h))       NLP_TRY(dist_top_k(h, buf, fill, opt->max_edges, &ob, &on));
-  else if (h->pair_pending) NLP_TRY(top_k_ordered(h, opt->max_edges, &ob, &on));
-  else                      NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
+  if (h->pair_pending)     NLP_TRY(ordered_top_k(h, opt->max_edges, &ob, &on));
+  else if (distributed(h)) NLP_TRY(dist_top_k(h, buf, fill, opt->max_edges, &ob, &on));
+  else                     NLP_TRY(top_k(h, buf, fill, opt->max_edges, &ob, &on));
   NLP_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
   NLP_CUDA(h, cudaEventSynchronize(h->ev_done));
   float sel = 0.f;

@@ -410,4 +410,188 @@ __global__ void __launch_bounds__(OC_THREADS) k_ordered_write(const uint32_t* __
   }
 }
 
+
+// ---- ordered top-K, exact (bucket path) --------------------------------------------------------
+// The kept pairs lie in ascending (u, v) order in record-aligned arrays.  The K best are
+//   every pair whose score is better than the K-th score, plus
+//   the first `need` pairs IN ARRAY ORDER of those tied with it (canonical order inside a tie class
+//   is ascending (u, v)),
+// so after an MSD radix select on the 32 score bits (digits of 11 + 11 + 10 bits; the first
+// histogram is accumulated by the scoring kernel itself) an in-order compaction leaves exactly K
+// survivors and a stable sort by score finishes the canonical order.  With several ranks the
+// histograms are all-reduced, so every rank narrows to the same global cutoff.
+struct Select11 {
+  uint32_t prefix;                    // resolved leading bits of desc_key(score), left-aligned
+  uint32_t bits;                      // 0, 11, 22 or 32
+  unsigned long long above;           // pairs strictly better than the undecided bucket
+  unsigned long long bucket;          // pairs in the undecided bucket
+  unsigned long long need;            // valid when done: how many of the bucket belong to the result
+  uint32_t done, pad;
+  unsigned long long hist[2048];
+  unsigned long long dhist[4][256];   // 8-bit digit histograms of the survivors' score keys (final sort: constant digits are skipped)
+};
+
+__device__ __forceinline__ int sel11_width(uint32_t bits) { return bits < 22u ? 11 : 10; }
+
+// 0: not a survivor, 1: better than the bucket, 2: in the bucket
+__device__ __forceinline__ int sel11_class(uint32_t prefix, uint32_t bits, uint32_t sbits) {
+  if (sbits == NLP_NO_SCORE) return 0;
+  if (bits == 0u) return 2;
+  const uint32_t k = desc_key(sbits) >> (32u - bits), p = prefix >> (32u - bits);
+  return k < p ? 1 : (k == p ? 2 : 0);
+}
+
+// Level histogram of the undecided bucket (skipped once the select is done).
+__global__ void __launch_bounds__(256) k_sel11_hist(const uint32_t* __restrict__ sbits, uint64_t n, Select11* st) {
+  __shared__ uint32_t sh[2048];
+  if (st->done) return;
+  for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
+  __syncthreads();
+  const uint32_t bits = st->bits, prefix = st->prefix;
+  const int width = sel11_width(bits);
+  const uint32_t shift = 32u - bits - (uint32_t)width, mask = (1u << width) - 1u;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t s = sbits[i];
+    if (sel11_class(prefix, bits, s) == 2) atomicAdd(&sh[(desc_key(s) >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 256)
+    if (sh[i]) atomicAdd(&st->hist[i], (unsigned long long)sh[i]);
+}
+
+// One block of 256 threads: the bin that holds the K-th pair, extend the prefix.  Done when all 32
+// bits are resolved (the bucket is an exact tie class: need = K - above of it) or when the whole
+// bucket belongs to the result anyway (above + bucket <= K).
+__global__ void __launch_bounds__(256) k_sel11_step(Select11* st, unsigned long long K) {
+  __shared__ unsigned long long s_part[256];
+  __shared__ int s_bin;
+  __shared__ unsigned long long s_before;
+  if (st->done) return;
+  const uint32_t bits = st->bits;
+  const int width = sel11_width(bits), nb = 1 << width, tid = threadIdx.x;
+  const int per = nb / 256;
+  unsigned long long loc[8], sum = 0;
+  for (int k = 0; k < per; ++k) { loc[k] = st->hist[tid * per + k]; sum += loc[k]; }
+  s_part[tid] = sum;
+  if (tid == 0) { s_bin = -1; s_before = 0; }
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {               // inclusive scan
+    const unsigned long long t = tid >= d ? s_part[tid - d] : 0ull;
+    __syncthreads();
+    s_part[tid] += t;
+    __syncthreads();
+  }
+  const unsigned long long above0 = st->above;
+  unsigned long long before = above0 + s_part[tid] - sum;    // pairs before this thread's bins
+  if (before < K && before + sum >= K) {             // exactly one thread (if any)
+    for (int k = 0; k < per; ++k) {
+      if (before + loc[k] >= K) { s_bin = tid * per + k; s_before = before; break; }
+      before += loc[k];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int bin = s_bin;
+    unsigned long long bef = s_before;
+    if (bin < 0) {                                    // fewer than K pairs in all: everything survives
+      bin = nb - 1;
+      bef = above0 + s_part[255] - st->hist[nb - 1];
+    }
+    const unsigned long long bucket = st->hist[bin];
+    st->prefix |= (uint32_t)bin << (32u - bits - (uint32_t)width);
+    st->above = bef;
+    st->bucket = bucket;
+    st->bits = bits + (uint32_t)width;
+    if (bef + bucket <= K) { st->done = 1; st->need = bucket; }
+    else if (bits + (uint32_t)width >= 32u) { st->done = 1; st->need = K - bef; }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2048; i += 256) st->hist[i] = 0;
+}
+
+// Per tile: survivors better than the bucket (high word) and in the bucket (low word), and the
+// 8-bit digit histograms of their keys.
+__global__ void __launch_bounds__(OC_THREADS) k_ordered_count2(const uint32_t* __restrict__ sbits, uint64_t n, Select11* st,
+                                                               unsigned long long* __restrict__ tile_counts) {
+  __shared__ unsigned long long s_warp[OC_THREADS / 32];
+  __shared__ uint32_t s_d[4][256];
+  for (int i = threadIdx.x; i < 1024; i += OC_THREADS) (&s_d[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t prefix = st->prefix, bits = st->bits;
+  const uint64_t base = (uint64_t)blockIdx.x * OC_TILE + (uint64_t)threadIdx.x * OC_PER_THREAD;
+  unsigned long long c = 0;
+  #pragma unroll
+  for (int k = 0; k < OC_PER_THREAD; ++k) {
+    if (base + k < n) {
+      const uint32_t s = sbits[base + k];
+      const int cls = sel11_class(prefix, bits, s);
+      if (cls) {
+        c += cls == 1 ? (1ull << 32) : 1ull;
+        const uint32_t key = desc_key(s);
+        atomicAdd(&s_d[0][key & 255u], 1u); atomicAdd(&s_d[1][(key >> 8) & 255u], 1u);
+        atomicAdd(&s_d[2][(key >> 16) & 255u], 1u); atomicAdd(&s_d[3][key >> 24], 1u);
+      }
+    }
+  }
+  #pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(NLP_FULL, c, d);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    #pragma unroll
+    for (int w = 0; w < OC_THREADS / 32; ++w) t += s_warp[w];
+    tile_counts[blockIdx.x] = t;
+  }
+  for (int i = threadIdx.x; i < 1024; i += OC_THREADS) {
+    const uint32_t x = (&s_d[0][0])[i];
+    if (x) atomicAdd(&st->dhist[0][0] + i, (unsigned long long)x);
+  }
+}
+
+// Survivors in array order: every better pair, and the bucket pairs whose index inside the bucket
+// (over the whole array, `tie_base` more on this rank's left) is below `need`.
+__global__ void __launch_bounds__(OC_THREADS) k_ordered_write2(const uint32_t* __restrict__ pu, const uint32_t* __restrict__ pv,
+                                                               const uint32_t* __restrict__ sbits, uint64_t n,
+                                                               const Select11* __restrict__ st, unsigned long long need,
+                                                               const unsigned long long* __restrict__ tile_off,
+                                                               uint32_t* __restrict__ ou, uint32_t* __restrict__ ov,
+                                                               uint32_t* __restrict__ os) {
+  __shared__ unsigned long long s_warp[OC_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t prefix = st->prefix, bits = st->bits;
+  const uint64_t base = (uint64_t)blockIdx.x * OC_TILE + (uint64_t)threadIdx.x * OC_PER_THREAD;
+  uint32_t sb[OC_PER_THREAD];
+  int cls[OC_PER_THREAD];
+  unsigned long long c = 0;
+  #pragma unroll
+  for (int k = 0; k < OC_PER_THREAD; ++k) {
+    sb[k] = base + k < n ? sbits[base + k] : NLP_NO_SCORE;
+    cls[k] = sel11_class(prefix, bits, sb[k]);
+    c += cls[k] == 1 ? (1ull << 32) : (cls[k] == 2 ? 1ull : 0ull);
+  }
+  unsigned long long inc = c;
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(NLP_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned long long before = 0;
+  #pragma unroll
+  for (int w = 0; w < OC_THREADS / 32; ++w) before += w < warp ? s_warp[w] : 0ull;
+  const unsigned long long at = tile_off[blockIdx.x] + before + inc - c;
+  unsigned long long nbetter = at >> 32, ntie = at & 0xffffffffull;
+  #pragma unroll
+  for (int k = 0; k < OC_PER_THREAD; ++k) {
+    if (cls[k] == 1 || (cls[k] == 2 && ntie < need)) {
+      const unsigned long long pos = nbetter + (ntie < need ? ntie : need);
+      ou[pos] = pu[base + k]; ov[pos] = pv[base + k]; os[pos] = sb[k];
+    }
+    nbetter += cls[k] == 1 ? 1ull : 0ull;
+    ntie += cls[k] == 2 ? 1ull : 0ull;
+  }
+}
+
 }  // namespace nlp
