@@ -44,8 +44,10 @@ WORKLOADS = {
     # BASELINE configs[2..4]: parity/scale cases, run with --workload (not the default bench line)
     "road24m": dict(kind="road", side=4900, keep=0.6, seed=44, frac=0.1,
                     desc="road/mesh-shaped 4900x4900 lattice, edges kept with p=0.6 (~24M vertices, avg degree ~2.4), 0.1|E| removed (configs[2])"),
-    "web50m": dict(kind="web", n=50_000_000, avg_out=19, seed=45, frac=0.1,
-                   desc="web-crawl-shaped, 50M vertices, power-law out-degree, host locality (configs[3], sk-2005 scale)"),
+    "web50m": dict(kind="web", n=50_000_000, avg_out=85, seed=45, frac=0.1,
+                   desc="web-crawl-shaped, 50M vertices, 3.0e9 generated links (~2.2e9 undirected edges, > 2^32 directed entries), "
+                        "power-law out-degree, host locality (BASELINE configs[3], sk-2005 scale)"),
+    "web50m_r1": dict(kind="web", n=50_000_000, avg_out=19, seed=45, frac=0.1, desc="round 1's under-sized configs[3] stand-in (1.0e9 directed entries)"),
     "web25m": dict(kind="web", n=25_000_000, avg_out=19, seed=45, frac=0.1, desc="web-crawl-shaped, 25M vertices (configs[3] at half scale)"),
     "web6m": dict(kind="web", n=6_250_000, avg_out=19, seed=45, frac=0.1, desc="web-crawl-shaped, 6.25M vertices (configs[3] at 1/8 scale)"),
     "rmat24": dict(kind="rmat", scale=24, ef=16, seed=46, frac=0.01, desc="R-MAT scale-24, 1e-2|E| removed (configs[4]; use --degree 0)"),
@@ -90,23 +92,29 @@ def build_workload(name, device, batch=0, pred=None):
     S = int(off.numel() - 1)
     batch_size = int(w["frac"] * int(keys.numel()) / 2)            # size_t(d * x.size() / 2), main.cxx:166
     seed = REMOVAL_SEED + batch
+    base = (off, keys)
     if pred is not None:
+        # on the device: draw (nlp_generate_deletions), apply (nlp_apply_deletions), copy the rebuilt CSR out
         pred.set_graph_pointers(off.data_ptr(), keys.data_ptr(), S, device=True, keep=(off, keys))
         n, _ = pred.generate_deletions(seed, batch_size, fetch=False)
         du = torch.empty(n, dtype=torch.int32, device=device); dv = torch.empty(n, dtype=torch.int32, device=device)
         if n:
             pred.fetch_deletions_into(du.data_ptr(), dv.data_ptr(), n)
+        pred.apply_deletions(pointers=(du.data_ptr(), dv.data_ptr(), n))
+        S2, M2 = pred.graph_size()
+        off = torch.empty(S2 + 1, dtype=torch.int64, device=device); keys = torch.empty(M2, dtype=torch.int32, device=device)
+        pred._check(pred.lib.nlp_fetch_graph(pred.h, off.data_ptr(), keys.data_ptr() if M2 else None))
     else:
         from oracle import oracle_py as O
         offn, keysn = N.graphs.to_numpy(off, keys)
         u, v, _ = O.oracle_edge_deletions(offn, keysn, seed, batch_size)
         du = torch.from_numpy(u.astype(np.int32)).to(device); dv = torch.from_numpy(v.astype(np.int32)).to(device)
         del offn, keysn
-    base = (off, keys)
-    off, keys = N.graphs.apply_deletions(off, keys, du, dv)
+        off, keys = N.graphs.apply_deletions(off, keys, du, dv)
     K = int(du.numel()) // 2
     if device != "cpu":
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()        # the library allocates with cudaMalloc: hand torch's cached blocks back
     info = {"workload": name, "description": w["desc"], "span": S, "entries": int(keys.numel()),
             "predict_count_K": K, "removal": "reference sampler (inc/batch.hxx:99-112), default_random_engine(%d)" % seed}
     BASE_GRAPH["graph"] = base

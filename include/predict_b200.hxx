@@ -33,6 +33,7 @@
 #include <tuple>
 #include <type_traits>
 #include <utility>
+#include <array>
 #include <vector>
 
 #include "nlp_b200.h"
@@ -73,7 +74,7 @@ struct Session {
   const void* resident = nullptr;   // DeviceGraph currently bound to the handle
   std::vector<uint64_t> offsets;    // staging for pack()
   std::vector<uint32_t> keys;
-  uint64_t fingerprint = 0;
+  std::array<uint64_t, 4> fingerprint{};   // {hash, second independent hash, span, entries}
   bool     have_fingerprint = false;
   bool     fetch_edges = true;      // setFetchEdges(false): results stay on the GPU (evaluateLastPrediction)
   static Session& get() { static Session s; return s; }
@@ -97,25 +98,32 @@ inline uint64_t mix(uint64_t a, uint64_t x) {
   return a * 0xBF58476D1CE4E5B9ull;
 }
 
-// G -> CSR (64-bit offsets, 32-bit keys), with a content fingerprint.
+inline uint64_t mix2(uint64_t a, uint64_t x) {
+  a = (a ^ x) * 0x100000001B3ull;
+  return a ^ (a >> 29);
+}
+
+// G -> CSR (64-bit offsets, 32-bit keys), with a content fingerprint: two independent 64-bit
+// hashes plus span and entry count (a graph is only taken for the resident one when all four agree).
+// Rows must be sorted ascending, as update() leaves them (_bitset.hxx:20); the library checks it.
 template <class G>
-inline uint64_t pack(const G& x, std::vector<uint64_t>& off, std::vector<uint32_t>& keys) {
+inline std::array<uint64_t, 4> pack(const G& x, std::vector<uint64_t>& off, std::vector<uint32_t>& keys) {
   const size_t S = x.span();
   off.assign(S + 1, 0);
   for (size_t u = 0; u < S; ++u)
     off[u + 1] = off[u] + (x.hasVertex(u) ? (uint64_t)x.degree(u) : 0);
   keys.resize(off[S]);
-  std::vector<uint64_t> rowhash(S, 0);
+  std::vector<uint64_t> rowhash(S, 0), rowhash2(S, 0);
   #pragma omp parallel for schedule(dynamic, 2048)
   for (size_t u = 0; u < S; ++u) {
     if (!x.hasVertex(u)) continue;
-    uint64_t i = off[u], hsh = off[u + 1];
-    x.forEachEdgeKey(u, [&](auto v) { keys[i++] = (uint32_t)v; hsh = mix(hsh, (uint64_t)v); });
-    rowhash[u] = hsh;
+    uint64_t i = off[u], hsh = off[u + 1], hs2 = 0xCBF29CE484222325ull ^ u;
+    x.forEachEdgeKey(u, [&](auto v) { keys[i++] = (uint32_t)v; hsh = mix(hsh, (uint64_t)v); hs2 = mix2(hs2, (uint64_t)v + 1); });
+    rowhash[u] = hsh; rowhash2[u] = hs2;
   }
-  uint64_t f = mix(S, off[S]);
-  for (size_t u = 0; u < S; ++u) f = mix(f, rowhash[u]);
-  return f;
+  uint64_t f = mix(S, off[S]), f2 = 0x9AE16A3B2F90404Full;
+  for (size_t u = 0; u < S; ++u) { f = mix(f, rowhash[u]); f2 = mix2(f2, rowhash2[u]); }
+  return {f, f2, (uint64_t)S, off[S]};
 }
 
 }  // namespace detail
@@ -141,6 +149,7 @@ class DeviceGraph {
   }
   ~DeviceGraph() {
     detail::Session& s = detail::Session::get();
+    std::lock_guard<std::mutex> lock(s.mu);
     if (s.resident == this) s.resident = nullptr;
   }
   DeviceGraph(const DeviceGraph&) = delete;
@@ -170,7 +179,7 @@ inline PredictLinkResult<K, W> predictLinksB200(const G& x, int measure, unsigne
   } else {
     // content-addressed: the same graph handed over again (main.cxx runs 99 predictions per
     // batch on one graph) is packed and compared, but not uploaded again
-    const uint64_t f = detail::pack(x, s.offsets, s.keys);
+    const auto f = detail::pack(x, s.offsets, s.keys);
     if (!(s.have_fingerprint && s.fingerprint == f && s.resident == nullptr)) {
       detail::check(h, nlp_set_graph(h, s.offsets.data(), s.keys.data(), (uint32_t)(s.offsets.size() - 1)), "nlp_set_graph");
       s.fingerprint = f; s.have_fingerprint = true; s.resident = nullptr;
@@ -248,7 +257,7 @@ inline auto generateEdgeDeletionsB200(const G& x, uint32_t seed, size_t batchSiz
   if constexpr (std::is_same<G, DeviceGraph>::value) {
     if (s.resident != &x) throw std::runtime_error("nlp_b200: this DeviceGraph is no longer resident (another graph was uploaded since)");
   } else {
-    const uint64_t f = detail::pack(x, s.offsets, s.keys);
+    const auto f = detail::pack(x, s.offsets, s.keys);
     if (!(s.have_fingerprint && s.fingerprint == f && s.resident == nullptr)) {
       detail::check(h, nlp_set_graph(h, s.offsets.data(), s.keys.data(), (uint32_t)(s.offsets.size() - 1)), "nlp_set_graph");
       s.fingerprint = f; s.have_fingerprint = true; s.resident = nullptr;

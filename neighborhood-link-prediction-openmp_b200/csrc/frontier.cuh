@@ -17,12 +17,16 @@
 
 namespace nlp {
 
+// maxdeg[0] = largest degree; maxdeg[1] |= 1 when the offsets are not non-decreasing or a row is
+// longer than 2^32 - 1 entries (validation of the caller's CSR, see k_validate_entries)
 __global__ void __launch_bounds__(256) k_degrees(const uint64_t* __restrict__ off, uint32_t S,
                                                  uint32_t* __restrict__ deg, unsigned long long* __restrict__ nchunks,
                                                  uint32_t* maxdeg) {
   uint32_t local = 0;
   for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < S; u += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t d = (uint32_t)(off[u + 1] - off[u]);
+    const uint64_t a = off[u], b = off[u + 1];
+    if (b < a || b - a > 0xffffffffull) atomicOr(maxdeg + 1, 1u);
+    const uint32_t d = b < a ? 0u : (uint32_t)(b - a);
     deg[u] = d;
     nchunks[u] = d > LONG_ROW ? (d + CHUNK - 1) / CHUNK : 0u;
     local = max(local, d);
@@ -48,6 +52,47 @@ __global__ void __launch_bounds__(256) k_chunk_fill(const uint32_t* __restrict__
 // entries are adjacent).  The reference counts ENTRIES, so with multiset rows a pair's count can
 // reach deg(u) times this number -- k_range's half-word counters need the bound.  One warp per 32
 // consecutive entries; the row of the first by bisection, the lanes walk forward from there.
+// Validation of the caller's CSR (include/nlp_b200.h promises NLP_ERR_ARG): every key below span
+// (flag 2), every row non-decreasing (flag 4) -- the kernels index deg[], the eligibility mask and
+// the counters with unchecked keys and bisect rows, so a bad input must not get past
+// nlp_set_graph -- and, in the same pass, the largest entry multiplicity (out[1]).
+__global__ void __launch_bounds__(256) k_validate_entries(DevGraph g, uint64_t M, unsigned int* __restrict__ flags,
+                                                          unsigned int* __restrict__ maxmult) {
+  const uint32_t* __restrict__ keys = g.keys;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t best = 1, bad = 0;
+  for (uint64_t base = warp0 * 32u; base < M; base += nwarps * 32u) {
+    uint32_t lo = 0, hi = g.S;                       // off[lo] <= base < off[hi]
+    while (lo + 1 < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldg(g.off + mid) <= base) lo = mid; else hi = mid;
+    }
+    const uint64_t e = base + lane;
+    if (e >= M) continue;
+    uint32_t u = lo;
+    while (u + 1 < g.S && __ldg(g.off + u + 1) <= e) ++u;
+    const uint64_t ub = __ldg(g.off + u), ue = __ldg(g.off + u + 1);
+    const uint32_t w = __ldg(keys + e);
+    if (w >= g.S) bad |= 2u;
+    if (e > ub) {
+      const uint32_t prev = __ldg(keys + e - 1);
+      if (prev > w) bad |= 4u;
+      if (prev == w) continue;                                   // multiplicity measured at the first entry of the run
+    }
+    uint32_t mult = 1;
+    while (e + mult < ue && __ldg(keys + e + mult) == w) ++mult;
+    best = mult > best ? mult : best;
+  }
+  best = __reduce_max_sync(NLP_FULL, best);
+  bad = __reduce_or_sync(NLP_FULL, bad);
+  if (lane == 0) {
+    if (best > 1u) atomicMax(maxmult, best);
+    if (bad) atomicOr(flags, bad);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_max_multiplicity(DevGraph g, uint64_t M, unsigned int* __restrict__ out) {
   const uint32_t* __restrict__ keys = g.keys;
   const int lane = threadIdx.x & 31;
@@ -264,16 +309,15 @@ __global__ void __launch_bounds__(256) k_work_long(DevGraph g, const uint32_t* _
 
 struct BinLists { uint32_t* list[NBINS]; };
 
-// flt: the float measures send every source above the 1K-slot hash bin to the sort-based path
-// range_c: counters per window of k_range (0 = that path is off); room = S-1-u
-__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, bool flt, uint32_t range_c, uint32_t range_div,
+// range_c: counters per window of k_range (0 = that path is off, e.g. for the float measures,
+// whose hub-heavy sources go to the dense spill tables); room = S-1-u
+__device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, uint32_t range_c, uint32_t range_div,
                                           uint32_t half_deg, uint32_t room) {
   if (du <= LONG_ROW) {
     if (work <= 8u) return 0;
     if (work <= 32u) return 1;
   }
   if (bound <= bin_limit(2)) return 2;
-  if (flt) return 3;
   if (bound <= bin_limit(3)) return 3;
   if (bound <= bin_limit(4)) return 4;
   if (range_c) {
@@ -289,7 +333,7 @@ __device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_
 }
 
 __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long long* __restrict__ work64, int rank, int world,
-                                             bool flt, uint32_t range_c, uint32_t range_div, uint32_t half_deg, uint32_t* __restrict__ work, BinLists bl,
+                                             uint32_t range_c, uint32_t range_div, uint32_t half_deg, uint32_t* __restrict__ work, BinLists bl,
                                              Counters* ctr) {
   __shared__ unsigned long long s_cnt[NBINS], s_sum[NBINS], s_base[NBINS], s_max;
   const int lane = threadIdx.x & 31;
@@ -311,7 +355,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) { bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, half_deg, room); need = bin < 2 ? w : bound; }
+        if (bound) { bin = choose_bin(w, bound, g.deg[u], range_c, range_div, half_deg, room); need = bin < 2 ? w : bound; }
       }
     }
     #pragma unroll
@@ -351,7 +395,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) bin = choose_bin(w, bound, g.deg[u], flt, range_c, range_div, half_deg, room);
+        if (bound) bin = choose_bin(w, bound, g.deg[u], range_c, range_div, half_deg, room);
       }
     }
     #pragma unroll

@@ -166,6 +166,7 @@ namespace {
     cudaError_t e__ = (expr);                                                                  \
     if (e__ != cudaSuccess) {                                                                  \
       (h)->err = std::string(#expr) + " (nlp_b200.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e__); \
+      cudaGetLastError();   /* a failed cudaMalloc must not resurface at the next launch check */ \
       return NLP_ERR_CUDA;                                                                     \
     }                                                                                          \
   } while (0)
@@ -334,13 +335,28 @@ int finish_graph(nlp_handle* h) {
       NLP_LAUNCHED(h);
     }
   }
-  uint32_t md = 0;
-  NLP_CUDA(h, cudaMemcpyAsync(&md, h->maxdeg_dev.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  // validate the entries (keys below span, rows sorted) and measure the largest entry
+  // multiplicity in the same pass; the offsets were checked by k_degrees -- a CSR whose offsets are
+  // not monotone must not be walked at all
+  uint32_t info[4] = {0, 0, 0, 0};                  // {max degree, validation flags, max multiplicity, -}
+  NLP_CUDA(h, cudaMemcpyAsync(info, h->maxdeg_dev.p, 16, cudaMemcpyDeviceToHost, h->stream));
   NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (info[1] & 1u) return fail(h, NLP_ERR_ARG, "graph: offsets are not non-decreasing");
   h->M = m;
+  if (m && S) {
+    DevGraph g = dev_graph(h);
+    k_validate_entries<<<grid_for(m, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, m, (unsigned int*)h->maxdeg_dev.p + 1,
+                                                                                   (unsigned int*)h->maxdeg_dev.p + 2);
+    NLP_LAUNCHED(h);
+    NLP_CUDA(h, cudaMemcpyAsync(info, h->maxdeg_dev.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (info[1] & 2u) return fail(h, NLP_ERR_ARG, "graph: a key is not below span");
+    if (info[1] & 4u) return fail(h, NLP_ERR_ARG, "graph: a row is not sorted ascending");
+  }
+  const uint32_t md = info[0];
   h->maxdeg = md;
   h->gtable_n = 0;
-  h->maxmult = 0;
+  h->maxmult = info[2] > 1u ? info[2] : 1u;
   h->sym_state = 0;
   h->pair_sizes.clear();
   clear_pair_cache(h);
@@ -471,15 +487,31 @@ int top_k(nlp_handle* h, int buf, uint64_t n, uint64_t K, int* out_buf, uint64_t
   return NLP_OK;
 }
 
-int ensure_candidates(nlp_handle* h, uint64_t cap) {
+// Grow the six candidate arrays together or not at all: the new arrays are allocated first, the old
+// ones are freed only once all six exist, so a failed allocation leaves the handle as it was
+// (cand_cap still describes real buffers).  *ok = false reports an out-of-memory condition to
+// callers that can fall back to another path; with ok == nullptr it is an error.
+int ensure_candidates(nlp_handle* h, uint64_t cap, bool* ok = nullptr) {
+  if (ok) *ok = true;
   if (cap < 1024) cap = 1024;
   if (cap <= h->cand_cap) return NLP_OK;
   // padded to whole sort tiles: k_scatter reads full tiles with TMA bulk copies
   const uint64_t padded = (cap + SORT_TILE - 1) / SORT_TILE * SORT_TILE + SORT_TILE;
-  for (int b = 0; b < 2; ++b) {
-    NLP_TRY(ensure(h, h->cu[b], padded * 4));
-    NLP_TRY(ensure(h, h->cv[b], padded * 4));
-    NLP_TRY(ensure(h, h->cs[b], padded * 4));
+  void* fresh[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 6; ++i) {
+    const cudaError_t e = cudaMalloc(&fresh[i], padded * 4);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int k = 0; k < i; ++k) cudaFree(fresh[k]);
+      if (ok) { *ok = false; return NLP_OK; }
+      h->err = std::string("candidate buffers (") + std::to_string(padded * 24) + " bytes): " + cudaGetErrorString(e);
+      return NLP_ERR_CUDA;
+    }
+  }
+  DevBuf* bufs[6] = {&h->cu[0], &h->cv[0], &h->cs[0], &h->cu[1], &h->cv[1], &h->cs[1]};
+  for (int i = 0; i < 6; ++i) {
+    if (bufs[i]->p) cudaFree(bufs[i]->p);
+    bufs[i]->p = fresh[i]; bufs[i]->cap = padded * 4;
   }
   h->cand_cap = cap;
   h->has_result = false;
@@ -572,9 +604,13 @@ int scratch_budget(nlp_handle* h, uint64_t* out) {
 int measure_budget(nlp_handle* h) {
   size_t free_b = 0, total_b = 0;
   NLP_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
-  uint64_t budget = (uint64_t)free_b + h->tables.cap + h->touched.cap;
+  // what is free now, plus what the handle already holds of exactly the buffers the plans below
+  // are checked against (candidate arrays, aligned output, plan arenas).  Scratch that a path keeps
+  // for itself (eligible lists, spill tables, item descriptors) is NOT headroom: it stays allocated.
+  uint64_t budget = (uint64_t)free_b;
   for (int b = 0; b < 2; ++b) budget += h->cu[b].cap + h->cv[b].cap + h->cs[b].cap;
-  budget += h->it_u.cap + h->it_cnt.cap + h->it_dw.cap + h->it_ptr.cap + h->it_off.cap + h->ecount.cap + h->ekeys.cap;
+  budget += h->al_u.cap + h->al_v.cap + h->al_s.cap + h->al_c.cap + h->plan_tmp.cap;
+  for (const auto& a : h->arena_pool) budget += a.cap;
   h->budget_base = budget / 10 * 8;
   return NLP_OK;
 }
@@ -788,7 +824,11 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   const uint64_t padded = (P + OC_TILE) / OC_TILE * OC_TILE + 1024;
   if (!try_ensure(h, h->al_u, padded * 4) || !try_ensure(h, h->al_v, padded * 4) || !try_ensure(h, h->al_s, padded * 4) ||
       !try_ensure(h, h->al_c, padded * 4)) return NLP_OK;
-  NLP_TRY(ensure_candidates(h, P));
+  {
+    bool ok = true;
+    NLP_TRY(ensure_candidates(h, P, &ok));
+    if (!ok) return NLP_OK;
+  }
   Counters* hc = h->h_ctr;
   NLP_CUDA(h, cudaMemsetAsync(h->ctr.p, 0, sizeof(Counters), h->stream));
   NLP_CUDA(h, cudaMemsetAsync(h->thr.p, 0, sizeof(Threshold), h->stream));
@@ -939,11 +979,9 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   NLP_TRY(scratch_budget(h, &budget));
   if (E) {
     if (E * 28 > budget / 2) return NLP_OK;
-    NLP_TRY(ensure(h, h->it_u, E * 4));
-    NLP_TRY(ensure(h, h->it_cnt, E * 4));
-    NLP_TRY(ensure(h, h->it_dw, E * 4));
-    NLP_TRY(ensure(h, h->it_ptr, E * 8));
-    NLP_TRY(ensure(h, h->it_off, E * 8));
+    // out of memory here is not an error: the source-centric kernels take over (*used stays false)
+    if (!try_ensure(h, h->it_u, E * 4) || !try_ensure(h, h->it_cnt, E * 4) || !try_ensure(h, h->it_dw, E * 4) ||
+        !try_ensure(h, h->it_ptr, E * 8) || !try_ensure(h, h->it_off, E * 8)) return NLP_OK;
     it.u = (uint32_t*)h->it_u.p; it.cnt = (uint32_t*)h->it_cnt.p; it.dw = (uint32_t*)h->it_dw.p;
     it.ptr = (unsigned long long*)h->it_ptr.p;
     k_pair_items<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(
@@ -955,8 +993,14 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
   NLP_TRY(scratch_budget(h, &budget));
-  if (P >= 0xfffffff0ull || (P + 1024) * 24 > budget) return NLP_OK;
-  NLP_TRY(ensure_candidates(h, P));
+  // items (28 B each), the six candidate arrays, the sort's tile counts, the reuse store: one budget
+  const uint64_t pair_need = E * 28 + (P + 2 * (uint64_t)SORT_TILE) * 24 + P / 4 + (h->reuse ? h->cache_bytes + P * 12 : 0);
+  if (P >= 0xfffffff0ull || pair_need > budget) return NLP_OK;
+  {
+    bool ok = true;
+    NLP_TRY(ensure_candidates(h, P, &ok));
+    if (!ok) return NLP_OK;
+  }
   p.cap = h->cand_cap;
   // with reuse on, the records always carry deg(w) so that they serve the float measures too
   const bool payload = FLT || h->reuse;
@@ -1105,7 +1149,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   uint32_t half_deg = 0;
   NLP_TRY(half_word_limit(h, range_c != 0u, &half_deg));
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
-                                                                  false, range_c, h->range_div, half_deg, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
+                                                                  range_c, h->range_div, half_deg, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -1669,7 +1713,9 @@ int nlp_set_graph_device(nlp_handle* h, const uint64_t* d_offsets, const uint32_
   h->d_off = d_offsets;
   h->d_keys = d_keys;
   h->S = span;
-  return finish_graph(h);
+  const int rc = finish_graph(h);
+  if (rc == NLP_OK && h->M && !d_keys) { h->has_graph = false; return fail(h, NLP_ERR_ARG, "nlp_set_graph_device: null keys"); }
+  return rc;
 }
 
 int nlp_set_partition(nlp_handle* h, int rank, int world) {

@@ -69,6 +69,48 @@ def csr_from_pairs(a, b, n):
     return offsets, keys
 
 
+def csr_from_undirected_keys(und, n, chunk=1 << 27):
+    """Sorted unique undirected keys lo * (n + 1) + hi (lo < hi)  ->  the same CSR csr_from_pairs
+    builds, without ever sorting the 2|E| directed entries: row u = its lower neighbours (found
+    by ONE more sort, by (hi, lo)) followed by its upper neighbours (already in order), written
+    to their final positions chunk by chunk.  For graphs of billions of entries (BASELINE
+    configs[3]), where csr_from_pairs' temporaries do not fit."""
+    dev = und.device
+    E = und.numel()
+    n1 = n + 1
+    nup = torch.zeros(n1, dtype=torch.int64, device=dev)     # upper neighbours per vertex (as lo)
+    nlow = torch.zeros(n1, dtype=torch.int64, device=dev)    # lower neighbours per vertex (as hi)
+    key2 = torch.empty(E, dtype=torch.int64, device=dev)
+    for s0 in range(0, E, chunk):
+        c = und[s0:s0 + chunk]
+        lo, hi = c // n1, c % n1
+        nup += torch.bincount(lo, minlength=n1)
+        nlow += torch.bincount(hi, minlength=n1)
+        key2[s0:s0 + chunk] = hi * n1 + lo
+        del lo, hi
+    deg = nup + nlow
+    offsets = torch.zeros(n1 + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=offsets[1:])
+    up_off = torch.cumsum(nup, 0) - nup                        # first index of vertex u's group in und
+    low_off = torch.cumsum(nlow, 0) - nlow                     # ... in key2 sorted
+    keys = torch.empty(2 * E, dtype=torch.int32, device=dev)
+    for s0 in range(0, E, chunk):                              # upper neighbours: und is sorted by (lo, hi)
+        c = und[s0:s0 + chunk]
+        lo, hi = c // n1, c % n1
+        i = torch.arange(s0, s0 + c.numel(), device=dev, dtype=torch.int64)
+        keys[offsets[lo] + nlow[lo] + i - up_off[lo]] = hi.to(torch.int32)
+        del lo, hi, i
+    del und
+    key2 = torch.unique(key2)                                  # already unique: this is the sort by (hi, lo)
+    for s0 in range(0, E, chunk):
+        c = key2[s0:s0 + chunk]
+        hi, lo = c // n1, c % n1
+        j = torch.arange(s0, s0 + c.numel(), device=dev, dtype=torch.int64)
+        keys[offsets[hi] + j - low_off[hi]] = lo.to(torch.int32)
+        del lo, hi, j
+    return offsets, keys
+
+
 def undirected_pairs(offsets, keys):
     """(lo, hi) with lo < hi, one row per undirected edge of a symmetric CSR."""
     S = offsets.numel() - 1
@@ -147,7 +189,8 @@ def web_crawl(n, avg_out=19, alpha=2.1, window=10000, local=0.9, max_out=None, s
     cs = torch.cumsum(out, 0)
     m = int(cs[-1])
     starts = cs - out
-    us, vs = [], []
+    n1 = n + 1
+    und = torch.empty(m, dtype=torch.int64, device=device)         # undirected keys lo * (n + 1) + hi, 0 = self-loop
     for s0 in range(0, m, chunk):
         cnt = min(chunk, m - s0)
         e = torch.arange(s0, s0 + cnt, device=device, dtype=torch.int64)
@@ -158,9 +201,15 @@ def web_crawl(n, avg_out=19, alpha=2.1, window=10000, local=0.9, max_out=None, s
         pop = torch.floor(n * r2 ** 4.0).to(torch.int64)             # popular targets: low "rank"
         pop = (pop * 0x9E3779B1 + 12345) % n                          # scatter the hubs over ids
         dst = torch.where(r1 < local, near, pop)
-        us.append(src); vs.append(dst)
-    del starts
-    return csr_from_pairs(torch.cat(us) + 1, torch.cat(vs) + 1, n)
+        a, b = src + 1, dst + 1
+        key = torch.minimum(a, b) * n1 + torch.maximum(a, b)
+        und[s0:s0 + cnt] = torch.where(a != b, key, torch.zeros_like(key))
+        del e, src, r1, r2, off, near, pop, dst, a, b, key
+    del starts, cs, out
+    und = torch.unique(und)
+    if und.numel() and int(und[0]) == 0:
+        und = und[1:]
+    return csr_from_undirected_keys(und, n)
 
 
 def planted_partition(n, communities, deg_in=12, deg_out=2, seed=47, device="cpu"):

@@ -18,8 +18,8 @@ def main():
     measures = sys.argv[3].split(",") if len(sys.argv) > 3 else ["JC", "AA"]
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
     path = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-    off, keys, K, info = bench.build_workload(wl, "cuda:0")
     pred = N.Predictor(0)
+    off, keys, K, info, _, _ = bench.build_workload(wl, "cuda:0", pred=pred)
     pred.set_graph_pointers(off.data_ptr(), keys.data_ptr(), off.numel() - 1, device=True, keep=(off, keys))
     pred.set_path(path)
     for _ in range(reps):
