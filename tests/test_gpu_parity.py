@@ -364,3 +364,21 @@ def test_lhub_float_long_rows_pruned_buffer(oracle, nlp):
                     assert r["passes"] > 1, r
     finally:
         p.close()
+
+
+def test_bad_graphs_are_rejected(pred, nlp):
+    """nlp_set_graph validates the CSR on the device (include/nlp_b200.h: NLP_ERR_ARG): offsets not
+    non-decreasing, a key not below span, a row not sorted -- the kernels index with the keys and
+    bisect the rows, so such input must not get past nlp_set_graph.  A good graph works afterwards."""
+    off, keys = parity.kat_graph()
+    bad_off = off.copy(); bad_off[4] = off[3] - 1
+    bad_key = keys.copy(); bad_key[5] = 8
+    unsorted = keys.copy(); unsorted[0], unsorted[1] = keys[1], keys[0]
+    for o, k, what in ((bad_off, keys, "offsets"), (off, bad_key, "span"), (off, unsorted, "sorted")):
+        with pytest.raises(nlp.NlpError) as e:
+            pred.set_graph(o, k)
+        assert e.value.code == 1 and what in str(e.value), str(e.value)
+        with pytest.raises(nlp.NlpError):
+            pred.predict("JC", 4)
+    pred.set_graph(off, keys)
+    assert pred.predict("JC", 0, max_edges=3)["count"] == 3
