@@ -40,7 +40,7 @@
 namespace nlp {
 
 enum { BK_THREADS = 256, BK_WARPS = 8, BK_GATHER = 4 };
-constexpr uint32_t BK_CAP_COUNT = 8192;   // records per bucket, count measures (6 B per record x 2 buffers)
+constexpr uint32_t BK_CAP_COUNT = 8192;   // default records per bucket, count measures (6 B per record x 2 buffers); NLP_B200_BUCKET_CAP=4096: three blocks per SM, one plan for all measures
 constexpr uint32_t BK_CAP_FLT = 4096;     // float measures carry deg(w) (10 B per record x 2 buffers)
 constexpr uint32_t BK_NONE = 0xffffffffu;   // aligned count array: no pair starts at this slot
 constexpr uint32_t BK_DONE = 0xfffffffeu;   // ... the slot's score is already final (big sources)
@@ -153,6 +153,7 @@ struct BucketPlanDev {
   const unsigned long long* s_ptr;         // [Es]
   const uint32_t* s_src;                   // [Es] index of the item's source in sm_*
   const unsigned long long* s_loff;        // [Es] first record of the item in the bucket record space
+  const uint32_t* bk_first;                // [nb + 1] first small source of every bucket (window of `half` records)
   uint32_t ns;
   uint32_t half;                           // bucket window = half records; CAP = 2 * half
 };
@@ -210,6 +211,15 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* __
     if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+
+// Plan: first small source of every bucket window (one thread per window; nb + 1 entries).
+__global__ void __launch_bounds__(256) k_plan_buckets(const unsigned long long* __restrict__ sm_soff, uint32_t ns, uint32_t half,
+                                                      uint64_t nb, uint32_t* __restrict__ bk_first) {
+  for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b <= nb; b += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t k = lower_bound_u64(sm_soff, ns + 1u, b * (unsigned long long)half);
+    bk_first[b] = k < ns ? k : ns;
+  }
 }
 
 // Multi-GPU: rank r of `world` owns the buckets [b0, b1) and with them an ascending range of
@@ -299,11 +309,10 @@ __device__ __forceinline__ void bucket_sort_pass(const uint32_t* __restrict__ ki
 }
 
 // One thread block per bucket (window `first_bucket + blockIdx.x` of the bucket record space).
-template <bool FLT>
-__global__ void __launch_bounds__(BK_THREADS, 2)
+template <bool FLT, uint32_t CAP>
+__global__ void __launch_bounds__(BK_THREADS, (CAP * (FLT ? 20u : 12u) + 16384u <= 74000u) ? 3 : 2)
 k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
          uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_c) {
-  constexpr uint32_t CAP = FLT ? BK_CAP_FLT : BK_CAP_COUNT;
   constexpr int MAXR = CAP / BK_THREADS;
   static_assert(BK_WARPS == SORT_WARPS && BK_THREADS == SORT_THREADS, "sort_block_exclusive is shared with select.cuh");
   extern __shared__ __align__(16) uint32_t bsm[];
@@ -321,13 +330,10 @@ k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
   const uint32_t* __restrict__ keys = p.g.keys;
 
   // ---- the bucket: small sources [k0, k1) that start inside the window --------------------------
-  const unsigned long long wlo = (first_bucket + blockIdx.x) * (unsigned long long)pl.half;
-  for (int i = tid; i < BK_WARPS * 256; i += BK_THREADS) { (&s_mask[0][0])[i] = 0; (&s_hist0[0][0])[i] = 0; }
-  if (tid == 0)  s_warp[8] = lower_bound_u64(pl.sm_soff, pl.ns + 1u, wlo);
-  if (tid == 32) s_warp[9] = lower_bound_u64(pl.sm_soff, pl.ns + 1u, wlo + pl.half);
-  __syncthreads();
-  const uint32_t k0 = s_warp[8], k1 = min(s_warp[9], pl.ns);
+  const uint32_t k0 = __ldg(pl.bk_first + first_bucket + blockIdx.x), k1 = __ldg(pl.bk_first + first_bucket + blockIdx.x + 1);
   if (k0 >= k1) return;                                            // block-uniform
+  for (int i = tid; i < BK_WARPS * 256; i += BK_THREADS) { (&s_mask[0][0])[i] = 0; (&s_hist0[0][0])[i] = 0; }
+  __syncthreads();
   const uint32_t i0 = __ldg(pl.sm_item + k0), i1 = __ldg(pl.sm_item + k1);
   const unsigned long long base = __ldg(pl.sm_soff + k0);
   const uint32_t n = (uint32_t)(__ldg(pl.sm_soff + k1) - base);    // <= CAP by construction
@@ -441,14 +447,35 @@ k_bucket(Params p, BucketPlanDev pl, uint64_t first_bucket, int key_passes,
   }
 }
 
+// Is v an entry of the sorted row [ub, ub + du)?  Quaternary search: three probes per round are
+// independent loads, so the dependent chain is log4 instead of log2 of the row length (k_score is
+// bound by exactly this latency chain: ncu, long-scoreboard stall 24.6 per issue).
+__device__ __forceinline__ bool row_contains_k4(const uint32_t* __restrict__ keys, uint64_t ub, uint32_t du, uint32_t v) {
+  uint32_t lo = 0, hi = du;                           // the first entry >= v, if any, lies in [lo, hi)
+  while (hi - lo > 4u) {
+    const uint32_t q = (hi - lo) >> 2;
+    const uint32_t m1 = lo + q, m2 = lo + 2u * q, m3 = lo + 3u * q;
+    const uint32_t k1 = __ldg(keys + ub + m1), k2 = __ldg(keys + ub + m2), k3 = __ldg(keys + ub + m3);
+    if (k2 < v) { if (k3 < v) lo = m3 + 1u; else { lo = m2 + 1u; hi = m3 + 1u; } }
+    else        { if (k1 < v) { lo = m1 + 1u; hi = m2 + 1u; } else hi = m1 + 1u; }
+  }
+  bool found = false;
+  #pragma unroll
+  for (uint32_t i = 0; i < 4u; ++i)
+    if (lo + i < hi) found |= __ldg(keys + ub + lo + i) == v;
+  return found;
+}
+
 // One thread per slot of the aligned arrays: existing-edge exclusion by binary search in row u
 // (inc/predict.hxx:306-307: such pairs keep their candidate slot with value 0), fused scoring
 // (inc/predict.hxx:309-311).  al_c: count (or float accumulator bits) at the first record of a
 // run, BK_NONE where there is no pair, BK_DONE where the score is already in al_s (big sources).
+// exclude = false: the counts already went through the exclusion (reuse store, nlp_set_reuse);
+// capture: write the count after the exclusion back (it is about to be stored).
 template <bool FLT>
 __global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restrict__ al_u, const uint32_t* __restrict__ al_v,
-                                               const uint32_t* __restrict__ al_c, uint32_t* __restrict__ al_s,
-                                               uint64_t lo, uint64_t hi, Select11* sel) {
+                                               uint32_t* al_c, uint32_t* __restrict__ al_s,
+                                               uint64_t lo, uint64_t hi, Select11* sel, bool exclude, bool capture) {
   // first level of the top-K select (select.cuh, Select11): histogram of the top 11 bits of every
   // kept score, accumulated here so that the select does not have to read the scores again
   __shared__ uint32_t s_h[2048];
@@ -468,7 +495,8 @@ __global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restr
       if (FLT) acc = __uint_as_float(c); else cnt = c;
       const uint64_t ub = __ldg(p.g.off + u);
       du = __ldg(p.g.deg + u);
-      if (row_contains(p.g.keys, ub, (uint32_t)du, v)) { cnt = 0; acc = 0.0f; }
+      if (exclude && row_contains_k4(p.g.keys, ub, (uint32_t)du, v)) { cnt = 0; acc = 0.0f; }
+      if (!FLT && capture) al_c[i] = cnt;              // the reuse store keeps the count after the exclusion
     }
     float score;
     const bool keep = score_pair(p, head, u, du, v, cnt, acc, tally, &score);
@@ -487,7 +515,7 @@ __global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restr
 // candidate buffers (record j of the big record space, local index j - first); copy them into
 // their slots of the aligned output.
 __global__ void __launch_bounds__(256) k_big_place(const uint32_t* __restrict__ pu, const uint32_t* __restrict__ pv,
-                                                   const uint32_t* __restrict__ ps, uint64_t n, uint64_t first,
+                                                   const uint32_t* __restrict__ ps, const uint32_t* __restrict__ pc, uint64_t n, uint64_t first,
                                                    const unsigned long long* __restrict__ bg_first,
                                                    const unsigned long long* __restrict__ bg_roff, uint32_t kb0, uint32_t kb1,
                                                    uint32_t* __restrict__ al_u, uint32_t* __restrict__ al_v, uint32_t* __restrict__ al_s,
@@ -502,8 +530,9 @@ __global__ void __launch_bounds__(256) k_big_place(const uint32_t* __restrict__ 
     const unsigned long long slot = __ldg(bg_roff + lo) + (pos - __ldg(bg_first + lo));
     const uint32_t s = ps[j];
     al_s[slot] = s;
-    al_c[slot] = BK_DONE;
-    if (s != NLP_NO_SCORE) { al_u[slot] = pu[j]; al_v[slot] = pv[j]; }
+    const uint32_t c = pc ? pc[j] : BK_DONE;           // with the counts (reuse store) k_score scores the slot again
+    al_c[slot] = c;
+    if (s != NLP_NO_SCORE || (pc && c != BK_NONE)) { al_u[slot] = pu[j]; al_v[slot] = pv[j]; }
   }
 }
 

@@ -70,6 +70,7 @@ struct nlp_handle {
   int coop_mode = 1;                         // 0: per-warp wedge streaming in k_hash / k_dense (count measures)
   int range_half = 1;                        // k_range: half-word counters for sources with deg < 2^15 (NLP_B200_RANGE_HALF=0: off)
   uint32_t range_div = 4;                    // weight of the per-row window cost in the k_range / k_dense rule (frontier.cuh)
+  uint32_t bucket_cap = BK_CAP_COUNT;        // records per bucket of the count measures (NLP_B200_BUCKET_CAP = 4096 | 8192)
   int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
@@ -119,6 +120,11 @@ struct nlp_handle {
     bool usable = false;                     // false: too large for the scratch budget (source path instead)
   };
   std::map<uint64_t, BucketPlan> plans;
+  // nlp_set_reuse on the bucket path: the distinct pairs of a threshold with their counts AFTER the
+  // exclusion (12 B per record slot of this rank), shared by the seven count measures
+  struct CountStore { DevBuf arena; const uint32_t* u = nullptr; const uint32_t* v = nullptr; const uint32_t* c = nullptr;
+                      uint64_t n = 0, candidates = 0, stamp = 0; };
+  std::map<uint64_t, CountStore> count_store;
   uint64_t plan_bytes = 0;
   DevBuf plan_tmp;                           // scratch of a plan build (kept: no allocation churn)
   DevBuf al_u, al_v, al_s, al_c;             // record-aligned output of the bucket path (pair, score bits, count)
@@ -297,7 +303,13 @@ bool take_arena(nlp_handle* h, DevBuf& a, size_t bytes) {
   return true;
 }
 
+void clear_count_store(nlp_handle* h) {
+  for (auto& kv : h->count_store) { h->plan_bytes -= std::min<uint64_t>(h->plan_bytes, kv.second.arena.cap); retire_arena(h, kv.second.arena); }
+  h->count_store.clear();
+}
+
 void clear_plans(nlp_handle* h) {
+  clear_count_store(h);
   for (auto& kv : h->plans) retire_arena(h, kv.second.arena);
   h->plans.clear();
   h->plan_bytes = 0;
@@ -729,6 +741,7 @@ int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan&
   plan.Es = Es; plan.Ps = Ps; plan.ns = ns; plan.nbig = nbig; plan.Eb = Eb; plan.Pb = Pb;
   // the plan itself, one allocation
   PlanScatterOut o;
+  uint32_t* bk_first = nullptr;
   auto carve_plan = [&](Carver& c) {
     o.sm_u = c.take<uint32_t>(ns); o.sm_item = c.take<uint32_t>(ns + 1);
     o.sm_soff = c.take<unsigned long long>(ns + 1); o.sm_roff = c.take<unsigned long long>(ns);
@@ -738,6 +751,7 @@ int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan&
     o.b_ptr = c.take<unsigned long long>(Eb); o.b_off = c.take<unsigned long long>(Eb);
     o.bg_first = c.take<unsigned long long>(nbig + 1); o.bg_roff = c.take<unsigned long long>(nbig);
     o.bg_item = c.take<uint32_t>(nbig + 1);
+    bk_first = c.take<uint32_t>((Ps + half - 1) / half + 2);
   };
   size_t bytes = 0;
   { Carver c(nullptr); carve_plan(c); bytes = c.off + 256; }
@@ -758,6 +772,12 @@ int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan&
   k_plan_scatter<<<gE, 256, 0, h->stream>>>(su, sidx, it_dw, it_ptr, g_cnt, head, hs, rc, f_item, si, sr, ks,
                                             E, Es, Ps, ns, nbig, P, o);
   NLP_LAUNCHED(h);
+  {
+    const uint64_t nb = (Ps + half - 1) / half;
+    k_plan_buckets<<<grid_for(nb + 1, 256, h->num_sms * 8), 256, 0, h->stream>>>(o.sm_soff, (uint32_t)ns, half, nb, bk_first);
+    NLP_LAUNCHED(h);
+  }
+  plan.dev.bk_first = bk_first;
   plan.dev.sm_u = o.sm_u; plan.dev.sm_item = o.sm_item; plan.dev.sm_soff = o.sm_soff; plan.dev.sm_roff = o.sm_roff;
   plan.dev.s_cnt = o.s_cnt; plan.dev.s_dw = o.s_dw; plan.dev.s_ptr = o.s_ptr; plan.dev.s_src = o.s_src; plan.dev.s_loff = o.s_loff;
   plan.dev.ns = (uint32_t)ns; plan.dev.half = half;
@@ -776,7 +796,7 @@ int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan&
 // their slots of the aligned output.  Launches on h->stream.
 template <bool FLT>
 int big_detour(nlp_handle* h, const nlp_handle::BucketPlan& plan, const Params& p, uint64_t kb0, uint64_t kb1,
-               uint32_t* al_u, uint32_t* al_v, uint32_t* al_s, uint32_t* al_c) {
+               uint32_t* al_u, uint32_t* al_v, uint32_t* al_s, uint32_t* al_c, bool capture) {
   const uint64_t ib0 = plan.h_bg_item[kb0], ib1 = plan.h_bg_item[kb1];
   const uint64_t r0 = plan.h_bg_first[kb0], r1 = plan.h_bg_first[kb1];
   const uint64_t Eb = ib1 - ib0, Pb = r1 - r0;
@@ -788,11 +808,13 @@ int big_detour(nlp_handle* h, const nlp_handle::BucketPlan& plan, const Params& 
   NLP_LAUNCHED(h);
   int sb = 0;
   NLP_TRY(radix_sort_pairs(h, 0, Pb, FLT, &sb));
+  // reuse store (count measures): the counts after the exclusion come along, in the idle payload array
+  uint32_t* pc = (capture && !FLT) ? (uint32_t*)h->cs[sb].p : nullptr;
   k_pair_reduce<FLT><<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-      p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, Pb, (uint32_t*)h->cs[sb ^ 1].p);
+      p, (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb].p, Pb, (uint32_t*)h->cs[sb ^ 1].p, pc);
   NLP_LAUNCHED(h);
   k_big_place<<<grid_for(Pb, 256, h->num_sms * 16), 256, 0, h->stream>>>(
-      (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb ^ 1].p, Pb, r0,
+      (const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, (const uint32_t*)h->cs[sb ^ 1].p, pc, Pb, r0,
       plan.bg_first, plan.bg_roff, (uint32_t)kb0, (uint32_t)kb1, al_u, al_v, al_s, al_c);
   NLP_LAUNCHED(h);
   return NLP_OK;
@@ -805,7 +827,8 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   *used = false;
   NLP_TRY(check_symmetry(h));
   if (h->sym_state != 1) return NLP_OK;
-  const uint32_t half = (FLT ? BK_CAP_FLT : BK_CAP_COUNT) / 2u;
+  const uint32_t cap_rec = FLT ? BK_CAP_FLT : h->bucket_cap;
+  const uint32_t half = cap_rec / 2u;
   const uint64_t key = ((uint64_t)opt->min_degree1 << 16) | half;
   auto it = h->plans.find(key);
   if (it == h->plans.end()) {
@@ -862,6 +885,38 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
     }
     kb0 = plan.part_kb0; kb1 = plan.part_kb1; slo = plan.part_slo; shi = plan.part_shi;
   }
+  // reuse store (nlp_set_reuse, count measures): the pairs of this threshold with their counts are
+  // resident -> score them and go straight to the select
+  const uint64_t skey = ((uint64_t)opt->min_degree1 << 24) | (rank << 12) | world;
+  const bool capture = !FLT && h->reuse != 0;
+  if (capture) {
+    auto hit = h->count_store.find(skey);
+    if (hit != h->count_store.end() && hit->second.n == shi - slo) {
+      nlp_handle::CountStore& cs = hit->second;
+      cs.stamp = ++h->cache_stamp;
+      NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
+      for (int i = 0; i < 3; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
+      NLP_CUDA(h, cudaMemsetAsync(h->sel11.p, 0, sizeof(Select11), h->stream));
+      if (cs.n) {
+        k_score<false><<<grid_for(cs.n, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+            p, cs.u, cs.v, const_cast<uint32_t*>(cs.c), al_s, 0, cs.n, (Select11*)h->sel11.p, false, false);
+        NLP_LAUNCHED(h);
+      }
+      h->sel11_l0 = true;
+      for (int i = 3; i < 7; ++i) NLP_CUDA(h, cudaEventRecord(h->ev_phase[i], h->stream));
+      h->phases_valid = true;
+      NLP_TRY(read_counters(h));
+      res->first_hop = plan.first_hop; res->eligible_first_hop = plan.elig; res->wedges = plan.wedges;
+      res->candidates = hc->candidates; res->kept = hc->kept; res->emitted = hc->kept;
+      res->passes = 1; res->path = NLP_PATH_PAIR; res->pair_records = P;
+      res->bin_sources[0] = plan.ns; res->bin_sources[1] = plan.nbig; res->bin_sources[7] = 1;   // [7]: served from the reuse store
+      h->pair_pending = true; h->pair_from_cache = true; h->pair_n = cs.n; h->pair_kept = hc->kept;
+      h->pair_pu = cs.u; h->pair_pv = cs.v; h->pair_ps = al_s; h->pair_score_buf = 0;
+      h->part_ordered = true;
+      *out_buf = 0; *out_fill = hc->kept; *used = true;
+      return NLP_OK;
+    }
+  }
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
   // big sources: global sort of their records (pairs.cuh), then into their slots -- issued on a
@@ -871,7 +926,7 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
     NLP_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     NLP_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     std::swap(h->stream, h->stream2);              // the helpers launch on h->stream
-    int rc = big_detour<FLT>(h, plan, p, kb0, kb1, al_u, al_v, al_s, al_c);
+    int rc = big_detour<FLT>(h, plan, p, kb0, kb1, al_u, al_v, al_s, al_c, capture);
     if (rc == NLP_OK && cudaEventRecord(h->ev_join, h->stream) != cudaSuccess) rc = fail(h, NLP_ERR_CUDA, "cudaEventRecord(ev_join)");
     std::swap(h->stream, h->stream2);
     NLP_TRY(rc);
@@ -881,8 +936,8 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
     const uint32_t top = h->S ? h->S - 1 : 0;
     int key_passes = 0;
     while (key_passes < 4 && (top >> (8 * key_passes)) != 0) ++key_passes;
-    auto kern = k_bucket<FLT>;
-    const uint32_t smem = bucket_smem_bytes(FLT, FLT ? BK_CAP_FLT : BK_CAP_COUNT);
+    auto kern = cap_rec == 4096u ? k_bucket<FLT, 4096u> : k_bucket<FLT, 8192u>;
+    const uint32_t smem = bucket_smem_bytes(FLT, cap_rec);
     NLP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (uint64_t s0 = b0; s0 < b1; s0 += 0x7fffffffull) {          // grid.x limit
       const unsigned grid = (unsigned)std::min<uint64_t>(b1 - s0, 0x7fffffffull);
@@ -897,7 +952,7 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   // histogram of the top-K select (Select11)
   NLP_CUDA(h, cudaMemsetAsync(h->sel11.p, 0, sizeof(Select11), h->stream));
   if (shi > slo) {
-    k_score<FLT><<<grid_for(shi - slo, 256, h->num_sms * 16), 256, 0, h->stream>>>(p, al_u, al_v, al_c, al_s, slo, shi, (Select11*)h->sel11.p);
+    k_score<FLT><<<grid_for(shi - slo, 256, h->num_sms * 16), 256, 0, h->stream>>>(p, al_u, al_v, al_c, al_s, slo, shi, (Select11*)h->sel11.p, true, capture);
     NLP_LAUNCHED(h);
   }
   h->sel11_l0 = true;
@@ -905,6 +960,31 @@ int bucket_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out
   h->phases_valid = true;
   NLP_TRY(read_counters(h));
   if (hc->overflow) return fail(h, NLP_ERR_CAPACITY, "internal: bucket overflow (inconsistent plan)");
+  if (capture && shi > slo) {
+    // keep (u, v, count after the exclusion) of this rank's slots for the other count measures at
+    // this threshold; least recently used thresholds go first, the arenas are pooled
+    const uint64_t n = shi - slo, bytes = n * 12 + 1024;
+    const uint64_t limit = budget / 4;
+    while (h->plan_bytes + bytes > limit && !h->count_store.empty()) {
+      auto lru = h->count_store.begin();
+      for (auto i = h->count_store.begin(); i != h->count_store.end(); ++i) if (i->second.stamp < lru->second.stamp) lru = i;
+      h->plan_bytes -= std::min<uint64_t>(h->plan_bytes, lru->second.arena.cap);
+      retire_arena(h, lru->second.arena);
+      h->count_store.erase(lru);
+    }
+    nlp_handle::CountStore cs;
+    if (h->plan_bytes + bytes <= limit && take_arena(h, cs.arena, bytes)) {
+      uint32_t* a = (uint32_t*)cs.arena.p;
+      NLP_CUDA(h, cudaMemcpyAsync(a, al_u + slo, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+      NLP_CUDA(h, cudaMemcpyAsync(a + n, al_v + slo, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+      NLP_CUDA(h, cudaMemcpyAsync(a + 2 * n, al_c + slo, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+      cs.u = a; cs.v = a + n; cs.c = a + 2 * n; cs.n = n; cs.candidates = hc->candidates; cs.stamp = ++h->cache_stamp;
+      h->plan_bytes += cs.arena.cap;
+      auto old = h->count_store.find(skey);
+      if (old != h->count_store.end()) { h->plan_bytes -= std::min<uint64_t>(h->plan_bytes, old->second.arena.cap); retire_arena(h, old->second.arena); h->count_store.erase(old); }
+      h->count_store[skey] = cs;
+    }
+  }
   res->first_hop = plan.first_hop; res->eligible_first_hop = plan.elig; res->wedges = plan.wedges;
   res->candidates = hc->candidates; res->kept = hc->kept; res->emitted = hc->kept;
   res->passes = 1; res->path = NLP_PATH_PAIR; res->pair_records = P;
@@ -1097,8 +1177,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
 
   if (lhub && h->path_mode != NLP_PATH_SOURCE) {
     bool used = false;
-    // reuse across measures still lives on the sorted-record store of the global-sort path
-    if (h->path_mode == NLP_PATH_PAIR_SORT || h->reuse) NLP_TRY(pair_pass<FLT>(h, opt, res, out_buf, out_fill, &used));
+    if (h->path_mode == NLP_PATH_PAIR_SORT) NLP_TRY(pair_pass<FLT>(h, opt, res, out_buf, out_fill, &used));
     else NLP_TRY(bucket_pass<FLT>(h, opt, res, out_buf, out_fill, &used));
     if (used) return NLP_OK;
   }
@@ -1595,6 +1674,7 @@ int nlp_create(nlp_handle** out, int device) {
   if (const char* e = getenv("NLP_B200_RANGE_HALF")) h->range_half = atoi(e);
   if (const char* e = getenv("NLP_B200_RANGE_DIV")) h->range_div = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
+  if (const char* e = getenv("NLP_B200_BUCKET_CAP")) h->bucket_cap = atoi(e) == 4096 ? 4096u : 8192u;
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string("nlp_create: ") + what + ": " + cudaGetErrorString(err);
     delete h;
@@ -1722,6 +1802,7 @@ int nlp_set_partition(nlp_handle* h, int rank, int world) {
   if (!h) return NLP_ERR_ARG;
   if (world < 1 || rank < 0 || rank >= world) return fail(h, NLP_ERR_ARG, "nlp_set_partition: need 0 <= rank < world");
   if (h->comm && (rank != h->rank || world != h->world)) return fail(h, NLP_ERR_ARG, "nlp_set_partition: a communicator is active (nlp_comm_destroy first)");
+  if (rank != h->rank || world != h->world) clear_count_store(h);
   h->rank = rank; h->world = world;
   return NLP_OK;
 }
@@ -1771,8 +1852,8 @@ uint64_t nlp_comm_bytes(const nlp_handle* h) { return h ? h->gathered_bytes : 0;
 int nlp_set_reuse(nlp_handle* h, int on) {
   if (!h) return NLP_ERR_ARG;
   NLP_CUDA(h, cudaSetDevice(h->device));
-  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
-  clear_pair_cache(h);
+  if (!h->pair_cache.empty()) { NLP_CUDA(h, cudaStreamSynchronize(h->stream)); clear_pair_cache(h); }
+  clear_count_store(h);        // arenas go back to the pool: no cudaFree / cudaMalloc in steady state (stream-ordered reuse)
   h->reuse = on ? 1 : 0;
   return NLP_OK;
 }

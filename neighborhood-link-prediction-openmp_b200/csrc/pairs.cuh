@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(256) k_pair_emit(const uint32_t* __restrict__ 
 // to sort by score.
 template <bool FLT>
 __global__ void __launch_bounds__(256) k_pair_reduce(Params p, const uint32_t* __restrict__ pu, const uint32_t* __restrict__ pv,
-                                                     const uint32_t* __restrict__ pw, uint64_t n, uint32_t* __restrict__ score_bits) {
+                                                     const uint32_t* pw, uint64_t n, uint32_t* __restrict__ score_bits,
+                                                     uint32_t* cnt_out = nullptr) {
   Tally tally;
   const uint64_t n32 = (n + 31u) & ~31ull;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n32; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -231,7 +232,12 @@ __global__ void __launch_bounds__(256) k_pair_reduce(Params p, const uint32_t* _
     }
     float score;
     const bool keep = score_pair(p, head, u, du, v, cnt, acc, tally, &score);
-    if (i < n) score_bits[i] = keep ? __float_as_uint(score) : NLP_NO_SCORE;
+    if (i < n) {
+      score_bits[i] = keep ? __float_as_uint(score) : NLP_NO_SCORE;
+      // count measures, on request: the count after the exclusion, aligned like the scores
+      // (0xffffffff = no pair starts here); may alias pw, which the count measures do not read
+      if (!FLT && cnt_out) cnt_out[i] = head ? cnt : 0xffffffffu;
+    }
   }
   tally.flush(p.ctr);
 }

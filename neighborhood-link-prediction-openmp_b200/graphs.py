@@ -69,6 +69,37 @@ def csr_from_pairs(a, b, n):
     return offsets, keys
 
 
+_CUB_LIMIT = (1 << 31) - 1024
+
+
+def sorted_unique(x, limit=_CUB_LIMIT):
+    """torch.unique(x) for 1-D int64 tensors of ANY length: torch's CUDA sort refuses more than
+    2^31 - 1 elements, so longer inputs are split into value ranges (splitters = quantiles of a
+    sample), each range is made unique on its own and the pieces are concatenated in range order."""
+    n = x.numel()
+    if n <= limit:
+        return torch.unique(x)
+    parts = 2 * ((n + limit - 1) // limit) + 2
+    step = max(1, n // (1 << 20))
+    sample, _ = torch.sort(x[::step])
+    cut = [int(sample[(i * sample.numel()) // parts]) for i in range(1, parts)]
+    cut = sorted(set(cut) | set(c + 1 for c in cut))            # a heavily repeated value gets a range of its own
+    bounds = [None] + cut + [None]
+    out = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        m = torch.ones(n, dtype=torch.bool, device=x.device) if lo is None else x >= lo
+        if hi is not None:
+            m &= x < hi
+        piece = x[m]
+        del m
+        if piece.numel() > limit and int(piece.min()) == int(piece.max()):
+            out.append(piece[:1].clone())                      # one value, repeated: nothing to split
+        else:
+            out.append(sorted_unique(piece, limit) if piece.numel() > limit else torch.unique(piece))
+        del piece
+    return torch.cat(out)
+
+
 def csr_from_undirected_keys(und, n, chunk=1 << 27):
     """Sorted unique undirected keys lo * (n + 1) + hi (lo < hi)  ->  the same CSR csr_from_pairs
     builds, without ever sorting the 2|E| directed entries: row u = its lower neighbours (found
@@ -101,7 +132,7 @@ def csr_from_undirected_keys(und, n, chunk=1 << 27):
         keys[offsets[lo] + nlow[lo] + i - up_off[lo]] = hi.to(torch.int32)
         del lo, hi, i
     del und
-    key2 = torch.unique(key2)                                  # already unique: this is the sort by (hi, lo)
+    key2 = sorted_unique(key2)                                 # already unique: this is the sort by (hi, lo)
     for s0 in range(0, E, chunk):
         c = key2[s0:s0 + chunk]
         hi, lo = c // n1, c % n1
@@ -206,7 +237,7 @@ def web_crawl(n, avg_out=19, alpha=2.1, window=10000, local=0.9, max_out=None, s
         und[s0:s0 + cnt] = torch.where(a != b, key, torch.zeros_like(key))
         del e, src, r1, r2, off, near, pop, dst, a, b, key
     del starts, cs, out
-    und = torch.unique(und)
+    und = sorted_unique(und)
     if und.numel() and int(und[0]) == 0:
         und = und[1:]
     return csr_from_undirected_keys(und, n)

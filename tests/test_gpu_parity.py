@@ -288,9 +288,10 @@ def test_hub_heavy_sources_windowed_counters(nlp, oracle, monkeypatch, half):
 
 
 def test_reuse_across_measures(pred, oracle, nlp):
-    """nlp_set_reuse: the sorted wedge records of a threshold feed every later measure at that
-    threshold (main.cxx:212-220 order: measure-major, thresholds inside); results stay bit-exact
-    and the later predictions skip emission and sort."""
+    """nlp_set_reuse: the distinct pairs of a threshold with their counts after the exclusion feed
+    every later count measure at that threshold (main.cxx:212-220 order: measure-major, thresholds
+    inside; the seven count measures share their counts); results stay bit-exact and the later
+    predictions skip gather, sort and exclusion.  Adjacent pairs survive with count 0 (min_score < 0)."""
     off, keys = _graph(nlp, "pp4k_symdup")
     pred.set_graph(off, keys)
     K = len(keys) // 10
@@ -301,18 +302,24 @@ def test_reuse_across_measures(pred, oracle, nlp):
             for D in (2, 16):
                 err, r, st = parity.check_case(pred, oracle, off, keys, m, D, K, tag="reuse")
                 assert err is None, err
-                assert r["path"] == PAIR_SORT_PATH      # the record store belongs to the global-sort pair path
-                if D in seen:     # no emission, no sort: only back-to-back event records (a few microseconds)
-                    assert r["phase_ms"][1] < 0.02 and r["phase_ms"][2] < 0.02, r["phase_ms"]
-                elif r["pair_records"] >= 4096:      # D = 2 leaves this graph next to no wedge records
-                    assert r["phase_ms"][2] > 0.005, r["phase_ms"]
-                seen.add(D)
+                assert r["path"] == PAIR_PATH
+                flt = m in ("AA", "RA")
+                if D in seen and not flt:     # served from the store: no bucket kernel, only back-to-back event records
+                    assert r["bin_sources"][7] == 1 and r["phase_ms"][1] < 0.02, (m, D, r["bin_sources"], r["phase_ms"])
+                else:
+                    assert r["bin_sources"][7] == 0
+                if not flt:
+                    seen.add(D)
+        err, r, st = parity.check_case(pred, oracle, off, keys, "SC", 16, K, min_score=-1.0, tag="reuse min_score<0")
+        assert err is None and r["bin_sources"][7] == 1, (err, r["bin_sources"])
         # a new graph empties the store
         off2, keys2 = _graph(nlp, "rmat12")
         pred.set_graph(off2, keys2)
-        err, r, st = parity.check_case(pred, oracle, off2, keys2, "AA", 16, 3000, tag="reuse-newgraph")
+        err, r, st = parity.check_case(pred, oracle, off2, keys2, "JC", 16, 3000, tag="reuse-newgraph")
         assert err is None, err
-        assert r["phase_ms"][2] > 0.02
+        assert r["bin_sources"][7] == 0
+        err, r, st = parity.check_case(pred, oracle, off2, keys2, "HD", 16, 3000, tag="reuse-newgraph")
+        assert err is None and r["bin_sources"][7] == 1
     finally:
         pred.set_reuse(False)
 
