@@ -202,4 +202,32 @@ __global__ void __launch_bounds__(DEL_THREADS) k_del_write(const uint32_t* __res
     if (!((gone >> k) & 1u)) out[pos++] = keys[base + k];
 }
 
+
+// First stored copy of b in the sorted row a; false when b is not stored.
+__device__ __forceinline__ bool del_first_copy(const DevGraph& g, uint32_t a, uint32_t b, uint64_t* e) {
+  const uint64_t ab = __ldg(g.off + a);
+  const uint32_t d = __ldg(g.deg + a);
+  uint32_t lo = 0, hi = d;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(g.keys + ab + mid) < b) lo = mid + 1; else hi = mid;
+  }
+  *e = ab + lo;
+  return lo < d && __ldg(g.keys + ab + lo) == b;
+}
+
+// Does the batch keep symmetric rows symmetric?  For every request (u, v) that removes an entry, the
+// first stored copy of the mirror entry (v, u) must be marked too (then both rows lose one copy of
+// the pair).  Runs after k_del_mark on a graph whose rows ARE symmetric; *asym != 0 afterwards = no.
+__global__ void __launch_bounds__(256) k_del_mirror(DevGraph g, const uint32_t* __restrict__ du, const uint32_t* __restrict__ dv,
+                                                    uint64_t n, const uint32_t* __restrict__ bits, unsigned int* __restrict__ asym) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = du[i], v = dv[i];
+    if (u >= g.S || v >= g.S) continue;
+    uint64_t e1 = 0, e2 = 0;
+    if (!del_first_copy(g, u, v, &e1)) continue;                     // the request removes nothing
+    if (!del_first_copy(g, v, u, &e2) || !((bits[e2 >> 5] >> (e2 & 31u)) & 1u)) atomicOr(asym, 1u);
+  }
+}
+
 }  // namespace nlp

@@ -55,41 +55,65 @@ __global__ void __launch_bounds__(256) k_chunk_fill(const uint32_t* __restrict__
 // Validation of the caller's CSR (include/nlp_b200.h promises NLP_ERR_ARG): every key below span
 // (flag 2), every row non-decreasing (flag 4) -- the kernels index deg[], the eligibility mask and
 // the counters with unchecked keys and bisect rows, so a bad input must not get past
-// nlp_set_graph -- and, in the same pass, the largest entry multiplicity (out[1]).
+// nlp_set_graph -- and, in the same pass, the largest entry multiplicity (out[1]) and a 64-bit
+// content fingerprint (sum over the entries of a hash of (position, row, key)): a graph that is
+// bound again unchanged (the base graph of the next batch) is recognised by it and keeps what is
+// already known about it (symmetric rows or not).
+// A warp takes VAL_CHUNK consecutive entries: ONE bisection of the offsets finds the row of the
+// first, after that the rows are walked forward.
+enum { VAL_CHUNK = 4096 };
+
+__device__ __forceinline__ unsigned long long val_mix(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
 __global__ void __launch_bounds__(256) k_validate_entries(DevGraph g, uint64_t M, unsigned int* __restrict__ flags,
-                                                          unsigned int* __restrict__ maxmult) {
+                                                          unsigned int* __restrict__ maxmult, unsigned long long* __restrict__ fingerprint) {
   const uint32_t* __restrict__ keys = g.keys;
   const int lane = threadIdx.x & 31;
   const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   uint32_t best = 1, bad = 0;
-  for (uint64_t base = warp0 * 32u; base < M; base += nwarps * 32u) {
-    uint32_t lo = 0, hi = g.S;                       // off[lo] <= base < off[hi]
+  unsigned long long fp = 0;
+  for (uint64_t c0 = warp0 * VAL_CHUNK; c0 < M; c0 += nwarps * VAL_CHUNK) {
+    uint32_t lo = 0, hi = g.S;                       // off[lo] <= c0 < off[hi]
     while (lo + 1 < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (__ldg(g.off + mid) <= base) lo = mid; else hi = mid;
+      if (__ldg(g.off + mid) <= c0) lo = mid; else hi = mid;
     }
-    const uint64_t e = base + lane;
-    if (e >= M) continue;
-    uint32_t u = lo;
-    while (u + 1 < g.S && __ldg(g.off + u + 1) <= e) ++u;
-    const uint64_t ub = __ldg(g.off + u), ue = __ldg(g.off + u + 1);
-    const uint32_t w = __ldg(keys + e);
-    if (w >= g.S) bad |= 2u;
-    if (e > ub) {
-      const uint32_t prev = __ldg(keys + e - 1);
-      if (prev > w) bad |= 4u;
-      if (prev == w) continue;                                   // multiplicity measured at the first entry of the run
+    uint32_t urow = lo;                              // row of the batch's first entry (warp-uniform)
+    const uint64_t cend = c0 + VAL_CHUNK < M ? c0 + VAL_CHUNK : M;
+    for (uint64_t base = c0; base < cend; base += 32u) {
+      while (urow + 1 < g.S && __ldg(g.off + urow + 1) <= base) ++urow;
+      const uint64_t e = base + lane;
+      if (e >= cend) continue;
+      uint32_t u = urow;
+      while (u + 1 < g.S && __ldg(g.off + u + 1) <= e) ++u;
+      const uint64_t ub = __ldg(g.off + u), ue = __ldg(g.off + u + 1);
+      const uint32_t w = __ldg(keys + e);
+      fp += val_mix(e * 0x9E3779B97F4A7C15ull + ((unsigned long long)u << 32) + w);
+      if (w >= g.S) bad |= 2u;
+      if (e > ub) {
+        const uint32_t prev = __ldg(keys + e - 1);
+        if (prev > w) bad |= 4u;
+        if (prev == w) continue;                                 // multiplicity measured at the first entry of the run
+      }
+      if (e + 1 < ue && __ldg(keys + e + 1) == w) {
+        uint32_t mult = 2;
+        while (e + mult < ue && __ldg(keys + e + mult) == w) ++mult;
+        best = mult > best ? mult : best;
+      }
     }
-    uint32_t mult = 1;
-    while (e + mult < ue && __ldg(keys + e + mult) == w) ++mult;
-    best = mult > best ? mult : best;
   }
   best = __reduce_max_sync(NLP_FULL, best);
   bad = __reduce_or_sync(NLP_FULL, bad);
+  #pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) fp += __shfl_xor_sync(NLP_FULL, fp, k);
   if (lane == 0) {
     if (best > 1u) atomicMax(maxmult, best);
     if (bad) atomicOr(flags, bad);
+    if (fp) atomicAdd(fingerprint, fp);
   }
 }
 

@@ -63,6 +63,8 @@ struct nlp_handle {
   // pair path (LHub on symmetric graphs)
   DevBuf it_u, it_cnt, it_dw, it_ptr, it_off, sym_flag;
   int sym_state = 0;                         // 0 unknown, 1 symmetric rows, 2 not symmetric
+  unsigned long long graph_id = 0;           // content fingerprint of the resident graph (0 = not taken)
+  std::map<unsigned long long, int> known_sym;   // fingerprint -> sym_state of graphs seen before
   // item / record counts of the pair path per (D, rank, world): a pure function of the resident
   // graph, so only the first prediction at a threshold pays the two host round trips for them
   std::map<uint64_t, std::pair<uint64_t, uint64_t>> pair_sizes;
@@ -315,19 +317,22 @@ void clear_plans(nlp_handle* h) {
   h->plan_bytes = 0;
 }
 
-int finish_graph(nlp_handle* h) {
+// trusted: the CSR was produced by this library from a validated graph (nlp_apply_deletions): no
+// validation pass; `known_sym` (1 symmetric, 2 not, 0 unknown) and the old multiplicity bound carry over.
+int finish_graph(nlp_handle* h, bool trusted = false, int known_sym = 0) {
   const uint32_t S = h->S;
+  const uint32_t old_maxmult = h->maxmult;
   NLP_TRY(ensure(h, h->deg, (size_t)S * 4));
   NLP_TRY(ensure(h, h->work, (size_t)S * 4));
   NLP_TRY(ensure(h, h->work64, (size_t)S * 8));
   NLP_TRY(ensure(h, h->chunk_base, (size_t)S * 8));
   NLP_TRY(ensure(h, h->elig, ((size_t)S + 31) / 32 * 4));
-  NLP_TRY(ensure(h, h->maxdeg_dev, 16));
+  NLP_TRY(ensure(h, h->maxdeg_dev, 32));
   for (int b = 0; b < NBINS; ++b) {
     NLP_TRY(ensure(h, h->list[b], (size_t)S * 4));
     if (b >= 2) NLP_TRY(ensure(h, h->defer[b], (size_t)S * 4));
   }
-  NLP_CUDA(h, cudaMemsetAsync(h->maxdeg_dev.p, 0, 16, h->stream));
+  NLP_CUDA(h, cudaMemsetAsync(h->maxdeg_dev.p, 0, 32, h->stream));
   uint64_t m = 0;
   NLP_CUDA(h, cudaMemcpyAsync(&m, h->d_off + S, 8, cudaMemcpyDeviceToHost, h->stream));
   h->nchunks = 0;
@@ -355,12 +360,15 @@ int finish_graph(nlp_handle* h) {
   NLP_CUDA(h, cudaStreamSynchronize(h->stream));
   if (info[1] & 1u) return fail(h, NLP_ERR_ARG, "graph: offsets are not non-decreasing");
   h->M = m;
-  if (m && S) {
+  unsigned long long fp = 0;
+  if (m && S && !trusted) {
     DevGraph g = dev_graph(h);
     k_validate_entries<<<grid_for(m, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, m, (unsigned int*)h->maxdeg_dev.p + 1,
-                                                                                   (unsigned int*)h->maxdeg_dev.p + 2);
+                                                                                   (unsigned int*)h->maxdeg_dev.p + 2,
+                                                                                   (unsigned long long*)h->maxdeg_dev.p + 2);
     NLP_LAUNCHED(h);
     NLP_CUDA(h, cudaMemcpyAsync(info, h->maxdeg_dev.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(&fp, (const char*)h->maxdeg_dev.p + 16, 8, cudaMemcpyDeviceToHost, h->stream));
     NLP_CUDA(h, cudaStreamSynchronize(h->stream));
     if (info[1] & 2u) return fail(h, NLP_ERR_ARG, "graph: a key is not below span");
     if (info[1] & 4u) return fail(h, NLP_ERR_ARG, "graph: a row is not sorted ascending");
@@ -368,8 +376,15 @@ int finish_graph(nlp_handle* h) {
   const uint32_t md = info[0];
   h->maxdeg = md;
   h->gtable_n = 0;
-  h->maxmult = info[2] > 1u ? info[2] : 1u;
-  h->sym_state = 0;
+  h->maxmult = trusted ? (old_maxmult > 1u ? old_maxmult : 1u) : (info[2] > 1u ? info[2] : 1u);
+  // what is already known about this very graph (same span, entry count and content fingerprint:
+  // the base graph of a batch loop is bound again for every batch)
+  h->graph_id = trusted ? 0ull : (fp ^ ((unsigned long long)S << 40) ^ (m * 0x9E3779B97F4A7C15ull)) | 1ull;
+  h->sym_state = known_sym;
+  if (!trusted) {
+    auto known = h->known_sym.find(h->graph_id);
+    if (known != h->known_sym.end()) h->sym_state = known->second;
+  }
   h->pair_sizes.clear();
   clear_pair_cache(h);
   clear_plans(h);
@@ -644,6 +659,10 @@ int check_symmetry(nlp_handle* h) {
   NLP_CUDA(h, cudaStreamSynchronize(h->stream));
   const bool f = (unsigned int)sf[0] != 0u || sf[1] != sf[2];
   h->sym_state = f ? 2 : 1;
+  if (h->graph_id) {
+    if (h->known_sym.size() >= 64) h->known_sym.clear();
+    h->known_sym[h->graph_id] = h->sym_state;
+  }
   // the check is graph preparation, not part of the prediction: restart the clock
   NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
   return NLP_OK;
@@ -2097,6 +2116,11 @@ int nlp_apply_deletions(nlp_handle* h, const uint32_t* del_u, const uint32_t* de
   const uint32_t S = h->S;
   const uint64_t M = h->M;
   const DevGraph g = dev_graph(h);
+  // Rows symmetric before?  Then a batch that holds both directions of every pair (as
+  // tidyBatchUpdateU leaves it) keeps them symmetric, which k_del_mirror verifies for the price of
+  // two bisections per request instead of a full symmetry pass over the new graph.
+  NLP_TRY(check_symmetry(h));
+  const int base_sym = h->sym_state;
   h->has_result = false;                               // the candidate buffers stage the request list
   NLP_TRY(ensure_candidates(h, n));
   uint32_t* du = (uint32_t*)h->cu[0].p; uint32_t* dv = (uint32_t*)h->cv[0].p;
@@ -2112,6 +2136,15 @@ int nlp_apply_deletions(nlp_handle* h, const uint32_t* del_u, const uint32_t* de
   if (n) {
     k_del_mark<<<grid_for(n, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, du, dv, n, (uint32_t*)h->del_bits.p, marks);
     NLP_LAUNCHED(h);
+  }
+  unsigned int asym = 0;
+  if (n && base_sym == 1) {
+    NLP_TRY(ensure(h, h->sym_flag, 32));
+    NLP_CUDA(h, cudaMemsetAsync(h->sym_flag.p, 0, 4, h->stream));
+    k_del_mirror<<<grid_for(n, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, du, dv, n, (const uint32_t*)h->del_bits.p,
+                                                                            (unsigned int*)h->sym_flag.p);
+    NLP_LAUNCHED(h);
+    NLP_CUDA(h, cudaMemcpyAsync(&asym, h->sym_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));   // read by the synchronize below
   }
   // the new CSR goes to buffers this handle owns; a borrowed graph (nlp_set_graph_device) is left untouched
   const bool cur_is_own = h->d_off == (const uint64_t*)h->own_off.p && h->own_off.p != nullptr;
@@ -2142,7 +2175,8 @@ int nlp_apply_deletions(nlp_handle* h, const uint32_t* del_u, const uint32_t* de
   h->d_off = (const uint64_t*)h->own_off.p;
   h->d_keys = (const uint32_t*)h->own_keys.p;
   h->has_graph = false;
-  return finish_graph(h);
+  // the result of a validated graph is valid by construction; its symmetry follows from the base's
+  return finish_graph(h, true, base_sym == 1 ? (asym ? 0 : 1) : base_sym == 2 ? 0 : 0);
 }
 
 int nlp_graph_size(nlp_handle* h, uint32_t* span, uint64_t* entries) {
