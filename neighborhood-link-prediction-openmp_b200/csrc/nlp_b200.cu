@@ -73,7 +73,8 @@ struct nlp_handle {
   int range_half = 1;                        // k_range: half-word counters for sources with deg < 2^15 (NLP_B200_RANGE_HALF=0: off)
   uint32_t range_div = 4;                    // weight of the per-row window cost in the k_range / k_dense rule (frontier.cuh)
   uint32_t bucket_cap = BK_CAP_COUNT;        // records per bucket of the count measures (NLP_B200_BUCKET_CAP = 4096 | 8192)
-  int range_mode = 1;                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
+  int range_mode = 1;
+  int flt_range_mode = 1;                    // 0: float measures keep the single-warp dense-table path for hub-heavy sources (NLP_B200_RANGE_FLT=0)                        // 0: hub-heavy count sources use k_dense (HBM tables) instead of k_range
   DevBuf list[NBINS], defer[NBINS];
   DevBuf gtable;
   uint32_t gtable_n = 0;
@@ -586,23 +587,33 @@ int launch_dense(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
 // Count measures: hub-heavy sources on windowed shared-memory counters (k_range).
 constexpr uint32_t RANGE_COUNTERS = 52 * 1024;      // 208 KB of u32 counters per block (+13 KB static)
 
-template <bool ADMIT>
+template <bool FLT, bool ADMIT>
 int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t n, uint32_t* deferred) {
   if (!n) return NLP_OK;
-  const size_t smem = (size_t)RANGE_COUNTERS * 4;
-  {
-    NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
-    // per block: row cursor + row end for every first-hop entry of its current source
-    const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
-    NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * 2 * stride * 8));
-    // per block: the vertices of its current window that have a count (at most 2 * RANGE_COUNTERS)
-    NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * 2 * RANGE_COUNTERS * 4));
-    k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS,
-                                                             (unsigned long long*)h->range_cursors.p, stride,
-                                                             (uint32_t*)h->range_touched.p);
+  const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
+  if (FLT) {
+    // one warp per source: per-warp row records (16 B) + deg(w) of every first-hop row
+    const size_t smem = (size_t)RFLT_WARPS * RFLT_WIN * 4;
+    NLP_CUDA(h, cudaFuncSetAttribute(k_range_flt<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n + RFLT_WARPS - 1) / RFLT_WARPS, (uint64_t)h->num_sms);
+    NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * RFLT_WARPS * stride * 16));
+    NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * RFLT_WARPS * stride * 4));
+    k_range_flt<ADMIT><<<grid, RFLT_WARPS * 32, smem, h->stream>>>(p, list, n, 6, deferred, (uint4*)h->range_cursors.p,
+                                                                   (uint32_t*)h->range_touched.p, stride);
     NLP_LAUNCHED(h);
+    return NLP_OK;
   }
+  const size_t smem = (size_t)RANGE_COUNTERS * 4;
+  NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
+  // per block: row cursor + row end for every first-hop entry of its current source
+  NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * 2 * stride * 8));
+  // per block: the vertices of its current window that have a count (at most 2 * RANGE_COUNTERS)
+  NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * 2 * RANGE_COUNTERS * 4));
+  k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS,
+                                                           (unsigned long long*)h->range_cursors.p, stride,
+                                                           (uint32_t*)h->range_touched.p);
+  NLP_LAUNCHED(h);
   return NLP_OK;
 }
 
@@ -1243,11 +1254,21 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   for (int b = 0; b < NBINS; ++b) bl.list[b] = (uint32_t*)h->list[b].p;
   // count measures may send hub-heavy sources to the windowed shared-memory counters (k_range);
   // the float measures need the ordered single-warp accumulation of k_dense
-  const uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS : 0u;
+  // the float measures walk windows too, one WARP per source (k_range_flt: rows one after the other
+  // keep the reference's accumulation order) -- on graphs without repeated entries in a row, and
+  // while the per-warp row records fit
+  uint32_t range_c = (!FLT && h->maxdeg < (1u << 22) && h->range_mode != 0) ? RANGE_COUNTERS : 0u;
+  uint32_t range_fixed = 256, range_div = h->range_div;
+  if (FLT && h->range_mode != 0 && h->flt_range_mode != 0 && h->maxmult <= 1u && h->maxdeg < (1u << 22)) {
+    const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
+    uint64_t budget0 = 0;
+    NLP_TRY(scratch_budget(h, &budget0));
+    if ((uint64_t)h->num_sms * RFLT_WARPS * stride * 20 <= budget0 / 4) { range_c = RFLT_WIN; range_fixed = 32; range_div = 4; }
+  }
   uint32_t half_deg = 0;
-  NLP_TRY(half_word_limit(h, range_c != 0u, &half_deg));
+  NLP_TRY(half_word_limit(h, range_c != 0u && !FLT, &half_deg));
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
-                                                                  range_c, h->range_div, half_deg, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
+                                                                  range_c, range_fixed, range_div, half_deg, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -1318,7 +1339,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   if (!admit) {
     // everything fits: one pass, no admission control, no host round trip until the end
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
-    NLP_TRY((launch_range<false>(h, p, (const uint32_t*)h->list[6].p, (uint32_t)nb[6], nullptr)));
+    NLP_TRY((launch_range<FLT, false>(h, p, (const uint32_t*)h->list[6].p, (uint32_t)nb[6], nullptr)));
     NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
     for (int b = 4; b >= 2; --b) {
@@ -1346,7 +1367,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
       NLP_CUDA(h, cudaMemcpyAsync((char*)h->ctr.p + offsetof(Counters, reserved), &fill, 8, cudaMemcpyHostToDevice, h->stream));
       p.soft_cap = std::min<uint64_t>(cap, fill + pass_quota);
       NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
-      NLP_TRY((launch_range<true>(h, p, lists[6], (uint32_t)remaining[6], defers[6])));
+      NLP_TRY((launch_range<FLT, true>(h, p, lists[6], (uint32_t)remaining[6], defers[6])));
       NLP_TRY((launch_dense<FLT, true>(h, p, lists[5], (uint32_t)remaining[5], defers[5], dense_slots, touched_cap)));
       NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
       for (int b = 4; b >= 2; --b) {
@@ -1692,6 +1713,7 @@ int nlp_create(nlp_handle** out, int device) {
   if (const char* e = getenv("NLP_B200_RANGE")) h->range_mode = atoi(e);   // experiment knobs
   if (const char* e = getenv("NLP_B200_RANGE_HALF")) h->range_half = atoi(e);
   if (const char* e = getenv("NLP_B200_RANGE_DIV")) h->range_div = (uint32_t)std::max(1, atoi(e));
+  if (const char* e = getenv("NLP_B200_RANGE_FLT")) h->flt_range_mode = atoi(e);
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
   if (const char* e = getenv("NLP_B200_BUCKET_CAP")) h->bucket_cap = atoi(e) == 4096 ? 4096u : 8192u;
   auto bail = [&](const char* what, cudaError_t err) {

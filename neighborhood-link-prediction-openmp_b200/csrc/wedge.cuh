@@ -887,4 +887,143 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
   tally.flush(p.ctr);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Range path of the FLOAT measures (Adamic-Adar, resource allocation), hub-heavy sources.
+// The reference accumulates acc(v) = float(double(acc(v)) + g(w)) over the first-hop entries w of u
+// in ascending order (inc/predict.hxx:788, 828), and float addition does not commute, so the
+// block-wide atomic counters of k_range cannot be used.  Here every WARP owns a source and a small
+// window of float accumulators in shared memory (32 warps x 1664 floats = 208 KB per block), and
+// walks the windows lo = u+1, u+1+1664, ...: per window the first-hop rows are visited 32 at a
+// time (lane = row: cursor record, "anything in this window?" from the cached next key, gallop to
+// the window's end), then the rows that have something are taken ONE AFTER THE OTHER in ascending
+// order, the window part of a row spread over the lanes -- the entries of one row are distinct
+// vertices, so the lanes never collide, and the row order is the reference's accumulation order:
+// bit-exact without atomics or sorting.  (Rows that repeat an entry -- multiset rows -- would
+// collide inside a row: such graphs keep the single-warp dense-table path.)
+// A window's accumulator is 0 = untouched, RFLT_ZEROED = touched, then zeroed because v is in N(u)
+// (inc/predict.hxx:306-307), else the sum (> 0: every term is positive).
+constexpr uint32_t RFLT_WIN = 1664;
+constexpr float RFLT_ZEROED = -1.0f;
+enum { RFLT_WARPS = 32 };
+
+template <bool ADMIT>
+__global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
+                                                                  uint32_t* __restrict__ deferred, uint4* __restrict__ rec_all,
+                                                                  uint32_t* __restrict__ dw_all, uint64_t rec_stride) {
+  extern __shared__ float facc[];                     // [RFLT_WARPS][RFLT_WIN]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* acc = facc + (uint32_t)warp * RFLT_WIN;
+  uint4* rec = rec_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * rec_stride;
+  uint32_t* dwrow = dw_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * rec_stride;
+  const uint32_t* __restrict__ keys = p.g.keys;
+  Tally tally;
+  for (uint32_t i = lane; i < RFLT_WIN; i += 32) acc[i] = 0.0f;
+  __syncwarp();
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = (uint32_t)atomicAdd(&p.ctr->queue[bin], 1ull);      // dynamic: sources differ by 1000x in work
+    qi = __shfl_sync(NLP_FULL, qi, 0);
+    if (qi >= n) break;
+    const uint32_t u = __ldg(list + qi);
+    uint32_t need = 0;
+    if (ADMIT) {
+      int go = 0;
+      if (lane == 0) go = admit_source(p, u, bin, deferred, &need) ? 1 : 0;
+      go = __shfl_sync(NLP_FULL, go, 0);
+      need = __shfl_sync(NLP_FULL, need, 0);
+      if (!go) continue;
+    }
+    const uint64_t ub = __ldg(p.g.off + u);
+    const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
+    const FirstHop f = first_hop(p, u, ub, du);
+    uint32_t emitted = 0;
+    for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += RFLT_WIN) {
+      const uint32_t vlo = (uint32_t)lo64;
+      const uint32_t vhi = (uint32_t)(lo64 + RFLT_WIN < p.g.S ? lo64 + RFLT_WIN : p.g.S);
+      const bool first = lo64 == (uint64_t)u + 1;
+      for (uint32_t c = 0; c < f.npieces; ++c) {
+        const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
+        const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
+        for (uint32_t base = 0; base < pc; base += 32) {
+          const uint32_t i = base + lane;
+          const bool has = i < pc;
+          const uint64_t ci = (uint64_t)c * CHUNK + i;
+          unsigned long long a = 0;
+          uint32_t cntw = 0, dw = 0;
+          if (has) {
+            unsigned long long e;
+            uint32_t next;
+            bool moved = false;
+            if (first) {
+              const uint32_t w = __ldg(pb + i);
+              const unsigned long long wb = __ldg(p.g.off + w);
+              e = __ldg(p.g.off + w + 1);
+              dw = (uint32_t)(e - wb);
+              dwrow[ci] = dw;
+              a = wb + lower_bound_row(keys, wb, dw, vlo);
+              next = a < e ? __ldg(keys + a) : 0xffffffffu;
+              moved = true;
+            } else {
+              const uint4 r = rec[ci];
+              a = (unsigned long long)r.x | ((unsigned long long)r.y << 32);
+              e = a + r.z;
+              next = r.w;
+            }
+            unsigned long long b = a;
+            if (next < vhi) {                         // the row has entries in this window (so a < e)
+              b = vhi >= p.g.S ? e : gallop_to<true>(keys, a, e, vhi);
+              next = b < e ? __ldg(keys + b) : 0xffffffffu;
+              moved = true;
+              if (!first) dw = dwrow[ci];
+            }
+            if (moved) rec[ci] = range_pack(b, e, next);
+            cntw = (uint32_t)(b - a);
+          }
+          // rows with wedges in the window, in ascending first-hop order
+          unsigned m = __ballot_sync(NLP_FULL, cntw != 0u);
+          while (m) {
+            const int r = __ffs(m) - 1;
+            m &= m - 1u;
+            const unsigned long long ar = __shfl_sync(NLP_FULL, a, r);
+            const uint32_t cr = __shfl_sync(NLP_FULL, cntw, r);
+            const uint32_t dr = __shfl_sync(NLP_FULL, dw, r);
+            const double g = flt_term(p, dr);          // inc/predict.hxx:788, 828: a double
+            for (uint32_t k = lane; k < cr; k += 32) {
+              const uint32_t x = __ldg(keys + ar + k) - vlo;
+              acc[x] = __double2float_rn(__dadd_rn((double)acc[x], g));
+            }
+            __syncwarp();                              // the next row may reach the same vertices
+          }
+        }
+      }
+      {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
+        const uint32_t a0 = lower_bound_row(keys, ub, du, vlo);
+        const uint32_t b0 = a0 + lower_bound_row(keys, ub + a0, du - a0, vhi);
+        for (uint32_t i = a0 + lane; i < b0; i += 32) {
+          const uint32_t x = __ldg(keys + ub + i) - vlo;
+          if (acc[x] != 0.0f) acc[x] = RFLT_ZEROED;
+        }
+        __syncwarp();
+      }
+      const uint32_t len = vhi - vlo;
+      for (uint32_t sb = 0; sb < len; sb += 32) {      // score the touched vertices, clear the window
+        const uint32_t i = sb + lane;
+        float val = 0.0f;
+        bool has = false;
+        if (i < len) {
+          val = acc[i];
+          has = val != 0.0f;
+          if (has) acc[i] = 0.0f;
+          if (val < 0.0f) val = 0.0f;                  // touched, then zeroed: a candidate with value 0
+        }
+        emitted += score_and_emit(p, has, u, du, vlo + i, 0u, val, tally);
+      }
+      __syncwarp();
+    }
+    if (ADMIT && lane == 0) atomicAdd(&p.ctr->reserved, (unsigned long long)emitted - (unsigned long long)need);
+  }
+  tally.flush(p.ctr);
+}
+
 }  // namespace nlp
