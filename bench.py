@@ -349,10 +349,11 @@ def run_b200(args):
             pred.fetch_async(o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n)
 
     def one_step_e2e():
-        # One batch of the harness, host buffers in, host results out (main.cxx:164-169 + 208-221): bind the
-        # base graph (resident since it was loaded, as main.cxx's x), send this batch's deletions from
-        # pinned host memory, apply them on the device (nlp_apply_deletions), predict, fetch.
-        pred.set_graph_pointers(base[0].data_ptr(), base[1].data_ptr(), S, device=True, keep=base)
+        # One batch of the harness, host buffers in, host results out (main.cxx:164-169 + 208-221): back to
+        # the base graph (resident since it was loaded, as main.cxx's x; nlp_graph_rollback = duplicate(x)),
+        # send this batch's deletions from pinned host memory, apply them on the device
+        # (nlp_apply_deletions), predict, fetch.
+        pred.graph_rollback()
         pred.apply_deletions(pointers=(h_du.data_ptr(), h_dv.data_ptr(), int(h_du.numel())))
         edges = 0
         for i, m in enumerate(measures):
@@ -451,13 +452,15 @@ def run_b200(args):
     e2e = None
     e2e_upload = None
     if do_e2e:
+        pred.set_graph_pointers(base[0].data_ptr(), base[1].data_ptr(), S, device=True, keep=base)
+        pred.graph_checkpoint()
         for _ in range(max(1, min(args.warmup, 2))):
             one_step_e2e()
         e_edges, e_ms, e_wall, _ = timed(one_step_e2e, args.steps)
         copies = 1 if shard in ("none",) else world      # every rank receives the batch
         e2e = {"value": e_edges / (e_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": 8 * int(h_du.numel()) * copies,
                "d2h_bytes_per_step": int(e_edges / args.steps) * 12, "ms_per_step": e_ms / args.steps,
-               "step": "bind the resident base graph, H2D of the batch's %d directed deletions from pinned memory, nlp_apply_deletions "
+               "step": "nlp_graph_rollback to the resident base graph, H2D of the batch's %d directed deletions from pinned memory, nlp_apply_deletions "
                        "(CSR rebuilt on the device), %d predictions, every (u, v, score) list fetched to pinned host memory" % (int(h_du.numel()), len(measures))}
         if args.e2e_upload:
             for _ in range(max(1, min(args.warmup, 2))):

@@ -261,6 +261,14 @@ int nlp_deletions_device(nlp_handle* h, const uint32_t** d_u, const uint32_t** d
  * bound again for the next batch).  Uses the candidate buffers: the last result is gone.         */
 int nlp_apply_deletions(nlp_handle* h, const uint32_t* del_u, const uint32_t* del_v, uint64_t n);
 
+/* runBatches starts every batch from a copy of the loaded graph (main.cxx:164: y = duplicate(x)).
+ * nlp_graph_checkpoint marks the resident graph as that base -- without copying: arrays the handle
+ * owns are set aside (nlp_apply_deletions writes its result elsewhere), lent arrays are only
+ * remembered -- and nlp_graph_rollback makes the base the resident graph again, without the
+ * validation and symmetry passes a fresh nlp_set_graph* pays.                                    */
+int nlp_graph_checkpoint(nlp_handle* h);
+int nlp_graph_rollback(nlp_handle* h);
+
 /* Size of the resident graph, and a copy of its CSR (offsets[span + 1], keys[entries]; host or
  * this GPU's pointers; either may be NULL).                                                      */
 int nlp_graph_size(nlp_handle* h, uint32_t* span, uint64_t* entries);

@@ -26,7 +26,9 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -276,6 +278,87 @@ inline auto generateEdgeDeletionsB200(const G& x, uint32_t seed, size_t batchSiz
   std::vector<std::tuple<K, K>> a((size_t)n);
   for (size_t i = 0; i < (size_t)n; ++i) a[i] = std::make_tuple((K)u[i], (K)v[i]);
   return a;
+}
+
+// ---- applying a batch on the GPU (inc/batch.hxx:239-247 as called at main.cxx:164-169) ------------
+// runBatches copies the loaded graph for every batch (y = duplicate(x)), applies the tidied
+// deletions to the copy (applyBatchUpdateOmpU) and predicts on it.  With the graph resident:
+//
+//   nlp_b200::DeviceGraph x(g);                        // once: upload (validated on the device)
+//   nlp_b200::checkpointGraph(x);                      // x is the base of every batch
+//   for (every batch) {
+//     nlp_b200::rollbackGraph(x);                      // y = duplicate(x): no copy, no upload
+//     auto deletions = nlp_b200::generateEdgeDeletionsB200(x, seed, batchSize, nullptr, true);
+//     nlp_b200::applyBatchUpdateB200(x, deletions);    // the resident graph is y now
+//     ... predictLinks*<D>(x, {repeat, deletions.size() / 2}) ...
+//   }
+inline void checkpointGraph(const DeviceGraph& x) {
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  if (s.resident != &x) throw std::runtime_error("nlp_b200: this DeviceGraph is no longer resident");
+  detail::check(s.handle(), nlp_graph_checkpoint(s.handle()), "nlp_graph_checkpoint");
+}
+
+inline void rollbackGraph(const DeviceGraph& x) {
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  if (s.resident != &x) throw std::runtime_error("nlp_b200: this DeviceGraph is no longer resident");
+  detail::check(s.handle(), nlp_graph_rollback(s.handle()), "nlp_graph_rollback");
+}
+
+// `deletions` = unique directed (u, v) pairs, as tidyBatchUpdateU leaves them (both directions of
+// every removed edge).  The resident graph loses one stored copy per pair.
+template <class Tuple>
+inline void applyBatchUpdateB200(const DeviceGraph& x, const std::vector<Tuple>& deletions) {
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  if (s.resident != &x) throw std::runtime_error("nlp_b200: this DeviceGraph is no longer resident");
+  nlp_handle* h = s.handle();
+  std::vector<uint32_t> u(deletions.size()), v(deletions.size());
+  for (size_t i = 0; i < deletions.size(); ++i) { u[i] = (uint32_t)std::get<0>(deletions[i]); v[i] = (uint32_t)std::get<1>(deletions[i]); }
+  detail::check(h, nlp_apply_deletions(h, u.data(), v.data(), (uint64_t)deletions.size()), "nlp_apply_deletions");
+}
+
+// ---- several GPUs -----------------------------------------------------------
+// One process per GPU (mpirun / torchrun / a shell loop), the same program on every rank.  Every
+// rank uploads the graph to its own GPU; after joinCommunicatorFromEnv() every predictLinks* call is
+// a collective: the sources are partitioned by wedge work, the library merges the ranks' candidates
+// over its NCCL communicator, and EVERY rank returns the full result.
+//   RANK, WORLD_SIZE          as the launcher sets them
+//   LOCAL_RANK                -> the CUDA device (unless NLP_B200_DEVICE is set)
+//   NLP_B200_COMM_FILE        a path all ranks can reach: rank 0 writes the 128-byte id there
+inline void joinCommunicatorFromEnv() {
+  const char* wr = std::getenv("WORLD_SIZE"); const char* rk = std::getenv("RANK");
+  const int world = wr ? std::atoi(wr) : 1, rank = rk ? std::atoi(rk) : 0;
+  if (world <= 1) return;
+  if (!std::getenv("NLP_B200_DEVICE")) { if (const char* lr = std::getenv("LOCAL_RANK")) setenv("NLP_B200_DEVICE", lr, 1); }
+  const char* path = std::getenv("NLP_B200_COMM_FILE");
+  if (!path) throw std::runtime_error("nlp_b200: set NLP_B200_COMM_FILE to a path every rank can read");
+  detail::Session& s = detail::Session::get();
+  std::lock_guard<std::mutex> lock(s.mu);
+  nlp_handle* h = s.handle();
+  unsigned char id[NLP_COMM_ID_BYTES];
+  const std::string tmp = std::string(path) + ".tmp";
+  if (rank == 0) {
+    if (nlp_comm_unique_id(id) != NLP_OK) throw std::runtime_error(std::string("nlp_b200: nlp_comm_unique_id: ") + nlp_last_error(nullptr));
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f || std::fwrite(id, 1, sizeof id, f) != sizeof id) throw std::runtime_error("nlp_b200: cannot write NLP_B200_COMM_FILE");
+    std::fclose(f);
+    std::rename(tmp.c_str(), path);
+  } else {
+    for (int tries = 0;; ++tries) {
+      FILE* f = std::fopen(path, "rb");
+      if (f) {
+        const size_t got = std::fread(id, 1, sizeof id, f);
+        std::fclose(f);
+        if (got == sizeof id) break;
+      }
+      if (tries > 6000) throw std::runtime_error("nlp_b200: no communicator id in NLP_B200_COMM_FILE after 10 minutes");
+      struct timespec ts = {0, 100000000L};
+      nanosleep(&ts, nullptr);
+    }
+  }
+  detail::check(h, nlp_comm_init(h, id, rank, world), "nlp_comm_init");
 }
 
 inline LinkEvaluation evaluateLastPrediction() {

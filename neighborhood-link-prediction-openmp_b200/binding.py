@@ -18,7 +18,7 @@ STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
            "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_set_reuse", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
            "nlp_comm_unique_id", "nlp_comm_init", "nlp_comm_destroy", "nlp_comm_bytes",
-           "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_apply_deletions", "nlp_graph_size", "nlp_fetch_graph", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
+           "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_apply_deletions", "nlp_graph_checkpoint", "nlp_graph_rollback", "nlp_graph_size", "nlp_fetch_graph", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
 class Options(C.Structure):
@@ -97,6 +97,8 @@ def load_library(build_if_missing=True):
     lib.nlp_fetch_deletions.argtypes = [vp, vp, vp, u64]
     lib.nlp_deletions_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     lib.nlp_apply_deletions.argtypes = [vp, vp, vp, u64]
+    lib.nlp_graph_checkpoint.argtypes = [vp]
+    lib.nlp_graph_rollback.argtypes = [vp]
     lib.nlp_graph_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u64)]
     lib.nlp_fetch_graph.argtypes = [vp, vp, vp]
     lib.nlp_launch_count.argtypes = [vp]
@@ -262,6 +264,14 @@ class Predictor:
             return
         u = np.ascontiguousarray(u, dtype=np.uint32); v = np.ascontiguousarray(v, dtype=np.uint32)
         self._check(self.lib.nlp_apply_deletions(self.h, u.ctypes.data if u.size else None, v.ctypes.data if v.size else None, u.size))
+
+    def graph_checkpoint(self):
+        """Mark the resident graph as the base of a batch loop (main.cxx:164)."""
+        self._check(self.lib.nlp_graph_checkpoint(self.h))
+
+    def graph_rollback(self):
+        """Make the checkpointed base graph the resident graph again."""
+        self._check(self.lib.nlp_graph_rollback(self.h))
 
     def graph_size(self):
         s, m = C.c_uint32(0), C.c_uint64(0)

@@ -50,6 +50,10 @@ struct nlp_handle {
   const uint32_t* d_keys = nullptr;
   DevBuf own_off, own_keys, spare_off, spare_keys;   // spare: destination of nlp_apply_deletions when the graph is the handle's own
   DevBuf del_bits;
+  // nlp_graph_checkpoint: the base graph of a batch loop (main.cxx:164: y = duplicate(x) per batch)
+  DevBuf base_off, base_keys;                // owned copy-free: the handle's own CSR moves here
+  const uint64_t* base_d_off = nullptr; const uint32_t* base_d_keys = nullptr;
+  uint32_t base_S = 0; int base_sym = 0; uint32_t base_maxmult = 1; unsigned long long base_id = 0; bool has_base = false;
   uint32_t S = 0;
   uint64_t M = 0;
   uint32_t maxdeg = 0;
@@ -673,6 +677,7 @@ int check_symmetry(nlp_handle* h) {
   if (h->graph_id) {
     if (h->known_sym.size() >= 64) h->known_sym.clear();
     h->known_sym[h->graph_id] = h->sym_state;
+    if (h->has_base && h->graph_id == h->base_id) h->base_sym = h->sym_state;
   }
   // the check is graph preparation, not part of the prediction: restart the clock
   NLP_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
@@ -1776,7 +1781,7 @@ int nlp_destroy(nlp_handle* h) {
     if (h->ev_stg_ready[i]) cudaEventDestroy(h->ev_stg_ready[i]);
     if (h->ev_stg_done[i]) cudaEventDestroy(h->ev_stg_done[i]);
   }
-  release(h->own_off); release(h->own_keys); release(h->spare_off); release(h->spare_keys); release(h->del_bits); release(h->deg); release(h->work); release(h->work64); release(h->elig); release(h->maxdeg_dev);
+  release(h->own_off); release(h->own_keys); release(h->spare_off); release(h->spare_keys); release(h->base_off); release(h->base_keys); release(h->del_bits); release(h->deg); release(h->work); release(h->work64); release(h->elig); release(h->maxdeg_dev);
   release(h->chunk_base); release(h->chunk_src); release(h->chunk_cnt); release(h->ecount); release(h->ekeys);
   release(h->scan_tiles); release(h->scan_total);
   release(h->it_u); release(h->it_cnt); release(h->it_dw); release(h->it_ptr); release(h->it_off); release(h->sym_flag);
@@ -2199,6 +2204,43 @@ int nlp_apply_deletions(nlp_handle* h, const uint32_t* del_u, const uint32_t* de
   h->has_graph = false;
   // the result of a validated graph is valid by construction; its symmetry follows from the base's
   return finish_graph(h, true, base_sym == 1 ? (asym ? 0 : 1) : base_sym == 2 ? 0 : 0);
+}
+
+int nlp_graph_checkpoint(nlp_handle* h) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_graph) return fail(h, NLP_ERR_NO_GRAPH, "nlp_graph_checkpoint: no graph set");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->d_off == (const uint64_t*)h->own_off.p && h->own_off.p) {
+    // the handle's own arrays become the base (no copy); nlp_apply_deletions then writes elsewhere
+    release(h->base_off); release(h->base_keys);
+    h->base_off = h->own_off; h->base_keys = h->own_keys;
+    h->own_off = DevBuf(); h->own_keys = DevBuf();
+  } else if (h->d_off == (const uint64_t*)h->base_off.p && h->base_off.p) {
+    // already the base
+  } else {
+    release(h->base_off); release(h->base_keys);     // a borrowed graph: only the pointers are remembered
+  }
+  h->base_d_off = h->d_off; h->base_d_keys = h->d_keys; h->base_S = h->S;
+  h->base_sym = h->sym_state; h->base_maxmult = h->maxmult; h->base_id = h->graph_id;
+  h->has_base = true;
+  return NLP_OK;
+}
+
+int nlp_graph_rollback(nlp_handle* h) {
+  if (!h) return NLP_ERR_ARG;
+  if (!h->has_base) return fail(h, NLP_ERR_NO_GRAPH, "nlp_graph_rollback: no checkpoint");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  if (h->base_sym == 0 && h->base_id) {               // learnt since the checkpoint?
+    auto known = h->known_sym.find(h->base_id);
+    if (known != h->known_sym.end()) h->base_sym = known->second;
+  }
+  h->d_off = h->base_d_off; h->d_keys = h->base_d_keys; h->S = h->base_S;
+  h->has_graph = false;
+  h->maxmult = h->base_maxmult;
+  const int rc = finish_graph(h, true, h->base_sym);   // validated when it was set: no second pass
+  if (rc == NLP_OK) h->graph_id = h->base_id;
+  return rc;
 }
 
 int nlp_graph_size(nlp_handle* h, uint32_t* span, uint64_t* entries) {

@@ -24,5 +24,10 @@ size_t instantiate(const MiniGraph& x, const nlp_b200::DeviceGraph& dg) {
   nlp_b200::setHeldBackEdges(a);
   nlp_b200::setFetchEdges(false);
   const nlp_b200::LinkEvaluation ev = nlp_b200::evaluateLastPrediction();
+  // the batch loop on the GPU: base graph, rollback, apply; several GPUs
+  nlp_b200::checkpointGraph(dg);
+  nlp_b200::rollbackGraph(dg);
+  nlp_b200::applyBatchUpdateB200(dg, b);
+  nlp_b200::joinCommunicatorFromEnv();
   return a.size() + b.size() + words + ev.common;
 }

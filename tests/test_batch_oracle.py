@@ -158,5 +158,32 @@ def test_device_apply_deletions_matches_reference(nlp, oracle):
                                    torch.from_numpy(du2.astype(np.int64)), torch.from_numpy(dv2.astype(np.int64)))
         to, tk = g.to_numpy(to, tk)
         assert np.array_equal(o3, to) and np.array_equal(k3, tk)
+        # the batch loop of main.cxx:163-169: checkpoint the base, per batch roll back and apply
+        for mode in ("host", "device"):
+            if mode == "host":
+                pred.set_graph(off, keys)
+            else:
+                d_off = torch.from_numpy(off.astype(np.int64)).cuda(); d_keys = torch.from_numpy(keys.astype(np.int32)).cuda()
+                pred.set_graph_pointers(d_off.data_ptr(), d_keys.data_ptr(), len(off) - 1, device=True, keep=(d_off, d_keys))
+            pred.graph_checkpoint()
+            for seed in (5, 6, 7):
+                pred.graph_rollback()
+                o0, k0 = pred.fetch_graph()
+                assert np.array_equal(o0, off) and np.array_equal(k0, keys), (mode, seed, "rollback")
+                du, dv, _ = pred.generate_deletions(seed, 300)
+                pred.apply_deletions(du, dv)
+                if seed == 6:                       # two batches in a row (BATCH_LENGTH = 2), still from this base
+                    du_b, dv_b, _ = pred.generate_deletions(seed + 100, 200)
+                    pred.apply_deletions(du_b, dv_b)
+                o1, k1 = pred.fetch_graph()
+                to, tk = g.apply_deletions(torch.from_numpy(off.astype(np.int64)), torch.from_numpy(keys.astype(np.int32)),
+                                           torch.from_numpy(du.astype(np.int64)), torch.from_numpy(dv.astype(np.int64)))
+                if seed == 6:
+                    to, tk = g.apply_deletions(to, tk, torch.from_numpy(du_b.astype(np.int64)), torch.from_numpy(dv_b.astype(np.int64)))
+                to, tk = g.to_numpy(to, tk)
+                assert np.array_equal(o1, to) and np.array_equal(k1, tk), (mode, seed)
+                r = pred.predict("JC", 4, max_edges=500)
+                want = oracle.oracle_predict(o1, k1, "JC", 4, max_edges=500)[:3]
+                assert parity.compare(pred.fetch(r["count"]), want, "batch loop %s %d" % (mode, seed)) is None
     finally:
         pred.close()
