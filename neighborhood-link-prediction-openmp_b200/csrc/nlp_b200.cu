@@ -1720,7 +1720,7 @@ int nlp_create(nlp_handle** out, int device) {
   if (const char* e = getenv("NLP_B200_RANGE_DIV")) h->range_div = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("NLP_B200_RANGE_FLT")) h->flt_range_mode = atoi(e);
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
-  if (const char* e = getenv("NLP_B200_BUCKET_CAP")) h->bucket_cap = atoi(e) == 4096 ? 4096u : 8192u;
+  if (const char* e = getenv("NLP_B200_BUCKET_CAP")) h->bucket_cap = atoi(e) == 8192 ? 8192u : 4096u;
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string("nlp_create: ") + what + ": " + cudaGetErrorString(err);
     delete h;

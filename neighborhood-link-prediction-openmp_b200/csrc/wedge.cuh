@@ -951,6 +951,7 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, cons
           const uint64_t ci = (uint64_t)c * CHUNK + i;
           unsigned long long a = 0;
           uint32_t cntw = 0, dw = 0;
+          double g = 0.0;
           if (has) {
             unsigned long long e;
             uint32_t next;
@@ -976,24 +977,44 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, cons
               next = b < e ? __ldg(keys + b) : 0xffffffffu;
               moved = true;
               if (!first) dw = dwrow[ci];
+              g = flt_term(p, dw);                     // inc/predict.hxx:788, 828: a double; one per row, computed by its lane
             }
             if (moved) rec[ci] = range_pack(b, e, next);
             cntw = (uint32_t)(b - a);
           }
-          // rows with wedges in the window, in ascending first-hop order
+          // Rows with wedges in the window, in ascending first-hop order, FOUR at a time: the key
+          // loads of four rows are issued together (a warp is a single dependent chain here, so the
+          // load latency per row is what bounds this kernel), the accumulations then follow one row
+          // after the other.
           unsigned m = __ballot_sync(NLP_FULL, cntw != 0u);
           while (m) {
-            const int r = __ffs(m) - 1;
-            m &= m - 1u;
-            const unsigned long long ar = __shfl_sync(NLP_FULL, a, r);
-            const uint32_t cr = __shfl_sync(NLP_FULL, cntw, r);
-            const uint32_t dr = __shfl_sync(NLP_FULL, dw, r);
-            const double g = flt_term(p, dr);          // inc/predict.hxx:788, 828: a double
-            for (uint32_t k = lane; k < cr; k += 32) {
-              const uint32_t x = __ldg(keys + ar + k) - vlo;
-              acc[x] = __double2float_rn(__dadd_rn((double)acc[x], g));
+            int rr[4];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) { rr[j] = m ? __ffs(m) - 1 : -1; if (m) m &= m - 1u; }
+            unsigned long long ar[4];
+            uint32_t cr[4], kv[4];
+            double gr[4];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = rr[j] < 0 ? 0 : rr[j];
+              ar[j] = __shfl_sync(NLP_FULL, a, r);
+              cr[j] = rr[j] < 0 ? 0u : __shfl_sync(NLP_FULL, cntw, r);
+              gr[j] = __shfl_sync(NLP_FULL, g, r);
+              kv[j] = (uint32_t)lane < cr[j] ? __ldg(keys + ar[j] + lane) : 0u;
             }
-            __syncwarp();                              // the next row may reach the same vertices
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (rr[j] < 0) break;                    // warp-uniform
+              if ((uint32_t)lane < cr[j]) {
+                const uint32_t x = kv[j] - vlo;
+                acc[x] = __double2float_rn(__dadd_rn((double)acc[x], gr[j]));
+              }
+              for (uint32_t k = 32u + lane; k < cr[j]; k += 32) {
+                const uint32_t x = __ldg(keys + ar[j] + k) - vlo;
+                acc[x] = __double2float_rn(__dadd_rn((double)acc[x], gr[j]));
+              }
+              __syncwarp();                            // the next row may reach the same vertices
+            }
           }
         }
       }

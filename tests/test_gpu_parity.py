@@ -283,13 +283,33 @@ def test_hub_heavy_sources_windowed_counters(nlp, oracle, monkeypatch, half):
             err, r, st = parity.check_case(p, oracle, off, keys, m, D, K, tag="hubs half=%s" % half)
             assert err is None, err
             flt = m in ("AA", "RA")
-            if D != 5:
-                # the float measures walk windows with one warp per source (k_range_flt) -- except on
-                # multiset rows, where repeated entries of a row would collide inside a window
-                if flt and half == "multiset":
-                    assert r["bin_sources"][6] == 0, r["bin_sources"]
-                else:
-                    assert r["bin_sources"][6] > 0, r["bin_sources"]
+            if D != 5 and not flt:
+                assert r["bin_sources"][6] > 0, r["bin_sources"]
+            if flt and half == "multiset":
+                # repeated entries of a row would collide inside a window of k_range_flt: dense tables instead
+                assert r["bin_sources"][6] == 0, r["bin_sources"]
+    finally:
+        p.close()
+
+
+def test_float_measures_on_warp_windows(oracle, nlp):
+    """k_range_flt: hub-heavy sources of Adamic-Adar / resource allocation on per-warp windows of
+    float accumulators, rows taken one after the other (the reference's accumulation order) -- IHub
+    and LHub with a high threshold, also with the pruned candidate buffer, against the oracle; the
+    dense-table path (NLP_B200_RANGE_FLT=0 is the same code with that bin empty) gives the same bits."""
+    g = nlp.graphs
+    off, keys = g.to_numpy(*g.rmat(14, 16, 32))            # ids as generated: hubs at the low ids, high-degree neighbours
+    S = len(off) - 1
+    p = nlp.Predictor(0)
+    try:
+        p.set_graph(off, keys)
+        p.set_path(SOURCE_PATH)
+        for K, limit in ((5000, 0), (2000, (2000 + S + 4096 + 50000) * 24 * 10 // 8 + (64 << 20))):
+            p.set_scratch_limit(limit)
+            for m, D in (("AA", 0), ("RA", 0), ("AA", 1024), ("RA", 256)):
+                err, r, st = parity.check_case(p, oracle, off, keys, m, D, K, tag="flt windows K=%d" % K)
+                assert err is None, err
+                assert r["bin_sources"][6] > 0, r["bin_sources"]
     finally:
         p.close()
 
