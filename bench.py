@@ -90,6 +90,9 @@ def build_workload(name, device, batch=0, pred=None):
     else:
         off, keys = N.graphs.web_crawl(w["n"], w["avg_out"], seed=w["seed"], device=device)
     S = int(off.numel() - 1)
+    if device != "cpu":
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()        # the library allocates with cudaMalloc: hand the generator's cached blocks back
     batch_size = int(w["frac"] * int(keys.numel()) / 2)            # size_t(d * x.size() / 2), main.cxx:166
     seed = REMOVAL_SEED + batch
     base = (off, keys)

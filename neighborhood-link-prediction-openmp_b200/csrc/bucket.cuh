@@ -84,27 +84,37 @@ __global__ void __launch_bounds__(256) k_plan_rows(DevGraph g, uint32_t D, uint3
   }
 }
 
-// One thread per eligible row: descriptors of its items, in (w, position) order, plus the
-// (u, item index) pairs the sort by u works on.
+// Descriptors of the items of every eligible row, in (w, position) order, plus the (u, item index)
+// pairs the sort by u works on.  A warp takes 32 consecutive rows (lane = row for the row data) and
+// then walks the rows one after the other with all lanes on the row's entries: thresholds like
+// D = 1024 make rows of a thousand items eligible, which one thread per row would serialise.
 __global__ void __launch_bounds__(256) k_plan_items(DevGraph g, const uint32_t* __restrict__ items,
                                                     const unsigned long long* __restrict__ item_off,
                                                     uint32_t* __restrict__ su, uint32_t* __restrict__ sidx,
                                                     uint32_t* __restrict__ it_cnt, uint32_t* __restrict__ it_dw,
                                                     unsigned long long* __restrict__ it_ptr) {
   const uint32_t* __restrict__ keys = g.keys;
-  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < g.S; w += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t n = items[w];
-    if (!n) continue;
-    const uint32_t d = g.deg[w];
-    const unsigned long long base = item_off[w];
-    const uint64_t wb = __ldg(g.off + w);
-    uint32_t j = 0;                                  // first entry > keys[wb + i]
-    for (uint32_t i = 0; i < n; ++i) {
-      const uint32_t u = __ldg(keys + wb + i);
-      if (j <= i) j = i + 1;
-      while (j < d && __ldg(keys + wb + j) == u) ++j;
-      su[base + i] = u; sidx[base + i] = (uint32_t)(base + i);
-      it_cnt[base + i] = d - j; it_dw[base + i] = d; it_ptr[base + i] = wb + j;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t w0 = warp0 * 32u; w0 < g.S; w0 += nwarps * 32u) {
+    const uint64_t w = w0 + lane;
+    uint32_t n = 0, d = 0;
+    unsigned long long base = 0, wb = 0;
+    if (w < g.S) { n = items[w]; if (n) { d = g.deg[w]; base = item_off[w]; wb = __ldg(g.off + w); } }
+    unsigned m = __ballot_sync(NLP_FULL, n != 0u);
+    while (m) {
+      const int r = __ffs(m) - 1;
+      m &= m - 1u;
+      const uint32_t nr = __shfl_sync(NLP_FULL, n, r), dr = __shfl_sync(NLP_FULL, d, r);
+      const unsigned long long br = __shfl_sync(NLP_FULL, base, r), wr = __shfl_sync(NLP_FULL, wb, r);
+      for (uint32_t i = lane; i < nr; i += 32) {
+        const uint32_t u = __ldg(keys + wr + i);
+        uint32_t j = i + 1;                            // first entry > u (rows are sorted multisets)
+        while (j < dr && __ldg(keys + wr + j) == u) ++j;
+        su[br + i] = u; sidx[br + i] = (uint32_t)(br + i);
+        it_cnt[br + i] = dr - j; it_dw[br + i] = dr; it_ptr[br + i] = wr + j;
+      }
     }
   }
 }

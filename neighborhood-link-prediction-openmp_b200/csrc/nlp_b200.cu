@@ -92,6 +92,9 @@ struct nlp_handle {
   uint64_t cand_cap = 0;
   // dense spill tables
   DevBuf tables, touched, range_cursors, range_touched;
+  DevBuf flt_cnt, flt_off, flt_items, flt_ids, flt_defer;   // k_range_flt: (source, window range) items
+  FltItems flt_it{nullptr, nullptr, nullptr};
+  uint64_t flt_n = 0;
   // select / sort scratch
   DevBuf counts, totals, hist, sel, cursor2, sel11;
   Select11* h_sel11 = nullptr;         // pinned (header + digit histograms)
@@ -602,7 +605,7 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
     const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n + RFLT_WARPS - 1) / RFLT_WARPS, (uint64_t)h->num_sms);
     NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * RFLT_WARPS * stride * 16));
     NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * RFLT_WARPS * stride * 4));
-    k_range_flt<ADMIT><<<grid, RFLT_WARPS * 32, smem, h->stream>>>(p, list, n, 6, deferred, (uint4*)h->range_cursors.p,
+    k_range_flt<ADMIT><<<grid, RFLT_WARPS * 32, smem, h->stream>>>(p, h->flt_it, list, n, 6, deferred, (uint4*)h->range_cursors.p,
                                                                    (uint32_t*)h->range_touched.p, stride);
     NLP_LAUNCHED(h);
     return NLP_OK;
@@ -742,7 +745,7 @@ int build_plan(nlp_handle* h, uint32_t D, uint32_t half, nlp_handle::BucketPlan&
   { Carver c(nullptr); carve_tmp(c); if (!try_ensure(h, h->plan_tmp, c.off + 256)) return NLP_OK; }
   { Carver c(h->plan_tmp.p); carve_tmp(c); }
   const unsigned gS = grid_for(S, 256, h->num_sms * 8), gE = grid_for(E, 256, h->num_sms * 16);
-  k_plan_items<<<gS, 256, 0, h->stream>>>(g, (const uint32_t*)h->work.p, (const unsigned long long*)h->work64.p,
+  k_plan_items<<<grid_for((uint64_t)S, 8 * 32, h->num_sms * 16), 256, 0, h->stream>>>(g, (const uint32_t*)h->work.p, (const unsigned long long*)h->work64.p,
                                           (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, it_cnt, it_dw, it_ptr);
   NLP_LAUNCHED(h);
   int buf = 0;
@@ -1266,9 +1269,9 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   uint32_t range_fixed = 256, range_div = h->range_div;
   if (FLT && h->range_mode != 0 && h->flt_range_mode != 0 && h->maxmult <= 1u && h->maxdeg < (1u << 22)) {
     const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
-    uint64_t budget0 = 0;
-    NLP_TRY(scratch_budget(h, &budget0));
-    if ((uint64_t)h->num_sms * RFLT_WARPS * stride * 20 <= budget0 / 4) { range_c = RFLT_WIN; range_fixed = 32; range_div = 4; }
+    // (against the memory that was free when the graph was set, not against nlp_set_scratch_limit:
+    // that limit is about the candidate buffer and the spill tables)
+    if ((uint64_t)h->num_sms * RFLT_WARPS * stride * 20 <= h->budget_base / 4) { range_c = RFLT_WIN; range_fixed = 32; range_div = 4; }
   }
   uint32_t half_deg = 0;
   NLP_TRY(half_word_limit(h, range_c != 0u && !FLT, &half_deg));
@@ -1320,6 +1323,30 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   }
   NLP_TRY(ensure_candidates(h, cap));
 
+  // float measures on warp windows: the bin-6 sources are cut into (source, window range) items,
+  // and the bin's work list becomes the list of item ids (also the unit of deferral)
+  const uint32_t* list6 = (const uint32_t*)h->list[6].p;
+  uint32_t* defer6 = (uint32_t*)h->defer[6].p;
+  uint64_t n6 = nb[6];
+  if (FLT && nb[6]) {
+    NLP_TRY(ensure(h, h->flt_cnt, nb[6] * 4));
+    NLP_TRY(ensure(h, h->flt_off, nb[6] * 8));
+    k_flt_item_counts<<<grid_for(nb[6], 256, h->num_sms * 8), 256, 0, h->stream>>>(g, list6, (uint32_t)nb[6], (uint32_t*)h->flt_cnt.p);
+    NLP_LAUNCHED(h);
+    uint64_t nitems = 0;
+    NLP_TRY(exclusive_scan<uint32_t>(h, (const uint32_t*)h->flt_cnt.p, nb[6], (unsigned long long*)h->flt_off.p, &nitems));
+    if (nitems >= 0xfffffff0ull) return fail(h, NLP_ERR_CAPACITY, "too many window items");
+    NLP_TRY(ensure(h, h->flt_items, nitems * 12 + 64));
+    NLP_TRY(ensure(h, h->flt_ids, nitems * 4));
+    NLP_TRY(ensure(h, h->flt_defer, nitems * 4));
+    h->flt_it.u = (uint32_t*)h->flt_items.p; h->flt_it.w0 = h->flt_it.u + nitems; h->flt_it.w1 = h->flt_it.w0 + nitems;
+    k_flt_item_fill<<<grid_for(nb[6], 256, h->num_sms * 8), 256, 0, h->stream>>>(g, list6, (uint32_t)nb[6],
+                                                                               (const unsigned long long*)h->flt_off.p, h->flt_it, (uint32_t*)h->flt_ids.p);
+    NLP_LAUNCHED(h);
+    h->flt_n = nitems;
+    list6 = (const uint32_t*)h->flt_ids.p; defer6 = (uint32_t*)h->flt_defer.p; n6 = nitems;
+  }
+
   int cur = 0;
   Params p;
   p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
@@ -1344,7 +1371,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   if (!admit) {
     // everything fits: one pass, no admission control, no host round trip until the end
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[0], h->stream));
-    NLP_TRY((launch_range<FLT, false>(h, p, (const uint32_t*)h->list[6].p, (uint32_t)nb[6], nullptr)));
+    NLP_TRY((launch_range<FLT, false>(h, p, list6, (uint32_t)n6, nullptr)));
     NLP_TRY((launch_dense<FLT, false>(h, p, (const uint32_t*)h->list[5].p, (uint32_t)nb[5], nullptr, dense_slots, touched_cap)));
     NLP_CUDA(h, cudaEventRecord(h->ev_phase[1], h->stream));
     for (int b = 4; b >= 2; --b) {
@@ -1362,8 +1389,10 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
     // best K (which fixes the pruning threshold) and continue with the deferred sources
     uint32_t* lists[NBINS]; uint32_t* defers[NBINS];
     for (int b = 0; b < NBINS; ++b) { lists[b] = (uint32_t*)h->list[b].p; defers[b] = (uint32_t*)h->defer[b].p; }
+    lists[6] = const_cast<uint32_t*>(list6); defers[6] = defer6;
     uint64_t remaining[NBINS];
     for (int b = 0; b < NBINS; ++b) remaining[b] = nb[b];
+    remaining[6] = n6;
     uint64_t tiny_pos[2] = {0, 0};
     uint64_t fill = 0;
     for (;; res->passes++) {
@@ -1788,7 +1817,7 @@ int nlp_destroy(nlp_handle* h) {
   for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
-  release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->counts); release(h->totals); release(h->hist);
+  release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->flt_cnt); release(h->flt_off); release(h->flt_items); release(h->flt_ids); release(h->flt_defer); release(h->counts); release(h->totals); release(h->hist);
   release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
   release(h->truth_key); release(h->truth_tmp); release(h->eval_ctr);
   release(h->bt_d); release(h->bt_uat); release(h->bt_hit); release(h->bt_jump[0]); release(h->bt_jump[1]);

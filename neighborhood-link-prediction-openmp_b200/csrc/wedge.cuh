@@ -907,8 +907,72 @@ constexpr uint32_t RFLT_WIN = 1664;
 constexpr float RFLT_ZEROED = -1.0f;
 enum { RFLT_WARPS = 32 };
 
+// A warp is one dependent chain, so one source per warp would leave the longest source (a hub: 3e4
+// rows x 157 windows at R-MAT 18) as the critical path of the whole kernel.  The windows of a source
+// are independent, so heavy sources are cut into ITEMS = (source, range of windows) of about
+// RFLT_ITEM_VISITS row visits each; an item is also the unit of admission when the candidate
+// buffer is pruned (its bound: min(work, vertices in its windows)).
+constexpr uint32_t RFLT_ITEM_VISITS = 1u << 16;
+
+struct FltItems {
+  uint32_t* u;        // [n] source vertex
+  uint32_t* w0;       // [n] first window
+  uint32_t* w1;       // [n] one past the last window
+};
+
+__device__ __forceinline__ uint32_t flt_item_chunks(uint32_t S, uint32_t u, uint32_t du) {
+  const uint32_t nwin = (S - 1u - u + RFLT_WIN - 1u) / RFLT_WIN;
+  if (nwin <= 1u) return 1u;
+  const unsigned long long visits = (unsigned long long)du * nwin;
+  unsigned long long c = (visits + RFLT_ITEM_VISITS - 1u) / RFLT_ITEM_VISITS;
+  if (c < 1ull) c = 1ull;
+  return (uint32_t)(c < nwin ? c : nwin);
+}
+
+__global__ void __launch_bounds__(256) k_flt_item_counts(DevGraph g, const uint32_t* __restrict__ list, uint32_t n, uint32_t* __restrict__ cnt) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = list[i];
+    cnt[i] = flt_item_chunks(g.S, u, g.deg[u]);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_flt_item_fill(DevGraph g, const uint32_t* __restrict__ list, uint32_t n,
+                                                       const unsigned long long* __restrict__ off, FltItems it, uint32_t* __restrict__ ids) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = list[i];
+    const uint32_t nwin = (g.S - 1u - u + RFLT_WIN - 1u) / RFLT_WIN;
+    const uint32_t c = flt_item_chunks(g.S, u, g.deg[u]);
+    const unsigned long long base = off[i];
+    for (uint32_t k = 0; k < c; ++k) {
+      it.u[base + k] = u;
+      it.w0[base + k] = (uint32_t)((unsigned long long)nwin * k / c);
+      it.w1[base + k] = (uint32_t)((unsigned long long)nwin * (k + 1) / c);
+      ids[base + k] = (uint32_t)(base + k);
+    }
+  }
+}
+
+// Admission of one item (pruned candidate buffer): as admit_source, with the item's own bound.
+__device__ __forceinline__ bool admit_item(const Params& p, uint32_t id, uint32_t need, int bin, uint32_t* deferred) {
+  for (;;) {
+    if (*reinterpret_cast<volatile unsigned long long*>(&p.ctr->cursor) >= p.soft_cap) break;
+    const unsigned long long r = atomicAdd(&p.ctr->reserved, (unsigned long long)need);
+    if (r + need <= p.cap) return true;
+    atomicAdd(&p.ctr->reserved, 0ull - (unsigned long long)need);
+    for (;;) {
+      const unsigned long long written = *reinterpret_cast<volatile unsigned long long*>(&p.ctr->cursor);
+      if (written + need > p.cap) goto defer;
+      if (*reinterpret_cast<volatile unsigned long long*>(&p.ctr->reserved) + need <= p.cap) break;
+      __nanosleep(2000);
+    }
+  }
+defer:
+  deferred[atomicAdd(&p.ctr->deferred[bin], 1ull)] = id;
+  return false;
+}
+
 template <bool ADMIT>
-__global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
+__global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltItems items, const uint32_t* __restrict__ list, uint32_t n, int bin,
                                                                   uint32_t* __restrict__ deferred, uint4* __restrict__ rec_all,
                                                                   uint32_t* __restrict__ dw_all, uint64_t rec_stride) {
   extern __shared__ float facc[];                     // [RFLT_WARPS][RFLT_WIN]
@@ -922,26 +986,31 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, cons
   __syncwarp();
   for (;;) {
     uint32_t qi = 0;
-    if (lane == 0) qi = (uint32_t)atomicAdd(&p.ctr->queue[bin], 1ull);      // dynamic: sources differ by 1000x in work
+    if (lane == 0) qi = (uint32_t)atomicAdd(&p.ctr->queue[bin], 1ull);      // dynamic: items still differ in work
     qi = __shfl_sync(NLP_FULL, qi, 0);
     if (qi >= n) break;
-    const uint32_t u = __ldg(list + qi);
+    const uint32_t id = __ldg(list + qi);
+    const uint32_t u = __ldg(items.u + id), w0 = __ldg(items.w0 + id), w1 = __ldg(items.w1 + id);
     uint32_t need = 0;
     if (ADMIT) {
+      const unsigned long long verts = (unsigned long long)(w1 - w0) * RFLT_WIN;
+      const uint32_t wk = p.work[u];
+      need = (unsigned long long)wk < verts ? wk : (uint32_t)verts;
       int go = 0;
-      if (lane == 0) go = admit_source(p, u, bin, deferred, &need) ? 1 : 0;
+      if (lane == 0) go = admit_item(p, id, need, bin, deferred) ? 1 : 0;
       go = __shfl_sync(NLP_FULL, go, 0);
-      need = __shfl_sync(NLP_FULL, need, 0);
       if (!go) continue;
     }
     const uint64_t ub = __ldg(p.g.off + u);
     const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
     const FirstHop f = first_hop(p, u, ub, du);
     uint32_t emitted = 0;
-    for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += RFLT_WIN) {
+    for (uint32_t win = w0; win < w1; ++win) {
+      const uint64_t lo64 = (uint64_t)u + 1 + (uint64_t)win * RFLT_WIN;
+      if (lo64 >= p.g.S) break;
       const uint32_t vlo = (uint32_t)lo64;
       const uint32_t vhi = (uint32_t)(lo64 + RFLT_WIN < p.g.S ? lo64 + RFLT_WIN : p.g.S);
-      const bool first = lo64 == (uint64_t)u + 1;
+      const bool first = win == w0;                    // the item's first window: the rows are bisected, later windows continue
       for (uint32_t c = 0; c < f.npieces; ++c) {
         const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
         const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
