@@ -44,9 +44,9 @@ WORKLOADS = {
     # BASELINE configs[2..4]: parity/scale cases, run with --workload (not the default bench line)
     "road24m": dict(kind="road", side=4900, keep=0.6, seed=44, frac=0.1,
                     desc="road/mesh-shaped 4900x4900 lattice, edges kept with p=0.6 (~24M vertices, avg degree ~2.4), 0.1|E| removed (configs[2])"),
-    "web50m": dict(kind="web", n=50_000_000, avg_out=85, seed=45, frac=0.1,
-                   desc="web-crawl-shaped, 50M vertices, 3.0e9 generated links (~2.2e9 undirected edges, > 2^32 directed entries), "
-                        "power-law out-degree, host locality (BASELINE configs[3], sk-2005 scale)"),
+    "web50m": dict(kind="web", n=50_000_000, avg_out=140, seed=45, frac=0.1, leaves=True,
+                   desc="web-crawl-shaped, 50M vertices, ~3e9 generated links (~2.2e9 undirected edges, > 2^32 directed entries), "
+                        "power-law out-degree, host locality, 40% leaf pages of degree 1-4 (BASELINE configs[3], sk-2005 scale)"),
     "web50m_r1": dict(kind="web", n=50_000_000, avg_out=19, seed=45, frac=0.1, desc="round 1's under-sized configs[3] stand-in (1.0e9 directed entries)"),
     "web25m": dict(kind="web", n=25_000_000, avg_out=19, seed=45, frac=0.1, desc="web-crawl-shaped, 25M vertices (configs[3] at half scale)"),
     "web6m": dict(kind="web", n=6_250_000, avg_out=19, seed=45, frac=0.1, desc="web-crawl-shaped, 6.25M vertices (configs[3] at 1/8 scale)"),
@@ -88,7 +88,7 @@ def build_workload(name, device, batch=0, pred=None):
     elif w["kind"] == "road":
         off, keys = N.graphs.road_lattice(w["side"], w["keep"], w["seed"], device=device)
     else:
-        off, keys = N.graphs.web_crawl(w["n"], w["avg_out"], seed=w["seed"], device=device)
+        off, keys = N.graphs.web_crawl(w["n"], w["avg_out"], seed=w["seed"], device=device, leaves=w.get("leaves", False))
     S = int(off.numel() - 1)
     if device != "cpu":
         torch.cuda.synchronize()

@@ -604,9 +604,9 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
     NLP_CUDA(h, cudaFuncSetAttribute(k_range_flt<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n + RFLT_WARPS - 1) / RFLT_WARPS, (uint64_t)h->num_sms);
     NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * RFLT_WARPS * stride * 16));
-    NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * RFLT_WARPS * stride * 4));
+    NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * RFLT_WARPS * stride * 8));
     k_range_flt<ADMIT><<<grid, RFLT_WARPS * 32, smem, h->stream>>>(p, h->flt_it, list, n, 6, deferred, (uint4*)h->range_cursors.p,
-                                                                   (uint32_t*)h->range_touched.p, stride);
+                                                                   (double*)h->range_touched.p, stride);
     NLP_LAUNCHED(h);
     return NLP_OK;
   }
@@ -1271,7 +1271,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
     const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
     // (against the memory that was free when the graph was set, not against nlp_set_scratch_limit:
     // that limit is about the candidate buffer and the spill tables)
-    if ((uint64_t)h->num_sms * RFLT_WARPS * stride * 20 <= h->budget_base / 4) { range_c = RFLT_WIN; range_fixed = 32; range_div = 4; }
+    if ((uint64_t)h->num_sms * RFLT_WARPS * stride * 24 <= h->budget_base / 4) { range_c = RFLT_WIN; range_fixed = 32; range_div = 4; }
   }
   uint32_t half_deg = 0;
   NLP_TRY(half_word_limit(h, range_c != 0u && !FLT, &half_deg));
@@ -1647,14 +1647,17 @@ int ordered_top_k(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
     k_ordered_count2<<<ntiles, OC_THREADS, 0, h->stream>>>(sbits, n, st, (unsigned long long*)h->oc_counts.p);
     NLP_LAUNCHED(h);
   }
-  if (api) NLP_NCCL(h, api->AllReduce(&st->dhist[0][0], &st->dhist[0][0], 1024, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->stream));
-  NLP_CUDA(h, cudaMemcpyAsync(h->h_sel11, st, sizeof(Select11), cudaMemcpyDeviceToHost, h->stream));
+  k_sel11_bits<<<1, 64, 0, h->stream>>>(st);          // which bits of the survivors' keys vary, as counters ...
+  NLP_LAUNCHED(h);
+  if (api) NLP_NCCL(h, api->AllReduce(st->bitflags, st->bitflags, 64, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->stream));   // ... over all ranks
+  NLP_CUDA(h, cudaMemcpyAsync(h->h_sel11, st, offsetof(Select11, hist), cudaMemcpyDeviceToHost, h->stream));
+  NLP_CUDA(h, cudaMemcpyAsync(h->h_sel11->bitflags, st->bitflags, sizeof(st->bitflags), cudaMemcpyDeviceToHost, h->stream));
   uint64_t packed = 0;
   if (n) NLP_TRY(exclusive_scan<unsigned long long>(h, (const unsigned long long*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &packed));
   else NLP_CUDA(h, cudaStreamSynchronize(h->stream));
   const uint64_t better = packed >> 32, tie = packed & 0xffffffffull;
   const uint64_t need = h->h_sel11->need;
-  uint64_t need_r = std::min(need, tie), sup = better + tie;     // sup: entries the digit histograms were taken over
+  uint64_t need_r = std::min(need, tie);
   if (dist) {
     // (better, tie) of every rank: ranks with ascending source ranges take the tie class in rank order
     const int W = h->world;
@@ -1667,8 +1670,7 @@ int ordered_top_k(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
     NLP_CUDA(h, cudaMemcpyAsync(all.data(), d_cnt, (size_t)W * 16, cudaMemcpyDeviceToHost, h->stream));
     NLP_CUDA(h, cudaStreamSynchronize(h->stream));
     uint64_t tie_before = 0;
-    sup = 0;
-    for (int r = 0; r < W; ++r) { if (r < h->rank) tie_before += all[2 * r + 1]; sup += all[2 * r] + all[2 * r + 1]; }
+    for (int r = 0; r < h->rank; ++r) tie_before += all[2 * r + 1];
     if (h->part_ordered) need_r = need > tie_before ? std::min<uint64_t>(need - tie_before, tie) : 0;
   }
   const uint64_t m = better + need_r;
@@ -1686,10 +1688,12 @@ int ordered_top_k(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
     NLP_LAUNCHED(h);
     if (!external && !h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
   } else if (external) res = 0;
-  unsigned constant = 0;
-  for (int d = 0; d < 4; ++d)
-    for (int b = 0; b < 256; ++b)
-      if (sup && h->h_sel11->dhist[d][b] == sup) { constant |= 1u << d; break; }
+  unsigned constant = 0;                             // digits of the score key in which no bit varies
+  for (int d = 0; d < 4; ++d) {
+    bool varies = false;
+    for (int b = 8 * d; b < 8 * d + 8; ++b) varies = varies || (h->h_sel11->bitflags[b] && h->h_sel11->bitflags[32 + b]);
+    if (!varies) constant |= 1u << d;
+  }
   uint64_t total = m;
   if (dist) {
     NLP_TRY(gather_candidates(h, res, m, &total));

@@ -427,8 +427,10 @@ struct Select11 {
   unsigned long long bucket;          // pairs in the undecided bucket
   unsigned long long need;            // valid when done: how many of the bucket belong to the result
   uint32_t done, pad;
+  uint32_t key_or, key_nor;           // OR of the survivors' score keys / of their complements: a bit varies iff set in both
+                                      // (the final sort skips the digits in which no bit varies)
   unsigned long long hist[2048];
-  unsigned long long dhist[4][256];   // 8-bit digit histograms of the survivors' score keys (final sort: constant digits are skipped)
+  unsigned long long bitflags[64];    // the same per bit as 0/1 counters, so that several ranks can be SUMMED (NCCL has no OR)
 };
 
 __device__ __forceinline__ int sel11_width(uint32_t bits) { return bits < 22u ? 11 : 10; }
@@ -509,17 +511,18 @@ __global__ void __launch_bounds__(256) k_sel11_step(Select11* st, unsigned long 
   for (int i = tid; i < 2048; i += 256) st->hist[i] = 0;
 }
 
-// Per tile: survivors better than the bucket (high word) and in the bucket (low word), and the
-// 8-bit digit histograms of their keys.
+// Per tile: survivors better than the bucket (high word) and in the bucket (low word); and, over
+// all survivors, which bits of the score key vary (OR of the keys, OR of their complements).
 __global__ void __launch_bounds__(OC_THREADS) k_ordered_count2(const uint32_t* __restrict__ sbits, uint64_t n, Select11* st,
                                                                unsigned long long* __restrict__ tile_counts) {
   __shared__ unsigned long long s_warp[OC_THREADS / 32];
-  __shared__ uint32_t s_d[4][256];
-  for (int i = threadIdx.x; i < 1024; i += OC_THREADS) (&s_d[0][0])[i] = 0;
+  __shared__ uint32_t s_or[2];
+  if (threadIdx.x < 2) s_or[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t prefix = st->prefix, bits = st->bits;
   const uint64_t base = (uint64_t)blockIdx.x * OC_TILE + (uint64_t)threadIdx.x * OC_PER_THREAD;
   unsigned long long c = 0;
+  uint32_t o1 = 0, o0 = 0;
   #pragma unroll
   for (int k = 0; k < OC_PER_THREAD; ++k) {
     if (base + k < n) {
@@ -528,25 +531,34 @@ __global__ void __launch_bounds__(OC_THREADS) k_ordered_count2(const uint32_t* _
       if (cls) {
         c += cls == 1 ? (1ull << 32) : 1ull;
         const uint32_t key = desc_key(s);
-        atomicAdd(&s_d[0][key & 255u], 1u); atomicAdd(&s_d[1][(key >> 8) & 255u], 1u);
-        atomicAdd(&s_d[2][(key >> 16) & 255u], 1u); atomicAdd(&s_d[3][key >> 24], 1u);
+        o1 |= key; o0 |= ~key;
       }
     }
   }
   #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(NLP_FULL, c, d);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  o1 = __reduce_or_sync(NLP_FULL, o1);
+  o0 = __reduce_or_sync(NLP_FULL, o0);
+  if ((threadIdx.x & 31) == 0) {
+    s_warp[threadIdx.x >> 5] = c;
+    if (o1) atomicOr(&s_or[0], o1);
+    if (o0) atomicOr(&s_or[1], o0);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long t = 0;
     #pragma unroll
     for (int w = 0; w < OC_THREADS / 32; ++w) t += s_warp[w];
     tile_counts[blockIdx.x] = t;
+    if (s_or[0]) atomicOr(&st->key_or, s_or[0]);
+    if (s_or[1]) atomicOr(&st->key_nor, s_or[1]);
   }
-  for (int i = threadIdx.x; i < 1024; i += OC_THREADS) {
-    const uint32_t x = (&s_d[0][0])[i];
-    if (x) atomicAdd(&st->dhist[0][0] + i, (unsigned long long)x);
-  }
+}
+
+// key_or / key_nor as 64 counters of 0 / 1 (bit b of key_or -> bitflags[b], of key_nor -> bitflags[32 + b]).
+__global__ void k_sel11_bits(Select11* st) {
+  const int t = threadIdx.x;
+  if (t < 64) st->bitflags[t] = ((t < 32 ? st->key_or >> t : st->key_nor >> (t - 32)) & 1u) ? 1ull : 0ull;
 }
 
 // Survivors in array order: every better pair, and the bucket pairs whose index inside the bucket

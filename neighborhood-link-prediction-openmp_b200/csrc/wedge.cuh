@@ -974,12 +974,12 @@ defer:
 template <bool ADMIT>
 __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltItems items, const uint32_t* __restrict__ list, uint32_t n, int bin,
                                                                   uint32_t* __restrict__ deferred, uint4* __restrict__ rec_all,
-                                                                  uint32_t* __restrict__ dw_all, uint64_t rec_stride) {
+                                                                  double* __restrict__ g_all, uint64_t rec_stride) {
   extern __shared__ float facc[];                     // [RFLT_WARPS][RFLT_WIN]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* acc = facc + (uint32_t)warp * RFLT_WIN;
   uint4* rec = rec_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * rec_stride;
-  uint32_t* dwrow = dw_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * rec_stride;
+  double* grow = g_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * rec_stride;   // per first-hop row: its term g(w)
   const uint32_t* __restrict__ keys = p.g.keys;
   Tally tally;
   for (uint32_t i = lane; i < RFLT_WIN; i += 32) acc[i] = 0.0f;
@@ -1019,7 +1019,7 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltI
           const bool has = i < pc;
           const uint64_t ci = (uint64_t)c * CHUNK + i;
           unsigned long long a = 0;
-          uint32_t cntw = 0, dw = 0;
+          uint32_t cntw = 0;
           double g = 0.0;
           if (has) {
             unsigned long long e;
@@ -1029,8 +1029,9 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltI
               const uint32_t w = __ldg(pb + i);
               const unsigned long long wb = __ldg(p.g.off + w);
               e = __ldg(p.g.off + w + 1);
-              dw = (uint32_t)(e - wb);
-              dwrow[ci] = dw;
+              const uint32_t dw = (uint32_t)(e - wb);
+              g = flt_term(p, dw);                     // inc/predict.hxx:788, 828: a double; kept per row for the later windows
+              grow[ci] = g;
               a = wb + lower_bound_row(keys, wb, dw, vlo);
               next = a < e ? __ldg(keys + a) : 0xffffffffu;
               moved = true;
@@ -1045,8 +1046,7 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltI
               b = vhi >= p.g.S ? e : gallop_to<true>(keys, a, e, vhi);
               next = b < e ? __ldg(keys + b) : 0xffffffffu;
               moved = true;
-              if (!first) dw = dwrow[ci];
-              g = flt_term(p, dw);                     // inc/predict.hxx:788, 828: a double; one per row, computed by its lane
+              if (!first) g = grow[ci];
             }
             if (moved) rec[ci] = range_pack(b, e, next);
             cntw = (uint32_t)(b - a);

@@ -209,14 +209,21 @@ def road_lattice(side, keep=0.6, seed=44, device="cpu"):
 
 
 def web_crawl(n, avg_out=19, alpha=2.1, window=10000, local=0.9, max_out=None, seed=45, device="cpu",
-              chunk=1 << 24):
+              chunk=1 << 24, leaves=False):
     """Web-crawl-shaped graph: power-law out-degrees, ``local`` of the links inside a +-window id
-    range (host locality), the rest to power-law-popular targets (heavy in-degree hubs)."""
+    range (host locality), the rest to power-law-popular targets (heavy in-degree hubs).
+    ``leaves``: two of every five ids are LEAF pages -- 1 to 4 out-links, never a link target -- the
+    low-degree vertices a real crawl is full of (and the only intermediates an LHub threshold of 4
+    admits: without them a graph of average degree ~90 has no vertex of degree <= 4 at all)."""
     ids = torch.arange(n, device=device, dtype=torch.int64)
     r = hash_unit(ids, seed, 1)
     dmin = max(1.0, avg_out * (alpha - 2.0) / (alpha - 1.0))
     out = torch.floor(dmin * (1.0 - r) ** (-1.0 / (alpha - 1.0))).to(torch.int64)
     out = torch.clamp(out, max=max_out if max_out else max(64, n // 50))
+    if leaves:
+        leaf = ((ids % 5) == 1) | ((ids % 5) == 3)
+        out = torch.where(leaf, 1 + (hash_u64(ids, seed, 4) & 3), out)
+        del leaf
     cs = torch.cumsum(out, 0)
     m = int(cs[-1])
     starts = cs - out
@@ -232,6 +239,10 @@ def web_crawl(n, avg_out=19, alpha=2.1, window=10000, local=0.9, max_out=None, s
         pop = torch.floor(n * r2 ** 4.0).to(torch.int64)             # popular targets: low "rank"
         pop = (pop * 0x9E3779B1 + 12345) % n                          # scatter the hubs over ids
         dst = torch.where(r1 < local, near, pop)
+        if leaves:                                                    # leaf pages are never linked to
+            res = dst % 5
+            dst = dst - ((res == 1) | (res == 3)).to(torch.int64)
+            del res
         a, b = src + 1, dst + 1
         key = torch.minimum(a, b) * n1 + torch.maximum(a, b)
         und[s0:s0 + cnt] = torch.where(a != b, key, torch.zeros_like(key))
