@@ -1781,7 +1781,13 @@ int nlp_create(nlp_handle** out, int device) {
   if ((e = cudaMallocHost((void**)&h->h_hist, 12 * 256 * 8)) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_sel, sizeof(SelectState))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost((void**)&h->h_sel11, sizeof(Select11))) != cudaSuccess) return bail("cudaMallocHost", e);
-  if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  {
+    // the big-source detour runs next to k_bucket, whose grid fills the GPU: a higher priority lets
+    // the detour's many small kernels be scheduled as blocks of k_bucket retire instead of after it
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   int rc = NLP_OK;
   if ((rc = ensure(h, h->ctr, sizeof(Counters), true)) || (rc = ensure(h, h->thr, sizeof(Threshold), true)) ||
