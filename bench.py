@@ -525,6 +525,9 @@ def run_b200(args):
         names = ["pair: eligible rows + item descriptors + scans", "pair: k_pair_emit (wedge records)",
                  "pair: radix sort by (u,v) (k_tilehist+k_rowscan+k_scatter per digit)", "pair: k_pair_reduce (run count + exclusion + score)",
                  "-", "-", "-", "select+sort (radix top-K)"]
+    else:
+        names = ["frontier(k_elig+k_work+k_bin)", "hub-heavy sources (k_range / k_range_flt + k_dense)", "k_hash(16K)", "k_hash(4K)", "k_hash(1K)",
+                 "k_tiny<32>", "k_tiny<8>", "select+sort (radix top-K)"]
     phase = [sum(r["phase_ms"][i] for r in results) for i in range(8)]
     nrun = len(results)
     peak, peak_src = peaks()

@@ -1554,19 +1554,27 @@ int global_count(nlp_handle* h, uint64_t mine, uint64_t* sum) {
 
 // All-gather the m local survivors in candidate buffer `buf` (counts first, then ONE padded
 // payload all-gather); afterwards buffer 0 holds the candidates of all ranks in rank order.
-int gather_candidates(nlp_handle* h, int buf, uint64_t m, uint64_t* total) {
+int gather_candidates(nlp_handle* h, int buf, uint64_t m, uint64_t* total, const std::vector<unsigned long long>* known = nullptr) {
   NcclApi* api = nccl_api();
   const int W = h->world;
-  NLP_TRY(ensure(h, h->gcnt, (size_t)(W + 1) * 8));
-  unsigned long long* d_cnt = (unsigned long long*)h->gcnt.p;
-  unsigned long long mine = m;
-  NLP_CUDA(h, cudaMemcpyAsync(d_cnt + W, &mine, 8, cudaMemcpyHostToDevice, h->stream));
-  NLP_NCCL(h, api->AllGather(d_cnt + W, d_cnt, 1, ncclUint64, (ncclComm_t)h->comm, h->stream));
+  if (W > 16) return fail(h, NLP_ERR_ARG, "multi-GPU merge: more than 16 ranks");
   std::vector<unsigned long long> cnt(W);
-  NLP_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 8, cudaMemcpyDeviceToHost, h->stream));
-  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (known) {
+    cnt = *known;                                  // the caller already exchanged what the counts follow from
+  } else {
+    NLP_TRY(ensure(h, h->gcnt, (size_t)(W + 1) * 8));
+    unsigned long long* d_cnt = (unsigned long long*)h->gcnt.p;
+    unsigned long long mine = m;
+    NLP_CUDA(h, cudaMemcpyAsync(d_cnt + W, &mine, 8, cudaMemcpyHostToDevice, h->stream));
+    NLP_NCCL(h, api->AllGather(d_cnt + W, d_cnt, 1, ncclUint64, (ncclComm_t)h->comm, h->stream));
+    NLP_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 8, cudaMemcpyDeviceToHost, h->stream));
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   uint64_t width = 1, sum = 0;
-  for (int r = 0; r < W; ++r) { width = std::max<uint64_t>(width, cnt[r]); sum += cnt[r]; }
+  GatherOffsets go;
+  go.world = W;
+  for (int r = 0; r < W; ++r) { go.off[r] = sum; width = std::max<uint64_t>(width, cnt[r]); sum += cnt[r]; }
+  go.off[W] = sum;
   if (sum >= 0xfffffff0ull) return fail(h, NLP_ERR_CAPACITY, "multi-GPU merge: too many candidates");
   NLP_TRY(ensure(h, h->gsend, (size_t)width * 12));
   NLP_TRY(ensure(h, h->grecv, (size_t)width * 12 * W));
@@ -1578,15 +1586,10 @@ int gather_candidates(nlp_handle* h, int buf, uint64_t m, uint64_t* total) {
   }
   NLP_NCCL(h, api->AllGather(send, h->grecv.p, (size_t)width * 3, ncclUint32, (ncclComm_t)h->comm, h->stream));
   NLP_TRY(ensure_candidates(h, sum));           // may reallocate the candidate buffers: the local survivors are in `send`
-  uint64_t at = 0;
-  for (int r = 0; r < W; ++r) {
-    const uint32_t* src = (const uint32_t*)h->grecv.p + (size_t)r * width * 3;
-    if (cnt[r]) {
-      NLP_CUDA(h, cudaMemcpyAsync((uint32_t*)h->cu[0].p + at, src, cnt[r] * 4, cudaMemcpyDeviceToDevice, h->stream));
-      NLP_CUDA(h, cudaMemcpyAsync((uint32_t*)h->cv[0].p + at, src + width, cnt[r] * 4, cudaMemcpyDeviceToDevice, h->stream));
-      NLP_CUDA(h, cudaMemcpyAsync((uint32_t*)h->cs[0].p + at, src + 2 * width, cnt[r] * 4, cudaMemcpyDeviceToDevice, h->stream));
-    }
-    at += cnt[r];
+  if (sum) {
+    k_gather_unpack<<<grid_for(sum, 256, h->num_sms * 16), 256, 0, h->stream>>>(
+        (const uint32_t*)h->grecv.p, (unsigned long long)width, go, (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+    NLP_LAUNCHED(h);
   }
   *total = sum;
   h->gathered_bytes += (uint64_t)width * 12 * W;
@@ -1647,31 +1650,39 @@ int ordered_top_k(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
     k_ordered_count2<<<ntiles, OC_THREADS, 0, h->stream>>>(sbits, n, st, (unsigned long long*)h->oc_counts.p);
     NLP_LAUNCHED(h);
   }
-  k_sel11_bits<<<1, 64, 0, h->stream>>>(st);          // which bits of the survivors' keys vary, as counters ...
-  NLP_LAUNCHED(h);
-  if (api) NLP_NCCL(h, api->AllReduce(st->bitflags, st->bitflags, 64, ncclUint64, ncclSum, (ncclComm_t)h->comm, h->stream));   // ... over all ranks
   NLP_CUDA(h, cudaMemcpyAsync(h->h_sel11, st, offsetof(Select11, hist), cudaMemcpyDeviceToHost, h->stream));
-  NLP_CUDA(h, cudaMemcpyAsync(h->h_sel11->bitflags, st->bitflags, sizeof(st->bitflags), cudaMemcpyDeviceToHost, h->stream));
   uint64_t packed = 0;
   if (n) NLP_TRY(exclusive_scan<unsigned long long>(h, (const unsigned long long*)h->oc_counts.p, ntiles, (unsigned long long*)h->oc_off.p, &packed));
   else NLP_CUDA(h, cudaStreamSynchronize(h->stream));
   const uint64_t better = packed >> 32, tie = packed & 0xffffffffull;
   const uint64_t need = h->h_sel11->need;
   uint64_t need_r = std::min(need, tie);
+  uint32_t key_or = h->h_sel11->key_or, key_nor = h->h_sel11->key_nor;   // which bits of the survivors' keys vary
+  std::vector<unsigned long long> counts;
   if (dist) {
-    // (better, tie) of every rank: ranks with ascending source ranges take the tie class in rank order
+    // ONE small exchange: (better, tie, key bits) of every rank.  Ranks with ascending source ranges
+    // take the tie class in rank order; everybody can then compute every rank's survivor count.
     const int W = h->world;
-    NLP_TRY(ensure(h, h->gcnt, (size_t)(2 * W + 2) * 8));
+    NLP_TRY(ensure(h, h->gcnt, (size_t)(4 * W + 4) * 8));
     unsigned long long* d_cnt = (unsigned long long*)h->gcnt.p;
-    unsigned long long mine[2] = {better, tie};
-    NLP_CUDA(h, cudaMemcpyAsync(d_cnt + 2 * W, mine, 16, cudaMemcpyHostToDevice, h->stream));
-    NLP_NCCL(h, api->AllGather(d_cnt + 2 * W, d_cnt, 2, ncclUint64, (ncclComm_t)h->comm, h->stream));
-    std::vector<unsigned long long> all(2 * W);
-    NLP_CUDA(h, cudaMemcpyAsync(all.data(), d_cnt, (size_t)W * 16, cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long mine[4] = {better, tie, key_or, key_nor};
+    NLP_CUDA(h, cudaMemcpyAsync(d_cnt + 4 * W, mine, 32, cudaMemcpyHostToDevice, h->stream));
+    NLP_NCCL(h, api->AllGather(d_cnt + 4 * W, d_cnt, 4, ncclUint64, (ncclComm_t)h->comm, h->stream));
+    std::vector<unsigned long long> all(4 * W);
+    NLP_CUDA(h, cudaMemcpyAsync(all.data(), d_cnt, (size_t)W * 32, cudaMemcpyDeviceToHost, h->stream));
     NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+    counts.resize(W);
     uint64_t tie_before = 0;
-    for (int r = 0; r < h->rank; ++r) tie_before += all[2 * r + 1];
-    if (h->part_ordered) need_r = need > tie_before ? std::min<uint64_t>(need - tie_before, tie) : 0;
+    key_or = 0; key_nor = 0;
+    for (int r = 0; r < W; ++r) {
+      const uint64_t b = all[4 * r], t = all[4 * r + 1];
+      uint64_t nr = std::min<uint64_t>(need, t);
+      if (h->part_ordered) nr = need > tie_before ? std::min<uint64_t>(need - tie_before, t) : 0;
+      if (r == h->rank) need_r = nr;
+      counts[r] = b + nr;
+      tie_before += t;
+      key_or |= (uint32_t)all[4 * r + 2]; key_nor |= (uint32_t)all[4 * r + 3];
+    }
   }
   const uint64_t m = better + need_r;
   // Survivors go to buffer `ob`.  When the records live in candidate buffer `ob` themselves (no
@@ -1689,14 +1700,12 @@ int ordered_top_k(nlp_handle* h, uint64_t K, int* out_buf, uint64_t* out_n) {
     if (!external && !h->pair_from_cache) std::swap(h->cs[0], h->cs[1]);
   } else if (external) res = 0;
   unsigned constant = 0;                             // digits of the score key in which no bit varies
-  for (int d = 0; d < 4; ++d) {
-    bool varies = false;
-    for (int b = 8 * d; b < 8 * d + 8; ++b) varies = varies || (h->h_sel11->bitflags[b] && h->h_sel11->bitflags[32 + b]);
-    if (!varies) constant |= 1u << d;
-  }
+  const uint32_t varying = key_or & key_nor;
+  for (int d = 0; d < 4; ++d)
+    if (((varying >> (8 * d)) & 255u) == 0u) constant |= 1u << d;
   uint64_t total = m;
   if (dist) {
-    NLP_TRY(gather_candidates(h, res, m, &total));
+    NLP_TRY(gather_candidates(h, res, m, &total, &counts));
     res = 0;
     if (!h->part_ordered) return top_k(h, 0, total, K, out_buf, out_n);
   }

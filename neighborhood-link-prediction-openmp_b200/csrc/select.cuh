@@ -606,4 +606,22 @@ __global__ void __launch_bounds__(OC_THREADS) k_ordered_write2(const uint32_t* _
   }
 }
 
+
+// Multi-GPU: the all-gather delivers every rank's survivors as [rank][3][width] words (u, v, score
+// bits, padded to the widest rank); one pass packs them into contiguous (u, v, score) arrays in
+// rank order.  off[r] = survivors of the ranks before r (off[W] = total), passed by value.
+struct GatherOffsets { unsigned long long off[17]; int world; };
+
+__global__ void __launch_bounds__(256) k_gather_unpack(const uint32_t* __restrict__ recv, unsigned long long width, GatherOffsets g,
+                                                       uint32_t* __restrict__ ou, uint32_t* __restrict__ ov, uint32_t* __restrict__ os) {
+  const unsigned long long total = g.off[g.world];
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    int r = 0;
+    while (r + 1 < g.world && g.off[r + 1] <= i) ++r;
+    const unsigned long long k = i - g.off[r];
+    const uint32_t* src = recv + (unsigned long long)r * width * 3ull;
+    ou[i] = src[k]; ov[i] = src[width + k]; os[i] = src[2ull * width + k];
+  }
+}
+
 }  // namespace nlp
