@@ -92,7 +92,7 @@ struct nlp_handle {
   uint64_t cand_cap = 0;
   // dense spill tables
   DevBuf tables, touched, range_cursors, range_touched;
-  DevBuf flt_cnt, flt_off, flt_items, flt_ids, flt_defer;   // k_range_flt: (source, window range) items
+  DevBuf flt_cnt, flt_off, flt_items, flt_ids, flt_defer, flt_tlist;   // k_range_flt: (source, window range) items
   FltItems flt_it{nullptr, nullptr, nullptr};
   uint64_t flt_n = 0;
   // select / sort scratch
@@ -605,8 +605,9 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
     const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n + RFLT_WARPS - 1) / RFLT_WARPS, (uint64_t)h->num_sms);
     NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * RFLT_WARPS * stride * 16));
     NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * RFLT_WARPS * stride * 8));
+    NLP_TRY(ensure(h, h->flt_tlist, (size_t)h->num_sms * RFLT_WARPS * RFLT_WIN * 4));
     k_range_flt<ADMIT><<<grid, RFLT_WARPS * 32, smem, h->stream>>>(p, h->flt_it, list, n, 6, deferred, (uint4*)h->range_cursors.p,
-                                                                   (double*)h->range_touched.p, stride);
+                                                                   (double*)h->range_touched.p, stride, (uint32_t*)h->flt_tlist.p);
     NLP_LAUNCHED(h);
     return NLP_OK;
   }
@@ -1836,7 +1837,7 @@ int nlp_destroy(nlp_handle* h) {
   for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
-  release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->flt_cnt); release(h->flt_off); release(h->flt_items); release(h->flt_ids); release(h->flt_defer); release(h->counts); release(h->totals); release(h->hist);
+  release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->flt_cnt); release(h->flt_off); release(h->flt_items); release(h->flt_ids); release(h->flt_defer); release(h->flt_tlist); release(h->counts); release(h->totals); release(h->hist);
   release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
   release(h->truth_key); release(h->truth_tmp); release(h->eval_ctr);
   release(h->bt_d); release(h->bt_uat); release(h->bt_hit); release(h->bt_jump[0]); release(h->bt_jump[1]);

@@ -974,12 +974,17 @@ defer:
 template <bool ADMIT>
 __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltItems items, const uint32_t* __restrict__ list, uint32_t n, int bin,
                                                                   uint32_t* __restrict__ deferred, uint4* __restrict__ rec_all,
-                                                                  double* __restrict__ g_all, uint64_t rec_stride) {
+                                                                  double* __restrict__ g_all, uint64_t rec_stride, uint32_t* __restrict__ tlist_all) {
   extern __shared__ float facc[];                     // [RFLT_WARPS][RFLT_WIN]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* acc = facc + (uint32_t)warp * RFLT_WIN;
   uint4* rec = rec_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * rec_stride;
   double* grow = g_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * rec_stride;   // per first-hop row: its term g(w)
+  // vertices of the current window that have a sum, in the order they were first reached: scoring
+  // walks this list with all lanes busy instead of scanning the window (12 % of it is touched at
+  // R-MAT 18), and only these accumulators need clearing
+  uint32_t* tlist = tlist_all + ((uint64_t)blockIdx.x * RFLT_WARPS + warp) * RFLT_WIN;
+  const unsigned lt = (1u << lane) - 1u;
   const uint32_t* __restrict__ keys = p.g.keys;
   Tally tally;
   for (uint32_t i = lane; i < RFLT_WIN; i += 32) acc[i] = 0.0f;
@@ -1011,6 +1016,7 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltI
       const uint32_t vlo = (uint32_t)lo64;
       const uint32_t vhi = (uint32_t)(lo64 + RFLT_WIN < p.g.S ? lo64 + RFLT_WIN : p.g.S);
       const bool first = win == w0;                    // the item's first window: the rows are bisected, later windows continue
+      uint32_t tn = 0;                                 // entries of tlist (warp-uniform)
       for (uint32_t c = 0; c < f.npieces; ++c) {
         const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
         const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
@@ -1074,13 +1080,20 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltI
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (rr[j] < 0) break;                    // warp-uniform
-              if ((uint32_t)lane < cr[j]) {
-                const uint32_t x = kv[j] - vlo;
-                acc[x] = __double2float_rn(__dadd_rn((double)acc[x], gr[j]));
-              }
-              for (uint32_t k = 32u + lane; k < cr[j]; k += 32) {
-                const uint32_t x = __ldg(keys + ar[j] + k) - vlo;
-                acc[x] = __double2float_rn(__dadd_rn((double)acc[x], gr[j]));
+              for (uint32_t k0 = 0; k0 < cr[j]; k0 += 32) {      // warp-uniform trip count
+                const uint32_t k = k0 + lane;
+                bool fresh = false;
+                uint32_t v = 0;
+                if (k < cr[j]) {
+                  v = k0 == 0 ? kv[j] : __ldg(keys + ar[j] + k);
+                  const uint32_t x = v - vlo;
+                  const float old = acc[x];
+                  acc[x] = __double2float_rn(__dadd_rn((double)old, gr[j]));
+                  fresh = old == 0.0f;                 // first wedge that reaches this vertex: list it
+                }
+                const unsigned fm = __ballot_sync(NLP_FULL, fresh);
+                if (fresh) tlist[tn + __popc(fm & lt)] = v;
+                tn += __popc(fm);
               }
               __syncwarp();                            // the next row may reach the same vertices
             }
@@ -1096,18 +1109,19 @@ __global__ void __launch_bounds__(RFLT_WARPS * 32, 1) k_range_flt(Params p, FltI
         }
         __syncwarp();
       }
-      const uint32_t len = vhi - vlo;
-      for (uint32_t sb = 0; sb < len; sb += 32) {      // score the touched vertices, clear the window
+      __syncwarp();
+      for (uint32_t sb = 0; sb < tn; sb += 32) {       // score the touched vertices and clear their accumulators
         const uint32_t i = sb + lane;
+        const bool has = i < tn;
+        uint32_t v = 0;
         float val = 0.0f;
-        bool has = false;
-        if (i < len) {
-          val = acc[i];
-          has = val != 0.0f;
-          if (has) acc[i] = 0.0f;
+        if (has) {
+          v = tlist[i];
+          val = acc[v - vlo];
+          acc[v - vlo] = 0.0f;
           if (val < 0.0f) val = 0.0f;                  // touched, then zeroed: a candidate with value 0
         }
-        emitted += score_and_emit(p, has, u, du, vlo + i, 0u, val, tally);
+        emitted += score_and_emit(p, has, u, du, v, 0u, val, tally);
       }
       __syncwarp();
     }
