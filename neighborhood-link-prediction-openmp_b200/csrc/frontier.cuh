@@ -117,33 +117,6 @@ __global__ void __launch_bounds__(256) k_validate_entries(DevGraph g, uint64_t M
   }
 }
 
-__global__ void __launch_bounds__(256) k_max_multiplicity(DevGraph g, uint64_t M, unsigned int* __restrict__ out) {
-  const uint32_t* __restrict__ keys = g.keys;
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  uint32_t best = 1;
-  for (uint64_t base = warp0 * 32u; base < M; base += nwarps * 32u) {
-    uint32_t lo = 0, hi = g.S;                       // off[lo] <= base < off[hi]
-    while (lo + 1 < hi) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (__ldg(g.off + mid) <= base) lo = mid; else hi = mid;
-    }
-    const uint64_t e = base + lane;
-    if (e >= M) continue;
-    uint32_t u = lo;
-    while (__ldg(g.off + u + 1) <= e) ++u;
-    const uint64_t ub = __ldg(g.off + u), ue = __ldg(g.off + u + 1);
-    const uint32_t w = __ldg(keys + e);
-    if (e > ub && __ldg(keys + e - 1) == w) continue;          // measured at the first entry of the run
-    uint32_t mult = 1;
-    while (e + mult < ue && __ldg(keys + e + mult) == w) ++mult;
-    best = mult > best ? mult : best;
-  }
-  best = __reduce_max_sync(NLP_FULL, best);
-  if (lane == 0 && best > 1u) atomicMax(out, best);
-}
-
 // One thread builds one 32-bit word of the mask.
 __global__ void __launch_bounds__(256) k_elig(const uint32_t* __restrict__ deg, uint32_t S, uint32_t D,
                                               uint32_t* __restrict__ bits) {

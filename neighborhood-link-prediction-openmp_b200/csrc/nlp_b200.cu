@@ -1186,24 +1186,11 @@ int pair_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* out_b
 
 // Sources of k_range with deg(u) below the returned limit may count in half words: a count is at
 // most deg(u) x (largest multiplicity of an entry in a row) and must stay below 2^15.  The
-// multiplicity is measured once per graph, the first time the range path is about to be used.
+// multiplicity is measured by the validation pass when the graph is set (k_validate_entries).
 int half_word_limit(nlp_handle* h, bool range_on, uint32_t* limit) {
   *limit = 0;
   if (!range_on || !h->range_half) return NLP_OK;
-  if (h->maxmult == 0) {
-    NLP_TRY(ensure(h, h->sym_flag, 32));
-    NLP_CUDA(h, cudaMemsetAsync((char*)h->sym_flag.p + 24, 0, 8, h->stream));
-    if (h->M) {
-      k_max_multiplicity<<<grid_for(h->M, 256, h->num_sms * 16), 256, 0, h->stream>>>(dev_graph(h), h->M,
-                                                                                       (unsigned int*)((char*)h->sym_flag.p + 24));
-      NLP_LAUNCHED(h);
-    }
-    unsigned int mm = 0;
-    NLP_CUDA(h, cudaMemcpyAsync(&mm, (char*)h->sym_flag.p + 24, 4, cudaMemcpyDeviceToHost, h->stream));
-    NLP_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->maxmult = mm > 1u ? mm : 1u;
-  }
-  *limit = 32768u / h->maxmult;
+  *limit = 32768u / (h->maxmult > 1u ? h->maxmult : 1u);   // the multiplicity comes from the validation pass of nlp_set_graph
   return NLP_OK;
 }
 

@@ -428,9 +428,8 @@ struct Select11 {
   unsigned long long need;            // valid when done: how many of the bucket belong to the result
   uint32_t done, pad;
   uint32_t key_or, key_nor;           // OR of the survivors' score keys / of their complements: a bit varies iff set in both
-                                      // (the final sort skips the digits in which no bit varies)
+                                      // (the final sort skips the digits in which no bit varies; several ranks OR theirs on the host)
   unsigned long long hist[2048];
-  unsigned long long bitflags[64];    // the same per bit as 0/1 counters, so that several ranks can be SUMMED (NCCL has no OR)
 };
 
 __device__ __forceinline__ int sel11_width(uint32_t bits) { return bits < 22u ? 11 : 10; }
@@ -553,12 +552,6 @@ __global__ void __launch_bounds__(OC_THREADS) k_ordered_count2(const uint32_t* _
     if (s_or[0]) atomicOr(&st->key_or, s_or[0]);
     if (s_or[1]) atomicOr(&st->key_nor, s_or[1]);
   }
-}
-
-// key_or / key_nor as 64 counters of 0 / 1 (bit b of key_or -> bitflags[b], of key_nor -> bitflags[32 + b]).
-__global__ void k_sel11_bits(Select11* st) {
-  const int t = threadIdx.x;
-  if (t < 64) st->bitflags[t] = ((t < 32 ? st->key_or >> t : st->key_nor >> (t - 32)) & 1u) ? 1ull : 0ull;
 }
 
 // Survivors in array order: every better pair, and the bucket pairs whose index inside the bucket
