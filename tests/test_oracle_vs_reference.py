@@ -51,3 +51,35 @@ def test_topk_scores_equal_reference_openmp(oracle, measure):
     for a, b, c in zip(ru, rv, rs.view(np.uint32)):
         assert lookup[(int(a), int(b))] == int(c)
     assert t >= ts >= 0.0
+
+
+def test_tie_straddling_cutoff_bounds_f1_difference(oracle):
+    """INTEGRATION.md, "Ties": with integer-valued common-neighbour scores the K-th score sits in
+    a large tie class; the reference keeps whichever tied pairs its heap saw last
+    (inc/predict.hxx:332), the canonical order keeps the smallest (u, v).  Pin what that can change:
+    both lists agree on every pair scored above the cutoff, hold the same number of pairs AT the
+    cutoff score, and so precision / recall (main.cxx:201-202) differ by at most the number of tied
+    pairs in the list over the list sizes."""
+    import nlp_b200 as N
+    g = N.graphs
+    off0, keys0 = g.planted_partition(1500, 30, 8, 2, 91)
+    off, keys, lo, hi = g.remove_edges(off0, keys0, 0.1, 92)
+    offn, keysn = g.to_numpy(off, keys)
+    lo, hi = lo.numpy(), hi.numpy()
+    K = len(lo)
+    S = len(offn) - 1
+    R = oracle.RefGraph(offn, keysn)
+    ru, rv, rs, _, _ = R.predict("CN", 0, max_edges=K, omp=False, canonical=False)
+    cu, cv, cs, _ = oracle.oracle_predict(offn, keysn, "CN", 0, max_edges=K)
+    assert len(ru) == len(cu) == K
+    cut = float(cs[-1])
+    assert float(rs.min()) == cut
+    tied = int((cs == cut).sum())
+    assert tied > 1 and int((rs == cut).sum()) == tied          # the cutoff really straddles a tie class
+    above_r = set(zip(ru[rs > cut].tolist(), rv[rs > cut].tolist()))
+    above_c = set(zip(cu[cs > cut].tolist(), cv[cs > cut].tolist()))
+    assert above_r == above_c
+    truth = set(zip(lo.tolist(), hi.tolist()))
+    hit_r = sum((a, b) in truth for a, b in zip(ru.tolist(), rv.tolist()))
+    hit_c = sum((a, b) in truth for a, b in zip(cu.tolist(), cv.tolist()))
+    assert abs(hit_r - hit_c) <= tied                             # precision = recall = hits / K here (K predictions, K removed)
