@@ -105,3 +105,29 @@ def test_cfg2_rmat22_nine_measures_against_compiled_reference(nlp, oracle):
         if R is not None:
             R.close()
         p.close()
+
+
+def test_cfg3_road24m_lhub_ihub_against_oracle(nlp, oracle):
+    """configs[2]: the low-degree road / mesh graph at its stated size (4900 x 4900 lattice, 24 M
+    vertices, average degree 2.4), 0.1 |E| removed with the reference sampler: LHub D = 4 (bucket
+    path) and IHub (sub-warp tiny-neighbourhood kernels), Jaccard + common neighbours + Adamic-Adar,
+    full lists and counters against the C oracle."""
+    g = nlp.graphs
+    off, keys = g.road_lattice(4900, 0.6, 44, device="cuda")
+    assert off.numel() - 1 == 4900 * 4900 + 1
+    p = nlp.Predictor(0)
+    try:
+        o2, k2, du, dv, batch = _removed(nlp, p, off, keys, 0.1)
+        del off, keys
+        K = du.size // 2
+        assert K > 2_000_000, K
+        o2n, k2n = g.to_numpy(o2, k2)
+        S = len(o2n) - 1
+        p.set_graph_pointers(o2.data_ptr(), k2.data_ptr(), S, device=True, keep=(o2, k2))
+        for D in (4, 0):
+            for m in ("JC", "CN", "AA"):
+                err, r, st = parity.check_case(p, oracle, o2n, k2n, m, D, K, tag="cfg3")
+                assert err is None, err
+                assert r["path"] == (2 if D else 1)
+    finally:
+        p.close()
