@@ -351,6 +351,8 @@ def run_b200(args):
             o = h_out[i % 2]
             pred.fetch_async(o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n)
 
+    e2e_marks = []
+
     def one_step_e2e():
         # One batch of the harness, host buffers in, host results out (main.cxx:164-169 + 208-221): back to
         # the base graph (resident since it was loaded, as main.cxx's x; nlp_graph_rollback = duplicate(x)),
@@ -364,6 +366,7 @@ def run_b200(args):
             fetch_results(i, n)
             edges += n
         pred.fetch_wait()
+        e2e_marks.append(time.perf_counter())
         return edges
 
     def one_step_upload():
@@ -459,10 +462,22 @@ def run_b200(args):
         pred.graph_checkpoint()
         for _ in range(max(1, min(args.warmup, 2))):
             one_step_e2e()
+        # PCIe probe (explains run-to-run spread of the end-to-end figure: the step moves 0.5 GB to the host)
+        pe0 = torch.cuda.Event(enable_timing=True); pe1 = torch.cuda.Event(enable_timing=True)
+        probe_src = torch.empty(K, dtype=torch.int32, device=dev)
+        h_out[0][0].copy_(probe_src, non_blocking=True); torch.cuda.synchronize()
+        pe0.record(); h_out[0][0].copy_(probe_src, non_blocking=True); pe1.record(); torch.cuda.synchronize()
+        d2h_gbps = 4 * K / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+        del probe_src
+        del e2e_marks[:]
+        e2e_marks.append(time.perf_counter())
         e_edges, e_ms, e_wall, _ = timed(one_step_e2e, args.steps)
+        gaps = sorted((b - a) * 1e3 for a, b in zip(e2e_marks[-args.steps - 1:-1], e2e_marks[-args.steps:]))
         copies = 1 if shard in ("none",) else world      # every rank receives the batch
         e2e = {"value": e_edges / (e_ms / 1e3), "unit": "edges/s", "h2d_bytes_per_step": 8 * int(h_du.numel()) * copies,
                "d2h_bytes_per_step": int(e_edges / args.steps) * 12, "ms_per_step": e_ms / args.steps,
+               "host_ms_per_step_min_median_max": [round(gaps[0], 2), round(gaps[len(gaps) // 2], 2), round(gaps[-1], 2)] if gaps else None,
+               "pinned_d2h_probe_gbps": round(d2h_gbps, 1),
                "step": "nlp_graph_rollback to the resident base graph, H2D of the batch's %d directed deletions from pinned memory, nlp_apply_deletions "
                        "(CSR rebuilt on the device), %d predictions, every (u, v, score) list fetched to pinned host memory" % (int(h_du.numel()), len(measures))}
         if args.e2e_upload:

@@ -484,15 +484,8 @@ __device__ __forceinline__ bool row_contains_k4(const uint32_t* __restrict__ key
 // run, BK_NONE where there is no pair, BK_DONE where the score is already in al_s (big sources).
 // exclude = false: the counts already went through the exclusion (reuse store, nlp_set_reuse);
 // capture: write the count after the exclusion back (it is about to be stored).
-// One round of the quaternary search (see row_contains_k4) on the range [lo, hi) of row `ub`.
-__device__ __forceinline__ void k4_round(const uint32_t* __restrict__ keys, uint64_t ub, uint32_t v, uint32_t& lo, uint32_t& hi) {
-  const uint32_t q = (hi - lo) >> 2;
-  const uint32_t m1 = lo + q, m2 = lo + 2u * q, m3 = lo + 3u * q;
-  const uint32_t k1 = __ldg(keys + ub + m1), k2 = __ldg(keys + ub + m2), k3 = __ldg(keys + ub + m3);
-  if (k2 < v) { if (k3 < v) lo = m3 + 1u; else { lo = m2 + 1u; hi = m3 + 1u; } }
-  else        { if (k1 < v) { lo = m1 + 1u; hi = m2 + 1u; } else hi = m1 + 1u; }
-}
-
+// (A two-slots-per-thread variant with interleaved searches measured 0.9 ms per step SLOWER on
+// BASELINE configs[1] -- profiles/r02_summary.md -- and was dropped.)
 template <bool FLT>
 __global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restrict__ al_u, const uint32_t* __restrict__ al_v,
                                                uint32_t* al_c, uint32_t* __restrict__ al_s,
@@ -503,58 +496,28 @@ __global__ void __launch_bounds__(256) k_score(Params p, const uint32_t* __restr
   for (int i = threadIdx.x; i < 2048; i += 256) s_h[i] = 0;
   __syncthreads();
   Tally tally;
-  const uint32_t* __restrict__ keys = p.g.keys;
-  const uint64_t n = hi - lo;
-  const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
-  // TWO slots per thread and iteration (t and t + G): the searches in row u are chains of dependent
-  // loads (ncu: half of the stall samples of the one-slot version sat in the search), and two
-  // independent chains per thread hide each other's latency.
-  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += 2 * G) {
-    uint64_t idx[2] = {lo + t, lo + t + G};
-    bool in[2] = {true, t + G < n};
-    uint32_t c[2], u[2] = {0, 0}, v[2] = {0, 0}, cnt[2] = {0, 0}, du[2] = {0, 0}, slo[2] = {0, 0}, shi[2] = {0, 0};
-    uint64_t ub[2] = {0, 0};
-    float acc[2] = {0.0f, 0.0f};
-    bool head[2];
-    #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      c[k] = in[k] ? al_c[idx[k]] : BK_DONE;
-      head[k] = c[k] != BK_NONE && c[k] != BK_DONE;
+  const uint64_t n = hi - lo, n32 = (n + 31u) & ~31ull;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n32; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = lo + t;
+    const uint32_t c = t < n ? al_c[i] : BK_DONE;
+    const bool head = c != BK_NONE && c != BK_DONE;
+    uint32_t u = 0, v = 0, cnt = 0;
+    uint64_t du = 0;
+    float acc = 0.0f;
+    if (head) {
+      u = al_u[i]; v = al_v[i];
+      if (FLT) acc = __uint_as_float(c); else cnt = c;
+      const uint64_t ub = __ldg(p.g.off + u);
+      du = __ldg(p.g.deg + u);
+      if (exclude && row_contains_k4(p.g.keys, ub, (uint32_t)du, v)) { cnt = 0; acc = 0.0f; }
+      if (!FLT && capture) al_c[i] = cnt;              // the reuse store keeps the count after the exclusion
     }
-    #pragma unroll
-    for (int k = 0; k < 2; ++k)
-      if (head[k]) { u[k] = al_u[idx[k]]; v[k] = al_v[idx[k]]; }
-    #pragma unroll
-    for (int k = 0; k < 2; ++k)
-      if (head[k]) {
-        if (FLT) acc[k] = __uint_as_float(c[k]); else cnt[k] = c[k];
-        ub[k] = __ldg(p.g.off + u[k]);
-        du[k] = __ldg(p.g.deg + u[k]);
-        shi[k] = exclude ? du[k] : 0u;               // search range [slo, shi) in row u
-      }
-    while (shi[0] - slo[0] > 4u || shi[1] - slo[1] > 4u) {
-      #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if (shi[k] - slo[k] > 4u) k4_round(keys, ub[k], v[k], slo[k], shi[k]);
-    }
-    #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      bool found = false;
-      #pragma unroll
-      for (uint32_t i = 0; i < 4u; ++i)
-        if (slo[k] + i < shi[k]) found |= __ldg(keys + ub[k] + slo[k] + i) == v[k];
-      if (found) { cnt[k] = 0; acc[k] = 0.0f; }     // existing edge: the slot stays, with value 0
-      if (!FLT && capture && head[k]) al_c[idx[k]] = cnt[k];    // the reuse store keeps the count after the exclusion
-    }
-    #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      float score;
-      const bool keep = score_pair(p, head[k], u[k], (uint64_t)du[k], v[k], cnt[k], acc[k], tally, &score);
-      uint32_t sb = keep ? __float_as_uint(score) : NLP_NO_SCORE;
-      if (c[k] != BK_DONE) al_s[idx[k]] = sb;
-      else if (in[k]) sb = al_s[idx[k]];             // big source: scored by k_pair_reduce already
-      if (sb != NLP_NO_SCORE) atomicAdd(&s_h[desc_key(sb) >> 21], 1u);
-    }
+    float score;
+    const bool keep = score_pair(p, head, u, du, v, cnt, acc, tally, &score);
+    uint32_t sb = keep ? __float_as_uint(score) : NLP_NO_SCORE;
+    if (c != BK_DONE) al_s[i] = sb;
+    else if (t < n) sb = al_s[i];                      // big source: scored by k_pair_reduce already
+    if (sb != NLP_NO_SCORE) atomicAdd(&s_h[desc_key(sb) >> 21], 1u);
   }
   tally.flush(p.ctr);
   __syncthreads();

@@ -68,6 +68,7 @@ struct Params {
   uint32_t F2;         // MAXFACTOR2
   uint32_t coop;       // count measures: block-cooperative wedge streaming (maxdeg small enough)
   uint32_t range_half; // k_range: sources with deg < range_half count in half words (windows twice as wide); 0 = never
+  uint32_t range_quarter; // ... and those with deg < range_quarter in bytes (four times as wide); 0 = never
   int      measure;
   float    min_score;
   const uint32_t* elig;     // LHub eligibility bitmask (bit w = deg(w) <= D), null for IHub

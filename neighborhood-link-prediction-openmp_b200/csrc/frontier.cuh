@@ -309,7 +309,7 @@ struct BinLists { uint32_t* list[NBINS]; };
 // range_c: counters per window of k_range (0 = that path is off, e.g. for the float measures,
 // whose hub-heavy sources go to the dense spill tables); room = S-1-u
 __device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_t du, uint32_t range_c, uint32_t range_fixed,
-                                          uint32_t range_div, uint32_t half_deg, uint32_t room) {
+                                          uint32_t range_div, uint32_t half_deg, uint32_t quarter_deg, uint32_t room) {
   if (du <= LONG_ROW) {
     if (work <= 8u) return 0;
     if (work <= 32u) return 1;
@@ -323,8 +323,9 @@ __device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_
     // atomic, R-MAT 18/20 IHub).  range_fixed + du / range_div is the cost of one window of one
     // source (count measures: 256 + du / NLP_B200_RANGE_DIV; float measures, whose windows are
     // one warp's 1664 accumulators: 32 + du / 4).
-    // Sources with deg < half_deg count in half words: their windows are twice as wide.
-    const unsigned long long rc = (unsigned long long)range_c << (du < half_deg ? 1 : 0);
+    // Sources with deg < half_deg count in half words: their windows are twice as wide (deg <
+    // quarter_deg: bytes, four times).
+    const unsigned long long rc = (unsigned long long)range_c << (du < quarter_deg ? 2 : (du < half_deg ? 1 : 0));
     const unsigned long long passes = ((unsigned long long)room + rc - 1) / rc;
     if ((unsigned long long)work >= passes * ((unsigned long long)range_fixed + du / range_div)) return 6;
   }
@@ -332,7 +333,7 @@ __device__ __forceinline__ int choose_bin(uint32_t work, uint32_t bound, uint32_
 }
 
 __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long long* __restrict__ work64, int rank, int world,
-                                             uint32_t range_c, uint32_t range_fixed, uint32_t range_div, uint32_t half_deg, uint32_t* __restrict__ work, BinLists bl,
+                                             uint32_t range_c, uint32_t range_fixed, uint32_t range_div, uint32_t half_deg, uint32_t quarter_deg, uint32_t* __restrict__ work, BinLists bl,
                                              Counters* ctr) {
   __shared__ unsigned long long s_cnt[NBINS], s_sum[NBINS], s_base[NBINS], s_max;
   const int lane = threadIdx.x & 31;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) { bin = choose_bin(w, bound, g.deg[u], range_c, range_fixed, range_div, half_deg, room); need = bin < 2 ? w : bound; }
+        if (bound) { bin = choose_bin(w, bound, g.deg[u], range_c, range_fixed, range_div, half_deg, quarter_deg, room); need = bin < 2 ? w : bound; }
       }
     }
     #pragma unroll
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(256) k_bin(DevGraph g, const unsigned long lon
       if (w) {
         const uint32_t room = g.S - 1u - (uint32_t)u;
         const uint32_t bound = w < room ? w : room;
-        if (bound) bin = choose_bin(w, bound, g.deg[u], range_c, range_fixed, range_div, half_deg, room);
+        if (bound) bin = choose_bin(w, bound, g.deg[u], range_c, range_fixed, range_div, half_deg, quarter_deg, room);
       }
     }
     #pragma unroll

@@ -92,6 +92,12 @@ struct nlp_handle {
   uint64_t cand_cap = 0;
   // dense spill tables
   DevBuf tables, touched, range_cursors, range_touched;
+  DevBuf fence_slot, fence_tab;              // k_range: fence tables of the long rows (per graph, built at first use)
+  bool fence_valid = false;
+  uint32_t fence_ncell = 0;
+  uint64_t fence_rows = 0;
+  int range_fence = 1;                       // NLP_B200_RANGE_FENCE=0: no fence tables
+  int range_quarter = 1;                     // NLP_B200_RANGE_QUARTER=0: no byte counters
   DevBuf flt_cnt, flt_off, flt_items, flt_ids, flt_defer, flt_tlist;   // k_range_flt: (source, window range) items
   FltItems flt_it{nullptr, nullptr, nullptr};
   uint64_t flt_n = 0;
@@ -396,6 +402,7 @@ int finish_graph(nlp_handle* h, bool trusted = false, int known_sym = 0) {
   h->pair_sizes.clear();
   clear_pair_cache(h);
   clear_plans(h);
+  h->fence_valid = false;
   NLP_TRY(measure_budget(h));
   h->has_graph = true;
   h->has_result = false;
@@ -594,11 +601,50 @@ int launch_dense(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
 // Count measures: hub-heavy sources on windowed shared-memory counters (k_range).
 constexpr uint32_t RANGE_COUNTERS = 52 * 1024;      // 208 KB of u32 counters per block (+13 KB static)
 
+// Fence tables of the rows that are long against the number of window cells (wedge.cuh, range_batch):
+// fence[c] = first position of the row with key >= c * RANGE_COUNTERS.  A row gets one when it holds
+// at least two entries per cell, so all tables together take at most 2 bytes per entry of the graph.
+int ensure_fences(nlp_handle* h) {
+  if (h->fence_valid) return NLP_OK;
+  const uint32_t S = h->S;
+  const uint32_t ncell = (uint32_t)(((uint64_t)S + RANGE_COUNTERS - 1) / RANGE_COUNTERS);
+  h->fence_ncell = ncell;
+  h->fence_rows = 0;
+  h->fence_valid = true;
+  uint32_t min_deg = std::max<uint32_t>(2u * ncell, 64u);
+  if (!h->range_fence || !S || h->maxdeg < min_deg) return NLP_OK;
+  const DevGraph g = dev_graph(h);
+  NLP_TRY(ensure(h, h->fence_slot, (size_t)S * 4));
+  DevBuf tmp;
+  NLP_TRY(ensure(h, tmp, (size_t)S * 8));
+  uint64_t rows = 0;
+  for (int attempt = 0; attempt < 8; ++attempt, min_deg *= 2u) {
+    k_fence_mark<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, min_deg, (uint32_t*)h->fence_slot.p);
+    NLP_LAUNCHED(h);
+    const int rc = exclusive_scan<uint32_t>(h, (const uint32_t*)h->fence_slot.p, S, (unsigned long long*)tmp.p, &rows);
+    if (rc != NLP_OK) { release(tmp); return rc; }
+    if (rows * (uint64_t)(ncell + 1u) * 4u <= h->budget_base / 8) break;
+    rows = 0;
+  }
+  if (rows) {
+    const int rc = ensure(h, h->fence_tab, (size_t)rows * (ncell + 1u) * 4u);
+    if (rc != NLP_OK) { release(tmp); return rc; }
+    k_fence_fill<<<grid_for((uint64_t)S * 32, 256, h->num_sms * 16), 256, 0, h->stream>>>(g, min_deg, RANGE_COUNTERS, ncell,
+                                                                                            (const unsigned long long*)tmp.p,
+                                                                                            (uint32_t*)h->fence_slot.p, (uint32_t*)h->fence_tab.p);
+    NLP_LAUNCHED(h);
+    NLP_CUDA(h, cudaStreamSynchronize(h->stream));      // tmp is freed below
+  }
+  release(tmp);
+  h->fence_rows = rows;
+  return NLP_OK;
+}
+
 template <bool FLT, bool ADMIT>
 int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t n, uint32_t* deferred) {
   if (!n) return NLP_OK;
   const uint64_t stride = ((uint64_t)h->maxdeg + CHUNK + 31) / 32 * 32;
-  if (FLT) {
+  if constexpr (FLT) {
     // one warp per source: per-warp row records (16 B) + deg(w) of every first-hop row
     const size_t smem = (size_t)RFLT_WARPS * RFLT_WIN * 4;
     NLP_CUDA(h, cudaFuncSetAttribute(k_range_flt<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -610,19 +656,25 @@ int launch_range(nlp_handle* h, const Params& p, const uint32_t* list, uint32_t 
                                                                    (double*)h->range_touched.p, stride, (uint32_t*)h->flt_tlist.p);
     NLP_LAUNCHED(h);
     return NLP_OK;
-  }
+  } else {
+  NLP_TRY(ensure_fences(h));
+  RangeFences fx;
+  fx.slot_of = h->fence_rows ? (const uint32_t*)h->fence_slot.p : nullptr;
+  fx.fence = (const uint32_t*)h->fence_tab.p;
+  fx.ncell = h->fence_ncell;
   const size_t smem = (size_t)RANGE_COUNTERS * 4;
   NLP_CUDA(h, cudaFuncSetAttribute(k_range<ADMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms);
   // per block: row cursor + row end for every first-hop entry of its current source
   NLP_TRY(ensure(h, h->range_cursors, (size_t)h->num_sms * 2 * stride * 8));
-  // per block: the vertices of its current window that have a count (at most 2 * RANGE_COUNTERS)
-  NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * 2 * RANGE_COUNTERS * 4));
-  k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, list, n, 6, deferred, RANGE_COUNTERS,
+  // per block: the vertices of its current window that have a count (at most 4 * RANGE_COUNTERS)
+  NLP_TRY(ensure(h, h->range_touched, (size_t)h->num_sms * 4 * RANGE_COUNTERS * 4));
+  k_range<ADMIT><<<grid, RANGE_THREADS, smem, h->stream>>>(p, fx, list, n, 6, deferred, RANGE_COUNTERS,
                                                            (unsigned long long*)h->range_cursors.p, stride,
                                                            (uint32_t*)h->range_touched.p);
   NLP_LAUNCHED(h);
   return NLP_OK;
+  }
 }
 
 template <bool FLT>
@@ -1263,8 +1315,9 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   }
   uint32_t half_deg = 0;
   NLP_TRY(half_word_limit(h, range_c != 0u && !FLT, &half_deg));
+  const uint32_t quarter_deg = (half_deg && h->range_quarter) ? 128u / (h->maxmult > 1u ? h->maxmult : 1u) : 0u;
   k_bin<<<grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(g, (const unsigned long long*)h->work64.p, h->rank, h->world,
-                                                                  range_c, range_fixed, range_div, half_deg, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
+                                                                  range_c, range_fixed, range_div, half_deg, quarter_deg, (uint32_t*)h->work.p, bl, (Counters*)h->ctr.p);
   NLP_LAUNCHED(h);
   NLP_CUDA(h, cudaEventRecord(h->ev_frontier, h->stream));
   NLP_TRY(read_counters(h));
@@ -1340,6 +1393,7 @@ int scoring_pass(nlp_handle* h, const nlp_options* opt, nlp_result* res, int* ou
   p.g = g; p.D = opt->min_degree1; p.F2 = opt->max_factor2; p.measure = opt->measure; p.min_score = opt->min_score;
   p.coop = (h->maxdeg < (1u << 22) && h->coop_mode != 0) ? 1u : 0u;
   p.range_half = half_deg;
+  p.range_quarter = quarter_deg;
   p.elig = lhub ? (const uint32_t*)h->elig.p : nullptr;
   p.ekeys = lhub ? (const uint32_t*)h->ekeys.p : nullptr;
   p.ecount = lhub ? (const uint32_t*)h->ecount.p : nullptr;
@@ -1747,6 +1801,8 @@ int nlp_create(nlp_handle** out, int device) {
   h->device = device;
   if (const char* e = getenv("NLP_B200_RANGE")) h->range_mode = atoi(e);   // experiment knobs
   if (const char* e = getenv("NLP_B200_RANGE_HALF")) h->range_half = atoi(e);
+  if (const char* e = getenv("NLP_B200_RANGE_QUARTER")) h->range_quarter = atoi(e);
+  if (const char* e = getenv("NLP_B200_RANGE_FENCE")) h->range_fence = atoi(e);
   if (const char* e = getenv("NLP_B200_RANGE_DIV")) h->range_div = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("NLP_B200_RANGE_FLT")) h->flt_range_mode = atoi(e);
   if (const char* e = getenv("NLP_B200_COOP")) h->coop_mode = atoi(e);
@@ -1783,6 +1839,7 @@ int nlp_create(nlp_handle** out, int device) {
     // the detour's many small kernels be scheduled as blocks of k_bucket retire instead of after it
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (const char* pe = getenv("NLP_B200_DETOUR_PRIORITY")) if (atoi(pe) == 0) hi = lo;
     if ((e = cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
   }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
@@ -1824,7 +1881,7 @@ int nlp_destroy(nlp_handle* h) {
   for (int b = 0; b < NBINS; ++b) { release(h->list[b]); release(h->defer[b]); }
   release(h->gtable); release(h->ctr); release(h->thr);
   for (int b = 0; b < 2; ++b) { release(h->cu[b]); release(h->cv[b]); release(h->cs[b]); }
-  release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->flt_cnt); release(h->flt_off); release(h->flt_items); release(h->flt_ids); release(h->flt_defer); release(h->flt_tlist); release(h->counts); release(h->totals); release(h->hist);
+  release(h->tables); release(h->touched); release(h->range_cursors); release(h->range_touched); release(h->fence_slot); release(h->fence_tab); release(h->flt_cnt); release(h->flt_off); release(h->flt_items); release(h->flt_ids); release(h->flt_defer); release(h->flt_tlist); release(h->counts); release(h->totals); release(h->hist);
   release(h->sel); release(h->cursor2); release(h->oc_counts); release(h->oc_off);
   release(h->truth_key); release(h->truth_tmp); release(h->eval_ctr);
   release(h->bt_d); release(h->bt_uat); release(h->bt_hit); release(h->bt_jump[0]); release(h->bt_jump[1]);

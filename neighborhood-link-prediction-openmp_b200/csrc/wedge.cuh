@@ -662,63 +662,99 @@ __device__ __forceinline__ unsigned long long gallop_to(const uint32_t* __restri
   return hi;
 }
 
-// HALF: two 16-bit counters per word (see k_range); the halves cannot carry into each other
-// because a count never exceeds deg(u) < 2^15.
-template <bool HALF>
+// PACK counters per 32-bit word (1, 2 or 4; see k_range): the fields cannot carry into each other
+// because a count never reaches the field's top bit, which is the "touched, then zeroed" mark.
+template <int PACK> struct RangeField {
+  static constexpr uint32_t BITS = 32u / PACK, SHIFT = PACK == 4 ? 2u : (PACK == 2 ? 1u : 0u);
+  static constexpr uint32_t MASK = PACK == 1 ? 0xffffffffu : ((1u << BITS) - 1u);
+  static constexpr uint32_t MARK = 1u << (BITS - 1u), VALUE = MARK - 1u;
+};
+
+template <int PACK>
 __device__ __forceinline__ bool range_count(uint32_t* cnt, uint32_t x) {   // true: first wedge that reaches this vertex
-  if (HALF) {
-    const uint32_t sh = (x & 1u) * 16u;
-    return ((atomicAdd(cnt + (x >> 1), 1u << sh) >> sh) & 0xffffu) == 0u;
-  }
-  return atomicAdd(cnt + x, 1u) == 0u;                // inc/predict.hxx:156-158
+  typedef RangeField<PACK> F;
+  if (PACK == 1) return atomicAdd(cnt + x, 1u) == 0u;   // inc/predict.hxx:156-158
+  const uint32_t sh = (x & (uint32_t)(PACK - 1)) * F::BITS;
+  return ((atomicAdd(cnt + (x >> F::SHIFT), 1u << sh) >> sh) & F::MASK) == 0u;
 }
 
 // Wedges behind up to RANGE_THREADS first-hop entries (thread t holds entry t) whose v lies in
-// [vlo, vhi): counter[v - vlo] += 1.  The window parts of all rows are laid end to end and dealt
+// [vlo, vhi): counter[v - wbase] += 1.  The window parts of all rows are laid end to end and dealt
 // to the threads of the WHOLE block, so one hub row among the entries is shared by 1024 threads
 // instead of stalling the one warp that drew it (ncu: 54 % of the first version's stall samples
 // sat at the barrier behind such warps).
-// rec[] (global scratch of this block, one 16-byte record per first-hop entry: position, entries
-// left, key at the position) carries every row from window to window: the first window finds the
-// first key > u by bisection, later windows read the record (one coalesced 16-byte load) and
-// know from the cached key whether the row has anything in the window at all -- at R-MAT 22 a
-// hub source walks 80 windows and two thirds of its (row, window) visits find nothing, and those
-// now cost neither a dependent key load nor a store.
+//
+// Windows are ALIGNED to multiples of the cell size C (window j of a source that packs PACK
+// counters per word covers the cells [j * PACK, (j + 1) * PACK)), so where the part of a row in a
+// window begins and ends does not depend on the source.  Long rows carry a fence table, built once
+// per graph (k_fence_fill): fence[c] = first position of the row whose key is >= c * C.  A visit
+// of such a row costs two independent loads.  At R-MAT 24 a hub-heavy source walks 80-320 windows
+// and the hub rows hold most of the wedges: the gallop of the first version (22 dependent loads
+// per visit of a 4e5-entry row) was the critical path of every window.
+// Short rows keep a 16-byte record in rec[] (position, entries left, key at the position), carried
+// from window to window: the first window finds the first key > u by bisection, later windows
+// read the record and know from the cached key whether the row has anything in the window at all.
+constexpr uint32_t RANGE_FENCED = 0x80000000u;
+
 __device__ __forceinline__ uint4 range_pack(unsigned long long pos, unsigned long long e, uint32_t next) {
   return make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), (uint32_t)(e - pos), next);
 }
 
-template <bool HALF>
-__device__ __forceinline__ void range_batch(const Params& p, bool has, bool first, uint32_t w, uint32_t vlo, uint32_t vhi,
+struct RangeFences {
+  const uint32_t* slot_of;   // [S] fence-table slot of a row, 0xffffffff = none (null: no tables at all)
+  const uint32_t* fence;     // [slots][ncell + 1]
+  uint32_t ncell;
+};
+
+template <int PACK>
+__device__ __forceinline__ void range_batch(const Params& p, const RangeFences& fx, bool has, bool first, uint32_t w,
+                                            uint32_t u, uint32_t cell0, uint32_t wbase, uint32_t vhi,
                                             uint4* rec, uint32_t* cnt, uint32_t* touched, uint32_t* s_tn,
                                             uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum) {
   const uint32_t* __restrict__ keys = p.g.keys;
   unsigned long long a = 0;
   uint32_t dw = 0;
   if (has) {
-    unsigned long long e;
-    uint32_t next;
-    bool moved = false;
+    const uint32_t cell1 = cell0 + (uint32_t)PACK < fx.ncell ? cell0 + (uint32_t)PACK : fx.ncell;
     if (first) {
       const unsigned long long wb = __ldg(p.g.off + w);
-      e = __ldg(p.g.off + w + 1);
-      a = wb + lower_bound_row(keys, wb, (uint32_t)(e - wb), vlo);
-      next = a < e ? __ldg(keys + a) : 0xffffffffu;
-      moved = true;
+      const unsigned long long e = __ldg(p.g.off + w + 1);
+      const uint32_t fs = fx.slot_of ? __ldg(fx.slot_of + w) : 0xffffffffu;
+      if (fs != 0xffffffffu) {
+        const uint32_t* f = fx.fence + (uint64_t)fs * (fx.ncell + 1u);
+        const uint32_t s0 = __ldg(f + cell0), s1 = __ldg(f + cell1);
+        a = wb + s0 + lower_bound_row(keys, wb + s0, s1 - s0, u + 1u);
+        dw = (uint32_t)(wb + s1 - a);
+        *rec = make_uint4((uint32_t)wb, (uint32_t)(wb >> 32), RANGE_FENCED | fs, 0u);
+      } else {
+        a = wb + lower_bound_row(keys, wb, (uint32_t)(e - wb), u + 1u);
+        uint32_t next = a < e ? __ldg(keys + a) : 0xffffffffu;
+        unsigned long long b = a;
+        if (next < vhi) {
+          b = vhi >= p.g.S ? e : gallop_to<true>(keys, a, e, vhi);
+          next = b < e ? __ldg(keys + b) : 0xffffffffu;
+        }
+        *rec = range_pack(b, e, next);
+        dw = (uint32_t)(b - a);
+      }
     } else {
       const uint4 r = *rec;
-      a = (unsigned long long)r.x | ((unsigned long long)r.y << 32);
-      e = a + r.z;
-      next = r.w;
+      const unsigned long long pos = (unsigned long long)r.x | ((unsigned long long)r.y << 32);
+      if (r.z & RANGE_FENCED) {
+        const uint32_t* f = fx.fence + (uint64_t)(r.z & ~RANGE_FENCED) * (fx.ncell + 1u);
+        const uint32_t s0 = __ldg(f + cell0), s1 = __ldg(f + cell1);
+        a = pos + s0;
+        dw = s1 - s0;
+      } else {
+        a = pos;
+        if (r.w < vhi) {                                // the row has entries in this window (so r.z > 0)
+          const unsigned long long e = a + r.z;
+          const unsigned long long b = vhi >= p.g.S ? e : gallop_to<true>(keys, a, e, vhi);
+          *rec = range_pack(b, e, b < e ? __ldg(keys + b) : 0xffffffffu);
+          dw = (uint32_t)(b - a);
+        }
+      }
     }
-    unsigned long long b = a;
-    if (next < vhi) {                                 // the row has entries in this window (so a < e)
-      b = vhi >= p.g.S ? e : gallop_to<true>(keys, a, e, vhi);
-      next = b < e ? __ldg(keys + b) : 0xffffffffu;
-      moved = true;
-    }
-    if (moved) *rec = range_pack(b, e, next);
-    dw = (uint32_t)(b - a);
   }
   s_wb[threadIdx.x] = a;
   block_scan_u32(dw, s_inc, s_wsum);                  // k_range is only used when 1024 * maxdeg < 2^32
@@ -726,6 +762,9 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, bool firs
   // row of the first, the others follow by walking s_inc forward.  (A bisection per wedge, the
   // first version, made this loop ~100 instructions per wedge and the whole kernel issue bound:
   // ncu, R-MAT 18 IHub, 69 % issue slots busy at 360 warp instructions per atomic instruction.)
+  // Two variants measured slower at R-MAT 22 IHub and were dropped (profiles/r02_summary.md): one
+  // warp-aggregated append to touched[] per step instead of an atomic per first touch (+8 %), and
+  // a separate warp-coalesced pass over the long row parts (+43 %: two phases, two tails).
   const uint32_t tot = s_inc[RANGE_THREADS - 1];
   for (uint32_t c0 = threadIdx.x * (uint32_t)RANGE_RUN; c0 < tot; c0 += RANGE_THREADS * (uint32_t)RANGE_RUN) {
     uint32_t lo = 0, hi = RANGE_THREADS - 1;          // smallest j with s_inc[j] > c0
@@ -753,30 +792,37 @@ __device__ __forceinline__ void range_batch(const Params& p, bool has, bool firs
       for (int k = 0; k < 4; ++k) v[k] = (c0 + (uint32_t)(h + k) < tot) ? __ldg(keys + addr[k]) : 0u;
       #pragma unroll
       for (int k = 0; k < 4; ++k)     // the first wedge that reaches a vertex also lists it for the scoring phase
-        if (c0 + (uint32_t)(h + k) < tot && range_count<HALF>(cnt, v[k] - vlo)) touched[atomicAdd(s_tn, 1u)] = v[k];
+        if (c0 + (uint32_t)(h + k) < tot && range_count<PACK>(cnt, v[k] - wbase)) touched[atomicAdd(s_tn, 1u)] = v[k];
     }
   }
   __syncthreads();
 }
 
-// All windows of one source.  HALF = 16-bit counters, two per word, so a window spans 2 * C
-// vertices and the source needs half the windows (half the (row, window) visits): valid while no
-// count can reach 2^15.  A count is at most deg(u) x (largest multiplicity of an entry in a row),
-// so the host allows it for deg(u) < 2^15 / that multiplicity (Params::range_half; the reference
-// counts entries, and rows may be multisets).  Bit 15 of a half is the "touched, then zeroed"
-// mark.  Returns what this thread emitted.
-template <bool HALF>
-__device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, uint64_t ub, uint32_t du, const FirstHop& f,
+// All windows of one source.  PACK = 2: 16-bit counters, two per word, so a window spans 2 * C
+// vertices and the source needs half the windows (half the (row, window) visits); PACK = 4: 8-bit
+// counters, a quarter of the windows.  Valid while no count can reach the field's top bit: a count
+// is at most deg(u) x (largest multiplicity of an entry in a row), so the host allows PACK = 2 for
+// deg(u) < 2^15 / that multiplicity and PACK = 4 for deg(u) < 2^7 / that multiplicity
+// (Params::range_half, range_quarter; the reference counts entries, and rows may be multisets).
+// The top bit of a field is the "touched, then zeroed" mark.  Returns what this thread emitted.
+template <int PACK>
+__device__ __forceinline__ uint32_t range_source(const Params& p, const RangeFences& fx, uint32_t u, uint64_t ub, uint32_t du, const FirstHop& f,
                                                  uint32_t C, uint4* rec, uint32_t* cnt, uint32_t* touched, uint32_t* s_tn,
                                                  uint32_t* s_inc, unsigned long long* s_wb, uint32_t* s_wsum, Tally& tally) {
+  typedef RangeField<PACK> F;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const uint32_t* __restrict__ keys = p.g.keys;
-  const uint32_t span = HALF ? 2u * C : C;            // vertices per window
+  const uint64_t span = (uint64_t)PACK * C;            // vertices per window
   uint32_t emitted = 0;
-  for (uint64_t lo64 = (uint64_t)u + 1; lo64 < p.g.S; lo64 += span) {
-    const uint32_t vlo = (uint32_t)lo64;
-    const uint32_t vhi = (uint32_t)(lo64 + span < p.g.S ? lo64 + span : p.g.S);
-    const bool first = lo64 == (uint64_t)u + 1;
+  // N(u) is walked along with the windows (every thread keeps the same cursor): xa = first entry of
+  // row u not below the current window, xnext = its key
+  uint32_t xa = lower_bound_row(keys, ub, du, u + 1u);
+  uint32_t xnext = xa < du ? __ldg(keys + ub + xa) : 0xffffffffu;
+  bool first = true;
+  for (uint64_t j = ((uint64_t)u + 1) / span; j * span < p.g.S; ++j, first = false) {
+    const uint32_t wbase = (uint32_t)(j * span);
+    const uint32_t vhi = (uint32_t)((j + 1) * span < p.g.S ? (j + 1) * span : p.g.S);
+    const uint32_t cell0 = (uint32_t)j * (uint32_t)PACK;
     for (uint32_t c = 0; c < f.npieces; ++c) {
       const uint32_t pc = f.npieces == 1 ? f.single_count : __ldg(f.piece_cnt + c);
       const uint32_t* pb = f.base + (uint64_t)c * CHUNK;
@@ -784,31 +830,32 @@ __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, ui
         const uint32_t i = base + tid;
         const bool has = i < pc;
         const uint64_t ci = (uint64_t)c * CHUNK + i;
-        range_batch<HALF>(p, has, first, (has && first) ? __ldg(pb + i) : 0u, vlo, vhi, rec + ci, cnt, touched, s_tn, s_inc, s_wb, s_wsum);
+        range_batch<PACK>(p, fx, has, first, (has && first) ? __ldg(pb + i) : 0u, u, cell0, wbase, vhi, rec + ci, cnt, touched, s_tn, s_inc, s_wb, s_wsum);
       }
     }
-    {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
-      const uint32_t a = lower_bound_row(keys, ub, du, vlo);
-      const uint32_t b = a + lower_bound_row(keys, ub + a, du - a, vhi);
+    if (xnext < vhi) {   // exclusion of N(u) inside the window (inc/predict.hxx:307)
+      const uint32_t a = xa;
+      const uint32_t b = vhi >= p.g.S ? du : (uint32_t)(gallop_to<true>(keys, ub + a, ub + du, vhi) - ub);
       for (uint32_t i = a + tid; i < b; i += blockDim.x) {
-        const uint32_t x = __ldg(keys + ub + i) - vlo;
-        if (HALF) {   // neighbours share words: atomics, one half each
-          const uint32_t sh = (x & 1u) * 16u;
-          if ((cnt[x >> 1] >> sh) & 0xffffu) {
-            atomicAnd(cnt + (x >> 1), ~(0x7fffu << sh));
-            atomicOr(cnt + (x >> 1), 0x8000u << sh);
+        const uint32_t x = __ldg(keys + ub + i) - wbase;
+        if (PACK > 1) {   // neighbours share words: atomics, one field each
+          const uint32_t sh = (x & (uint32_t)(PACK - 1)) * F::BITS;
+          if ((cnt[x >> F::SHIFT] >> sh) & F::MASK) {
+            atomicAnd(cnt + (x >> F::SHIFT), ~(F::VALUE << sh));
+            atomicOr(cnt + (x >> F::SHIFT), F::MARK << sh);
           }
         } else {
           if (cnt[x] != 0u) cnt[x] = RANGE_ZEROED;
         }
       }
+      xa = b;
+      xnext = b < du ? __ldg(keys + ub + b) : 0xffffffffu;
     }
     __syncthreads();
     // Scoring walks the list of touched vertices (appended by the first wedge that reached each),
     // 32 at a time with all lanes busy, and reads the count back from the counter.  (Scanning the
     // window's counters instead -- 12 % of them touched at R-MAT 18 IHub -- was a third of the
     // kernel's instructions, and scoring straight from the scan, 4 of 32 lanes busy, 60 %: ncu.)
-    // The window's counters are cleared together afterwards.
     {
       const uint32_t tn = *s_tn;
       for (uint32_t sb = (uint32_t)warp * 32u; sb < tn; sb += (uint32_t)nw * 32u) {
@@ -817,15 +864,20 @@ __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, ui
         uint32_t v = 0, c = 0;
         if (has) {
           v = __ldcg(touched + i);
-          const uint32_t x = v - vlo;
-          c = HALF ? ((cnt[x >> 1] >> ((x & 1u) * 16u)) & 0x7fffu) : (cnt[x] & ~RANGE_ZEROED);
+          const uint32_t x = v - wbase;
+          c = PACK == 1 ? (cnt[x] & ~RANGE_ZEROED) : ((cnt[x >> F::SHIFT] >> ((x & (uint32_t)(PACK - 1)) * F::BITS)) & F::VALUE);
         }
         emitted += score_and_emit(p, has, u, du, v, c, 0.0f, tally);
       }
       __syncthreads();                                                      // every warp has read its counts
-      const uint32_t len = vhi - vlo;
-      const uint32_t slots = HALF ? (len + 1u) >> 1 : len;
-      for (uint32_t i = tid; i < slots; i += blockDim.x) cnt[i] = 0u;
+      // clear: through the touched list when the window is sparsely hit (at R-MAT 24 a window sees a
+      // few thousand wedges for 53 248 words), else the whole window
+      const uint32_t slots = (vhi - wbase + (uint32_t)PACK - 1u) >> F::SHIFT;
+      if (tn < (slots >> 2)) {
+        for (uint32_t i = tid; i < tn; i += blockDim.x) cnt[(__ldcg(touched + i) - wbase) >> F::SHIFT] = 0u;
+      } else {
+        for (uint32_t i = tid; i < slots; i += blockDim.x) cnt[i] = 0u;
+      }
       if (tid == 0) *s_tn = 0u;
     }
     __syncthreads();
@@ -834,12 +886,12 @@ __device__ __forceinline__ uint32_t range_source(const Params& p, uint32_t u, ui
 }
 
 template <bool ADMIT>
-__global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint32_t* __restrict__ list, uint32_t n, int bin,
+__global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, RangeFences fx, const uint32_t* __restrict__ list, uint32_t n, int bin,
                                                              uint32_t* __restrict__ deferred, uint32_t C,
                                                              unsigned long long* __restrict__ cursors, uint64_t cursor_stride,
                                                              uint32_t* __restrict__ touched_all) {
-  extern __shared__ uint32_t cnt[];                   // C counters (or 2 * C half-word counters)
-  uint32_t* touched = touched_all + (uint64_t)blockIdx.x * 2u * C;          // vertices of the current window with a count
+  extern __shared__ uint32_t cnt[];                   // C words: C, 2 * C or 4 * C counters
+  uint32_t* touched = touched_all + (uint64_t)blockIdx.x * 4u * C;          // vertices of the current window with a count
   uint4* rec = reinterpret_cast<uint4*>(cursors + (uint64_t)blockIdx.x * 2 * cursor_stride);   // [cursor_stride] row records
   __shared__ unsigned long long s_wb[RANGE_THREADS];
   __shared__ uint32_t s_inc[RANGE_THREADS];
@@ -871,9 +923,10 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
     const uint64_t ub = __ldg(p.g.off + u);
     const uint32_t du = (uint32_t)(__ldg(p.g.off + u + 1) - ub);
     const FirstHop f = first_hop(p, u, ub, du);
-    const uint32_t emitted = du < p.range_half
-        ? range_source<true>(p, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally)
-        : range_source<false>(p, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally);
+    uint32_t emitted;
+    if (du < p.range_quarter)   emitted = range_source<4>(p, fx, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally);
+    else if (du < p.range_half) emitted = range_source<2>(p, fx, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally);
+    else                        emitted = range_source<1>(p, fx, u, ub, du, f, C, rec, cnt, touched, &s_tn, s_inc, s_wb, s_wsum, tally);
     if (ADMIT) {
       if (lane == 0 && emitted) atomicAdd(&s_emitted, emitted);
       __syncthreads();
@@ -887,6 +940,33 @@ __global__ void __launch_bounds__(RANGE_THREADS, 1) k_range(Params p, const uint
   tally.flush(p.ctr);
 }
 
+// Fence tables of the long rows (see range_batch): one warp per listed row, lanes over the cells.
+__global__ void __launch_bounds__(256) k_fence_mark(DevGraph g, uint32_t min_deg, uint32_t* __restrict__ flag) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < g.S; w += (uint64_t)gridDim.x * blockDim.x)
+    flag[w] = g.deg[w] >= min_deg ? 1u : 0u;
+}
+
+// scan[] = exclusive scan of the marks (slot of a marked row); rows that are not marked get
+// slot 0xffffffff, marked rows fill their table.
+__global__ void __launch_bounds__(256) k_fence_fill(DevGraph g, uint32_t min_deg, uint32_t C, uint32_t ncell,
+                                                    const unsigned long long* __restrict__ scan,
+                                                    uint32_t* __restrict__ slot_of, uint32_t* __restrict__ fence) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t w = warp; w < g.S; w += nwarps) {
+    const uint32_t dw = g.deg[w];
+    const bool marked = dw >= min_deg;
+    const uint32_t slot = (uint32_t)scan[w];
+    if (lane == 0) slot_of[w] = marked ? slot : 0xffffffffu;
+    if (!marked) continue;
+    const uint64_t wb = g.off[w];
+    uint32_t* f = fence + (uint64_t)slot * (ncell + 1u);
+    for (uint32_t c = lane; c <= ncell; c += 32) {
+      const uint64_t x = (uint64_t)c * C;
+      f[c] = x >= g.S ? dw : lower_bound_row(g.keys, wb, dw, (uint32_t)x);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Range path of the FLOAT measures (Adamic-Adar, resource allocation), hub-heavy sources.

@@ -262,12 +262,15 @@ def _hub_graph(nlp, n=250_000, hubs=6, hub_deg=3000, bg_deg=5, seed=71):
     return nlp.graphs.to_numpy(*nlp.graphs.csr_from_pairs(torch.cat(a), torch.cat(b), n))
 
 
-@pytest.mark.parametrize("half", ["1", "0", "multiset"])
+@pytest.mark.parametrize("half", ["1", "0", "multiset", "nofence", "noquarter"])
 def test_hub_heavy_sources_windowed_counters(nlp, oracle, monkeypatch, half):
     """k_range (hub-heavy sources on windowed shared-memory counters): several windows per source,
-    word counters and half-word counters (NLP_B200_RANGE_HALF), IHub and LHub (first-hop lists cut
+    word, half-word and byte counters (NLP_B200_RANGE_HALF / _QUARTER), long rows through their fence
+    tables and through cursor records (NLP_B200_RANGE_FENCE), IHub and LHub (first-hop lists cut
     into pieces), against the oracle."""
     monkeypatch.setenv("NLP_B200_RANGE_HALF", "0" if half == "0" else "1")
+    monkeypatch.setenv("NLP_B200_RANGE_FENCE", "0" if half == "nofence" else "1")
+    monkeypatch.setenv("NLP_B200_RANGE_QUARTER", "0" if half == "noquarter" else "1")
     off, keys = _hub_graph(nlp)
     if half == "multiset":     # rows with repeated entries: counts exceed the simple-graph bound, the
         import torch           # half-word limit must follow the largest multiplicity (3 here)

@@ -1,7 +1,7 @@
-"""Where the end-to-end step goes (bench.py's `e2e` leg): host timings, with a device
-synchronize on both sides, of each C-ABI call of one step on the default workload.
+"""Where the end-to-end step goes (bench.py's `e2e` leg): host timings, with a device synchronize
+on both sides, of each C-ABI call of the batch loop on the default workload, for several steps.
 
-    python tools/e2e_breakdown.py [workload] [D]
+    python tools/e2e_breakdown.py [workload] [D] [steps]
 """
 import json
 import os
@@ -18,31 +18,35 @@ import nlp_b200 as N   # noqa: E402
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "rmat22"
     D = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 8
     pred = N.Predictor(0)
-    off, keys, K, info, _, _ = bench.build_workload(name, "cuda:0", pred=pred)
+    off, keys, K, info, (du, dv), _ = bench.build_workload(name, "cuda:0", pred=pred)
+    base = bench.BASE_GRAPH["graph"]
     S = int(off.numel() - 1)
-    h_off = off.cpu().pin_memory(); h_keys = keys.cpu().pin_memory()
-    out = [torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(3)]
+    h_du = du.cpu().pin_memory(); h_dv = dv.cpu().pin_memory()
+    out = [[torch.empty(K, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.empty(K, dtype=torch.float32).pin_memory()] for _ in range(2)]
+    pred.set_graph_pointers(base[0].data_ptr(), base[1].data_ptr(), S, device=True, keep=base)
+    pred.graph_checkpoint()
 
     def t(fn):
         torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
-        return (time.perf_counter() - t0) * 1e3, r
+        return round((time.perf_counter() - t0) * 1e3, 3), r
 
     rows = []
-    for rep in range(3):
-        ms_set, _ = t(lambda: pred.set_graph_pointers(h_off.data_ptr(), h_keys.data_ptr(), S, device=False, keep=(h_off, h_keys)))
-        ms_first, r = t(lambda: pred.predict("CN", D, max_edges=K))
-        ms_second, r2 = t(lambda: pred.predict("JC", D, max_edges=K))
-        ms_fetch, _ = t(lambda: pred.fetch_into(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), r2["count"]))
+    for rep in range(steps):
+        row = {}
+        row["rollback_ms"], _ = t(pred.graph_rollback)
+        row["apply_ms"], _ = t(lambda: pred.apply_deletions(pointers=(h_du.data_ptr(), h_dv.data_ptr(), int(h_du.numel()))))
         per = {}
-        for m in ("SI", "SC", "HP", "HD", "LHN", "AA", "RA"):
-            ms_m, rm = t(lambda: pred.predict(m, D, max_edges=K))
-            per[m] = [round(ms_m, 3), round(rm["time_ms"], 3), rm["path"]]
-        rows.append({"set_graph_ms": ms_set, "first_predict_ms": ms_first, "first_predict_device_ms": r["time_ms"],
-                     "second_predict_ms": ms_second, "second_predict_device_ms": r2["time_ms"], "fetch_ms": ms_fetch,
-                     "rest_host_ms_device_ms_path": per, "first_path": r["path"],
-                     "h2d_GBps": ((S + 1) * 8 + keys.numel() * 4) / ms_set / 1e6, "d2h_GBps": r2["count"] * 12 / ms_fetch / 1e6})
-    print(json.dumps({"workload": name, "D": D, "K": K, "reps": rows}))
+        for i, m in enumerate(N.MEASURES):
+            ms, r = t(lambda: pred.predict(m, D, max_edges=K))
+            o = out[i % 2]
+            fms, _ = t(lambda: pred.fetch_into(o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), r["count"]))
+            per[m] = [ms, round(r["time_ms"], 3), fms]
+        row["predict_host_ms__device_ms__fetch_ms"] = per
+        row["sum_ms"] = round(row["rollback_ms"] + row["apply_ms"] + sum(v[0] + v[2] for v in per.values()), 2)
+        rows.append(row)
+    print(json.dumps({"workload": name, "D": D, "K": K, "deletions": int(h_du.numel()), "steps": rows}))
 
 
 if __name__ == "__main__":

@@ -1,7 +1,7 @@
 """Hot CUDA source lines of one kernel in an .ncu-rep (stall samples and executed instructions per
 line; needs -lineinfo and --import-source on).  Read here with `ncu -i`, no GPU needed.
 
-    python tools/ncu_hotlines.py report.ncu-rep kernel-regex [top]
+    python tools/ncu_hotlines.py report.ncu-rep kernel-regex [top] [launches to skip]
 """
 import csv
 import subprocess
@@ -11,8 +11,9 @@ import sys
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+    skip = sys.argv[4] if len(sys.argv) > 4 else "0"      # launches of that kernel to skip in the report
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv",
-                          "--kernel-name", "regex:" + kern, "--launch-count", "1"], capture_output=True, text=True).stdout
+                          "--kernel-name", "regex:" + kern, "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     acc, fname = [], None
     for r in rows:
