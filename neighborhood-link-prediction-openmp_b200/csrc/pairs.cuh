@@ -239,7 +239,9 @@ __global__ void __launch_bounds__(256) k_pair_reduce(Params p, const uint32_t* _
       if (!FLT && cnt_out) cnt_out[i] = head ? cnt : 0xffffffffu;
     }
   }
-  tally.flush(p.ctr);
+  // with cnt_out the caller scores these pairs again from the counts (k_score, reuse store) and the
+  // candidate / kept counters are taken there -- counting here as well would count them twice
+  if (FLT || !cnt_out) tally.flush(p.ctr);
 }
 
 }  // namespace nlp
