@@ -274,6 +274,24 @@ int nlp_graph_rollback(nlp_handle* h);
 int nlp_graph_size(nlp_handle* h, uint32_t* span, uint64_t* entries);
 int nlp_fetch_graph(nlp_handle* h, uint64_t* offsets, uint32_t* keys);
 
+/* Graph ingest on the device.  Replaces main.cxx:243-245 --
+ * readMtxOmpW (inc/mtx.hxx:151-188, header: inc/mtx.hxx:38-55), symmetrizeOmp
+ * (inc/symmetrize.hxx:71-82), removeSelfLoopsOmpU (inc/selfLoop.hxx:117-124) -- entry for entry:
+ * repeated lines collapse, but the reference's merge of the reverse edges (set_union_last_inplace,
+ * inc/_algorithm.hxx:177-221) stores some entries that are in both directions of the file twice,
+ * and the prediction counts entries, so that is reproduced (csrc/ingest.cuh).  text = the whole
+ * Matrix Market coordinate file in HOST memory.  Body lines are "u v [weight]" with 1-based ids; the weight is ignored, blank and
+ * '%' lines are skipped.  A "symmetric" / "skew-symmetric" banner stores both directions of every
+ * line, as the reference's reader does; NLP_INGEST_SYMMETRIZE does it for a "general" file
+ * (main.cxx:244), NLP_INGEST_DROP_SELF_LOOPS is main.cxx:245.  The CSR (span = max(rows, cols) + 1,
+ * vertex 0 unused, rows sorted) is built on the GPU into arrays the handle owns
+ * and becomes the resident graph; nlp_graph_size / nlp_fetch_graph return it.
+ * NLP_ERR_ARG: not a coordinate matrix, or a vertex id outside 1..max(rows, cols).
+ * NLP_ERR_CAPACITY: 2^32 - 16 or more directed pairs before deduplication.                        */
+#define NLP_INGEST_SYMMETRIZE      1u
+#define NLP_INGEST_DROP_SELF_LOOPS 2u
+int nlp_ingest_mtx(nlp_handle* h, const char* text, uint64_t bytes, uint32_t flags, uint32_t* span, uint64_t* entries);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t nlp_launch_count(const nlp_handle* h);
 

@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
+#include <fstream>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -154,16 +155,36 @@ class DeviceGraph {
     std::lock_guard<std::mutex> lock(s.mu);
     if (s.resident == this) s.resident = nullptr;
   }
+  // The Matrix Market file at `path`, ingested ON THE GPU the way main.cxx:243-245 does it on the
+  // host: readMtxOmpW, symmetrizeOmp unless `symmetric` (main.cxx's second argument), then
+  // removeSelfLoopsOmpU -- entry for entry the reference's graph (nlp_ingest_mtx).
+  struct FromMtx {};
+  DeviceGraph(FromMtx, const std::string& path, bool symmetric = false, bool dropSelfLoops = true) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::runtime_error("nlp_b200: cannot open " + path);
+    const std::streamsize bytes = f.tellg();
+    std::vector<char> text((size_t)bytes);
+    f.seekg(0);
+    if (bytes && !f.read(text.data(), bytes)) throw std::runtime_error("nlp_b200: cannot read " + path);
+    detail::Session& s = detail::Session::get();
+    std::lock_guard<std::mutex> lock(s.mu);
+    nlp_handle* h = s.handle();
+    uint32_t span = 0; uint64_t entries = 0;
+    const uint32_t flags = (symmetric ? 0u : NLP_INGEST_SYMMETRIZE) | (dropSelfLoops ? NLP_INGEST_DROP_SELF_LOOPS : 0u);
+    detail::check(h, nlp_ingest_mtx(h, text.data(), (uint64_t)text.size(), flags, &span, &entries), "nlp_ingest_mtx");
+    s.resident = this; s.have_fingerprint = false; span_ = span; entries_ = entries;
+  }
   DeviceGraph(const DeviceGraph&) = delete;
   DeviceGraph& operator=(const DeviceGraph&) = delete;
   size_t span() const { return span_; }
+  size_t size() const { return entries_; }         // directed entries (known for ingested graphs)
  private:
   void upload(detail::Session& s, const uint64_t* off, const uint32_t* keys, uint32_t span) {
     nlp_handle* h = s.handle();
     detail::check(h, nlp_set_graph(h, off, keys, span), "nlp_set_graph");
     s.resident = this; s.have_fingerprint = false; span_ = span;
   }
-  size_t span_ = 0;
+  size_t span_ = 0, entries_ = 0;
   template <class K, class W, class G> friend PredictLinkResult<K, W> predictLinksB200(const G&, int, unsigned, unsigned, const PredictLinkOptions<W>&);
 };
 

@@ -18,7 +18,7 @@ STATUS = {0: "NLP_OK", 1: "NLP_ERR_ARG", 2: "NLP_ERR_CUDA", 3: "NLP_ERR_NO_GRAPH
 EXPORTS = ["nlp_create", "nlp_destroy", "nlp_set_graph", "nlp_set_graph_device", "nlp_set_partition",
            "nlp_set_scratch_limit", "nlp_set_path", "nlp_fetch_async", "nlp_fetch_wait", "nlp_set_reuse", "nlp_predict", "nlp_fetch", "nlp_result_device", "nlp_merge",
            "nlp_comm_unique_id", "nlp_comm_init", "nlp_comm_destroy", "nlp_comm_bytes",
-           "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_apply_deletions", "nlp_graph_checkpoint", "nlp_graph_rollback", "nlp_graph_size", "nlp_fetch_graph", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
+           "nlp_set_truth", "nlp_evaluate", "nlp_generate_deletions", "nlp_fetch_deletions", "nlp_deletions_device", "nlp_apply_deletions", "nlp_graph_checkpoint", "nlp_graph_rollback", "nlp_graph_size", "nlp_fetch_graph", "nlp_ingest_mtx", "nlp_launch_count", "nlp_stream", "nlp_last_error", "nlp_version"]
 
 
 class Options(C.Structure):
@@ -101,6 +101,7 @@ def load_library(build_if_missing=True):
     lib.nlp_graph_rollback.argtypes = [vp]
     lib.nlp_graph_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u64)]
     lib.nlp_fetch_graph.argtypes = [vp, vp, vp]
+    lib.nlp_ingest_mtx.argtypes = [vp, C.c_char_p, u64, u32, C.POINTER(u32), C.POINTER(u64)]
     lib.nlp_launch_count.argtypes = [vp]
     lib.nlp_launch_count.restype = u64
     lib.nlp_stream.argtypes = [vp]
@@ -284,6 +285,15 @@ class Predictor:
         off = np.empty(S + 1, np.uint64); keys = np.empty(M, np.uint32)
         self._check(self.lib.nlp_fetch_graph(self.h, off.ctypes.data, keys.ctypes.data if M else None))
         return off, keys
+
+    def ingest_mtx(self, text, symmetrize=True, drop_self_loops=True):
+        """Matrix Market coordinate text (bytes) -> resident CSR, built on the GPU (main.cxx:243-245).
+        Returns (span, entries)."""
+        s, m = C.c_uint32(0), C.c_uint64(0)
+        flags = (1 if symmetrize else 0) | (2 if drop_self_loops else 0)
+        self._check(self.lib.nlp_ingest_mtx(self.h, text, len(text), flags, C.byref(s), C.byref(m)))
+        self._keep = None
+        return int(s.value), int(m.value)
 
     def launch_count(self):
         return int(self.lib.nlp_launch_count(self.h))

@@ -12,6 +12,7 @@
 #include "bucket.cuh"
 #include "evaluate.cuh"
 #include "batch.cuh"
+#include "ingest.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>      // types only: libnccl.so.2 is dlopen'ed by nlp_comm_init
@@ -2351,6 +2352,146 @@ int nlp_fetch_graph(nlp_handle* h, uint64_t* offsets, uint32_t* keys) {
   if (offsets) NLP_CUDA(h, cudaMemcpyAsync(offsets, h->d_off, ((size_t)h->S + 1) * 8, cudaMemcpyDefault, h->stream));
   if (keys && h->M) NLP_CUDA(h, cudaMemcpyAsync(keys, h->d_keys, (size_t)h->M * 4, cudaMemcpyDefault, h->stream));
   NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLP_OK;
+}
+
+// Header of a Matrix Market file, as readMtxHeader reads it (inc/mtx.hxx:38-55): lines that start
+// with '%' are skipped, the "%%" banner names the format and the symmetry, the first other line holds
+// rows, cols and the number of lines.  Returns the offset of the body, or 0 when the text has none.
+static uint64_t mtx_header(const char* text, uint64_t bytes, bool* coordinate, bool* symmetric, uint64_t* rows, uint64_t* cols, uint64_t* size) {
+  *coordinate = false; *symmetric = false; *rows = *cols = *size = 0;
+  uint64_t p = 0;
+  while (p < bytes) {
+    uint64_t e = p;
+    while (e < bytes && text[e] != '\n') ++e;
+    const std::string line(text + p, text + e);
+    const uint64_t next = e < bytes ? e + 1 : e;
+    if (!line.empty() && line[0] == '%') {
+      if (line.size() > 1 && line[1] == '%') {
+        std::vector<std::string> tok;
+        size_t i = 0;
+        while (i < line.size()) {
+          while (i < line.size() && isspace((unsigned char)line[i])) ++i;
+          size_t j = i;
+          while (j < line.size() && !isspace((unsigned char)line[j])) ++j;
+          if (j > i) tok.push_back(line.substr(i, j - i));
+          i = j;
+        }
+        *coordinate = tok.size() > 2 && tok[1] == "matrix" && tok[2] == "coordinate";
+        *symmetric = tok.size() > 4 && (tok[4] == "symmetric" || tok[4] == "skew-symmetric");
+      }
+      p = next;
+      continue;
+    }
+    unsigned long long r = 0, c = 0, n = 0;
+    sscanf(line.c_str(), "%llu %llu %llu", &r, &c, &n);
+    *rows = r; *cols = c; *size = n;
+    return next;
+  }
+  return bytes;
+}
+
+int nlp_ingest_mtx(nlp_handle* h, const char* text, uint64_t bytes, uint32_t flags, uint32_t* span, uint64_t* entries) {
+  if (!h) return NLP_ERR_ARG;
+  if (!text || !bytes) return fail(h, NLP_ERR_ARG, "nlp_ingest_mtx: no text");
+  NLP_CUDA(h, cudaSetDevice(h->device));
+  bool coordinate = false, symmetric = false;
+  uint64_t rows = 0, cols = 0, size = 0;
+  const uint64_t body0 = mtx_header(text, bytes, &coordinate, &symmetric, &rows, &cols, &size);
+  if (!coordinate) return fail(h, NLP_ERR_ARG, "nlp_ingest_mtx: not a Matrix Market coordinate file");
+  const uint64_t n = std::max(rows, cols);
+  if (n >= 0xfffffffeull) return fail(h, NLP_ERR_CAPACITY, "nlp_ingest_mtx: more than 2^32 - 3 vertices");
+  const uint32_t S = (uint32_t)n + 1u;
+  // second pair of a line: 1 = the reader stores it too (symmetric banner), 2 = symmetrizeOmp adds it
+  const int second = symmetric ? 1 : ((flags & NLP_INGEST_SYMMETRIZE) ? 2 : 0);
+  const int drop_self = (flags & NLP_INGEST_DROP_SELF_LOOPS) ? 1 : 0;
+  h->has_graph = false; h->has_result = false; h->has_base = false;
+  h->S = S;                                             // the pair sort reads its digit count from the span
+  // the text on the device
+  const uint64_t body = bytes - body0;
+  DevBuf d_text, d_tiles, d_at, d_ymin, d_xmax;
+  auto drop = [&](int rc) { release(d_text); release(d_tiles); release(d_at); release(d_ymin); release(d_xmax); return rc; };
+  uint64_t L = 0, P = 0, M = 0;
+  int rc = NLP_OK;
+  if (body) {
+    if ((rc = ensure(h, d_text, bytes + 16)) != NLP_OK) return drop(rc);
+    NLP_CUDA(h, cudaMemcpyAsync(d_text.p, text, bytes, cudaMemcpyHostToDevice, h->stream));
+    const uint64_t ntiles = (body + MTX_TILE - 1) / MTX_TILE;
+    if (ntiles >= 0xffffffffull) return drop(fail(h, NLP_ERR_CAPACITY, "nlp_ingest_mtx: text too large"));
+    if ((rc = ensure(h, h->oc_counts, (size_t)ntiles * 4)) != NLP_OK) return drop(rc);
+    if ((rc = ensure(h, d_tiles, (size_t)ntiles * 8)) != NLP_OK) return drop(rc);
+    k_mtx_count<<<(unsigned)ntiles, MTX_THREADS, 0, h->stream>>>((const uint8_t*)d_text.p, body0, bytes, (uint32_t*)h->oc_counts.p);
+    NLP_LAUNCHED(h);
+    if ((rc = exclusive_scan<uint32_t>(h, (const uint32_t*)h->oc_counts.p, ntiles, (unsigned long long*)d_tiles.p, &L)) != NLP_OK) return drop(rc);
+    if (2 * L >= 0xfffffff0ull) return drop(fail(h, NLP_ERR_CAPACITY, "nlp_ingest_mtx: too many lines for one pass"));
+    if ((rc = ensure_candidates(h, 2 * L + 16)) != NLP_OK) return drop(rc);
+    uint32_t* eu = (uint32_t*)h->cu[1].p; uint32_t* ev = (uint32_t*)h->cv[1].p; uint32_t* cnt = (uint32_t*)h->cs[1].p;
+    if (L) {
+      if ((rc = ensure(h, h->sym_flag, 32)) != NLP_OK) return drop(rc);
+      NLP_CUDA(h, cudaMemsetAsync(h->sym_flag.p, 0, 4, h->stream));
+      k_mtx_parse<<<(unsigned)ntiles, MTX_THREADS, 0, h->stream>>>((const uint8_t*)d_text.p, body0, bytes, (uint32_t)n,
+                                                                   (const unsigned long long*)d_tiles.p, eu, ev, (unsigned int*)h->sym_flag.p);
+      NLP_LAUNCHED(h);
+      unsigned int bad = 0;
+      NLP_CUDA(h, cudaMemcpyAsync(&bad, h->sym_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+      k_ing_count<<<grid_for(L, 256, h->num_sms * 16), 256, 0, h->stream>>>(eu, L, second, cnt);
+      NLP_LAUNCHED(h);
+      if ((rc = ensure(h, d_at, (size_t)L * 8)) != NLP_OK) return drop(rc);
+      if ((rc = exclusive_scan<uint32_t>(h, cnt, L, (unsigned long long*)d_at.p, &P)) != NLP_OK) return drop(rc);   // synchronises: `bad` is valid
+      if (bad & 1u) return drop(fail(h, NLP_ERR_ARG, "nlp_ingest_mtx: a vertex id is outside 1..max(rows, cols)"));
+      if (P) {
+        k_ing_emit<<<grid_for(L, 256, h->num_sms * 16), 256, 0, h->stream>>>(eu, ev, L, cnt, (const unsigned long long*)d_at.p, second,
+                                                                            (uint32_t*)h->cu[0].p, (uint32_t*)h->cv[0].p, (uint32_t*)h->cs[0].p);
+        NLP_LAUNCHED(h);
+      }
+    }
+  }
+  // sort by (u, v) with the tag as payload, copies per distinct pair, rows -> offsets
+  int sb = 0;
+  uint32_t* copies = nullptr;
+  if (P) {
+    if ((rc = radix_sort_pairs(h, 0, P, true, &sb)) != NLP_OK) return drop(rc);
+    copies = (uint32_t*)h->cs[sb ^ 1].p;
+    if ((rc = ensure(h, d_ymin, (size_t)S * 4)) != NLP_OK) return drop(rc);
+    if ((rc = ensure(h, d_xmax, (size_t)S * 4)) != NLP_OK) return drop(rc);
+    NLP_CUDA(h, cudaMemsetAsync(d_ymin.p, 0xff, (size_t)S * 4, h->stream));
+    NLP_CUDA(h, cudaMemsetAsync(d_xmax.p, 0, (size_t)S * 4, h->stream));
+    const uint32_t* pu = (const uint32_t*)h->cu[sb].p; const uint32_t* pv = (const uint32_t*)h->cv[sb].p;
+    k_ing_class<<<grid_for(P, 256, h->num_sms * 16), 256, 0, h->stream>>>(pu, pv, (const uint32_t*)h->cs[sb].p, P, copies,
+                                                                          (uint32_t*)d_ymin.p, (uint32_t*)d_xmax.p);
+    NLP_LAUNCHED(h);
+    k_ing_copies<<<grid_for(P, 256, h->num_sms * 16), 256, 0, h->stream>>>(pu, pv, P, (const uint32_t*)d_ymin.p, (const uint32_t*)d_xmax.p,
+                                                                           drop_self, copies);
+    NLP_LAUNCHED(h);
+    if ((rc = ensure(h, d_at, (size_t)P * 8)) != NLP_OK) return drop(rc);
+    if ((rc = exclusive_scan<uint32_t>(h, copies, P, (unsigned long long*)d_at.p, &M)) != NLP_OK) return drop(rc);
+  }
+  // a graph that is being replaced may live in own_*: the new one goes to the spare pair, as in nlp_apply_deletions
+  const bool cur_is_own = h->d_off == (const uint64_t*)h->own_off.p && h->own_off.p != nullptr;
+  DevBuf& n_off = cur_is_own ? h->spare_off : h->own_off;
+  DevBuf& n_keys = cur_is_own ? h->spare_keys : h->own_keys;
+  if ((rc = ensure(h, n_off, ((size_t)S + 1) * 8)) != NLP_OK) return drop(rc);
+  if ((rc = ensure(h, n_keys, (size_t)std::max<uint64_t>(M, 1) * 4)) != NLP_OK) return drop(rc);
+  if (P) {
+    k_ing_write<<<grid_for(P, 256, h->num_sms * 16), 256, 0, h->stream>>>((const uint32_t*)h->cu[sb].p, (const uint32_t*)h->cv[sb].p, P,
+                                                                          copies, (const unsigned long long*)d_at.p,
+                                                                          (uint32_t*)n_keys.p, (unsigned long long*)n_off.p);
+    NLP_LAUNCHED(h);
+  }
+  k_ing_tail<<<grid_for((uint64_t)S + 1, 256, h->num_sms * 8), 256, 0, h->stream>>>((const uint32_t*)h->cu[sb].p, P, S, (unsigned long long)M,
+                                                                                    (unsigned long long*)n_off.p);
+  NLP_LAUNCHED(h);
+  NLP_CUDA(h, cudaStreamSynchronize(h->stream));
+  drop(NLP_OK);
+  if (cur_is_own) { std::swap(h->own_off, h->spare_off); std::swap(h->own_keys, h->spare_keys); }
+  h->d_off = (const uint64_t*)h->own_off.p;
+  h->d_keys = (const uint32_t*)h->own_keys.p;
+  // validated like any other graph (fingerprint, largest entry multiplicity); whether the rows are
+  // symmetric as multisets is found out when a path needs to know (the reference's duplicated
+  // entries need not be mirrored)
+  NLP_TRY(finish_graph(h));
+  if (span) *span = S;
+  if (entries) *entries = h->M;
   return NLP_OK;
 }
 

@@ -155,6 +155,109 @@ def ref_apply_deletions(offsets, keys, del_u, del_v):
     return o2, k2[:n].copy()
 
 
+def ref_read_mtx(path, symmetric=False, drop_self_loops=True):
+    """The reference's own ingest (main.cxx:243-245: readMtxOmpW, symmetrizeOmp unless `symmetric`,
+    removeSelfLoopsOmpU) of the Matrix Market file at `path`; returns its graph as CSR."""
+    lib = C.CDLL(os.path.join(_HERE, "_ref", "libnlpref_batch.so"))
+    lib.nlpref_read_mtx.restype = C.c_int64
+    lib.nlpref_read_mtx.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
+    span = C.c_uint32(0)
+    m = lib.nlpref_read_mtx(path.encode(), int(symmetric), int(drop_self_loops), C.byref(span), None, None)
+    off = np.empty(span.value + 1, np.uint64); keys = np.empty(max(m, 1), np.uint32)
+    lib.nlpref_read_mtx(path.encode(), int(symmetric), int(drop_self_loops), C.byref(span), off.ctypes.data, keys.ctypes.data)
+    return off, keys[:m].copy()
+
+
+def _set_union_last(x, y):
+    """Literal port of the reference's set_union_last_inplace (inc/_algorithm.hxx:177-221) for sorted
+    lists of ints: y merged into x.  NOT a set union -- once the routine has left its first loop, an
+    element that is in both lists is written twice (the copy waiting in the deque follows the one
+    taken from y)."""
+    if not y:
+        return list(x)
+    if not x:
+        return sorted(set(y))
+    x = list(x); y = list(y)
+    xb = 0; yb = 0
+    while True:
+        while x[xb] < y[yb]:
+            xb += 1
+            if xb == len(x):
+                return x + sorted(set(y[yb:]))
+        if x[xb] != y[yb]:
+            break
+        x[xb] = y[yb]; yb += 1
+        if yb == len(y):
+            return x
+    out = x[:xb]                       # everything before the insertion point stays
+    q = [x[xb]]; xb += 1               # deque of displaced x elements
+    out.append(y[yb]); yb += 1
+    while yb < len(y):
+        if out[-1] == y[yb]:
+            out[-1] = y[yb]; yb += 1
+        else:
+            if xb < len(x):
+                q.append(x[xb]); xb += 1
+            if q and q[0] < y[yb]:
+                out.append(q.pop(0))
+            else:
+                out.append(y[yb]); yb += 1
+    while True:
+        if xb < len(x):
+            q.append(x[xb]); xb += 1
+        if not q:
+            break
+        out.append(q.pop(0))
+    return out
+
+
+def mtx_to_csr(text, symmetrize=True, drop_self_loops=True):
+    """Restatement of the reference's ingest for Matrix Market coordinate TEXT (bytes): header as
+    inc/mtx.hxx:38-55, body lines "u v [w]" (inc/mtx.hxx:173-179; both directions for a symmetric
+    banner), rows sorted and made unique by the first update, then -- with `symmetrize`
+    (main.cxx:244, inc/symmetrize.hxx:71-82) -- the reverse of every stored edge merged in by the
+    reference's own set_union_last_inplace (which leaves some common entries twice, see
+    _set_union_last), then one copy of every self-loop removed (inc/selfLoop.hxx:117-124,
+    set_difference_inplace).  Returns (offsets, keys) with span = max(rows, cols) + 1."""
+    lines = text.decode().split("\n")
+    sym = False
+    i = 0
+    while True:
+        ln = lines[i]; i += 1
+        if not ln.startswith("%"):
+            break
+        if ln.startswith("%%"):
+            h = ln.split()
+            assert h[1] == "matrix" and h[2] == "coordinate"
+            sym = len(h) > 4 and h[4] in ("symmetric", "skew-symmetric")
+    rows, cols, _ = (int(x) for x in ln.split()[:3])
+    n = max(rows, cols)
+    stored = [set() for _ in range(n + 1)]
+    for ln in lines[i:]:
+        t = ln.split()
+        if len(t) < 2 or ln.lstrip().startswith("%"):
+            continue
+        u, v = int(t[0]), int(t[1])
+        stored[u].add(v)
+        if sym:
+            stored[v].add(u)
+    x = [sorted(r) for r in stored]
+    if symmetrize:
+        rev = [[] for _ in range(n + 1)]
+        for u in range(n + 1):
+            for v in x[u]:
+                rev[v].append(u)          # ascending u: already sorted
+        x = [_set_union_last(x[u], rev[u]) for u in range(n + 1)]
+    if drop_self_loops:
+        for u in range(n + 1):
+            if u in x[u]:
+                x[u].remove(u)            # one copy
+    off = np.zeros(n + 2, np.uint64)
+    np.cumsum([len(r) for r in x], out=off[1:])
+    keys = np.array([v for r in x for v in r], np.uint32)
+    return off, keys
+
+
 def ref_available():
     return os.path.exists(os.path.join(_HERE, "_ref", "libnlpref.so"))
 

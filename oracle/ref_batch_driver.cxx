@@ -61,4 +61,26 @@ int64_t nlpref_apply_deletions(const uint64_t* offsets, const uint32_t* keys, ui
   return (int64_t)at;
 }
 
+// The reference's own ingest, as main.cxx:243-245 runs it: readMtxOmpW on the file at `path`, then
+// symmetrizeOmp unless `symmetric`, then removeSelfLoopsOmpU; the graph is dumped as CSR.  First call
+// with out_keys == NULL to learn the sizes (returns the entry count, *out_span = span).
+int64_t nlpref_read_mtx(const char* path, int symmetric, int drop_self_loops, uint32_t* out_span,
+                        uint64_t* out_offsets, uint32_t* out_keys) {
+  using K = uint32_t;
+  DiGraph<K, None, float> x;
+  auto fl = [](auto u) { return true; };
+  readMtxOmpW(x, path, false);
+  if (!symmetric) x = symmetrizeOmp(x);
+  if (drop_self_loops) removeSelfLoopsOmpU(x, fl);
+  const uint32_t span = (uint32_t)x.span();
+  *out_span = span;
+  uint64_t at = 0;
+  for (uint32_t u = 0; u < span; ++u) {
+    if (out_offsets) out_offsets[u] = at;
+    if (x.hasVertex(u)) x.forEachEdgeKey(u, [&](K v) { if (out_keys) out_keys[at] = v; ++at; });
+  }
+  if (out_offsets) out_offsets[span] = at;
+  return (int64_t)at;
+}
+
 }  // extern "C"
