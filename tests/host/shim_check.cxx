@@ -98,6 +98,37 @@ int main(int argc, char** argv) {
       if (half && (ev.recall != 1.0 || ev.precision != double(truth.size()) / double(2 * last.edges.size())))
         throw runtime_error("evaluateLastPrediction: wrong precision / recall");
     }
+    // graph ingest on the GPU (main.cxx:243-245): the edges u < v of x as a "general" Matrix Market
+    // file, symmetrized and stripped of self-loops on the device, must predict like the same graph
+    // built on the host
+    {
+      const string path = string(argv[2]) + ".mtx";
+      MiniGraph y;
+      vector<vector<uint32_t>> rows(S);
+      size_t lines = 0;
+      for (uint64_t u = 0; u < S; ++u)
+        for (uint64_t e = x.off[u]; e < x.off[u + 1]; ++e) {
+          const uint32_t v = x.keys[e];
+          if (u == 0 || u >= v || (e > x.off[u] && x.keys[e - 1] == v)) continue;
+          rows[u].push_back(v); rows[v].push_back((uint32_t)u); ++lines;
+        }
+      FILE* m = fopen(path.c_str(), "w");
+      if (!m) throw runtime_error("cannot write " + path);
+      fprintf(m, "%%%%MatrixMarket matrix coordinate real general\n%% written by shim_check\n%llu %llu %zu\n",
+              (unsigned long long)(S - 1), (unsigned long long)(S - 1), lines);
+      for (uint64_t u = 0; u < S; ++u)
+        for (uint32_t v : rows[u]) if (u < v) fprintf(m, "%llu %u 1.5\n", (unsigned long long)u, v);
+      fclose(m);
+      y.off.assign(S + 1, 0);
+      for (uint64_t u = 0; u < S; ++u) { sort(rows[u].begin(), rows[u].end()); y.off[u + 1] = y.off[u] + rows[u].size(); }
+      for (uint64_t u = 0; u < S; ++u) y.keys.insert(y.keys.end(), rows[u].begin(), rows[u].end());
+      const auto want = nlp_b200::predictLinksJaccardCoefficientOmp<8>(y, {1, 500});
+      nlp_b200::DeviceGraph fromFile(nlp_b200::DeviceGraph::FromMtx{}, path, /*symmetric=*/false, /*dropSelfLoops=*/true);
+      remove(path.c_str());
+      if (fromFile.span() != S || fromFile.size() != y.keys.size()) throw runtime_error("DeviceGraph(FromMtx): wrong span or size");
+      const auto got = nlp_b200::predictLinksJaccardCoefficientOmp<8>(fromFile, {1, 500});
+      if (got.edges != want.edges) throw runtime_error("DeviceGraph(FromMtx): prediction differs from the host-built graph");
+    }
     fclose(out);
   } catch (const std::exception& e) {
     fprintf(stderr, "shim_check: %s\n", e.what());
