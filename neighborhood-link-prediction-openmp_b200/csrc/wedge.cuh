@@ -764,7 +764,8 @@ __device__ __forceinline__ void range_batch(const Params& p, const RangeFences& 
   // ncu, R-MAT 18 IHub, 69 % issue slots busy at 360 warp instructions per atomic instruction.)
   // Two variants measured slower at R-MAT 22 IHub and were dropped (profiles/r02_summary.md): one
   // warp-aggregated append to touched[] per step instead of an atomic per first touch (+8 %), and
-  // a separate warp-coalesced pass over the long row parts (+43 %: two phases, two tails).
+  // a separate warp-coalesced pass over the long row parts (+43 %: two phases, two tails); a fast
+  // path for runs that lie in one row (no per-wedge row stepping) gained nothing either (+7 %).
   const uint32_t tot = s_inc[RANGE_THREADS - 1];
   for (uint32_t c0 = threadIdx.x * (uint32_t)RANGE_RUN; c0 < tot; c0 += RANGE_THREADS * (uint32_t)RANGE_RUN) {
     uint32_t lo = 0, hi = RANGE_THREADS - 1;          // smallest j with s_inc[j] > c0
