@@ -287,7 +287,8 @@ int nlp_fetch_graph(nlp_handle* h, uint64_t* offsets, uint32_t* keys);
  * vertex 0 unused, rows sorted) is built on the GPU into arrays the handle owns
  * and becomes the resident graph; nlp_graph_size / nlp_fetch_graph return it.
  * NLP_ERR_ARG: not a coordinate matrix, or a vertex id outside 1..max(rows, cols).
- * NLP_ERR_CAPACITY: 2^32 - 16 or more directed pairs before deduplication.                        */
+ * NLP_ERR_CAPACITY: 2^32 - 16 or more directed pairs before deduplication.  Everything is resident
+ * at once (about 100 bytes of GPU memory per line of the file).                                    */
 #define NLP_INGEST_SYMMETRIZE      1u
 #define NLP_INGEST_DROP_SELF_LOOPS 2u
 int nlp_ingest_mtx(nlp_handle* h, const char* text, uint64_t bytes, uint32_t flags, uint32_t* span, uint64_t* entries);
