@@ -13,6 +13,7 @@
 #include "evaluate.cuh"
 #include "batch.cuh"
 #include "ingest.cuh"
+#include "mtx_header.hpp"
 
 #include <dlfcn.h>
 #include <nccl.h>      // types only: libnccl.so.2 is dlopen'ed by nlp_comm_init
@@ -2355,49 +2356,13 @@ int nlp_fetch_graph(nlp_handle* h, uint64_t* offsets, uint32_t* keys) {
   return NLP_OK;
 }
 
-// Header of a Matrix Market file, as readMtxHeader reads it (inc/mtx.hxx:38-55): lines that start
-// with '%' are skipped, the "%%" banner names the format and the symmetry, the first other line holds
-// rows, cols and the number of lines.  Returns the offset of the body, or 0 when the text has none.
-static uint64_t mtx_header(const char* text, uint64_t bytes, bool* coordinate, bool* symmetric, uint64_t* rows, uint64_t* cols, uint64_t* size) {
-  *coordinate = false; *symmetric = false; *rows = *cols = *size = 0;
-  uint64_t p = 0;
-  while (p < bytes) {
-    uint64_t e = p;
-    while (e < bytes && text[e] != '\n') ++e;
-    const std::string line(text + p, text + e);
-    const uint64_t next = e < bytes ? e + 1 : e;
-    if (!line.empty() && line[0] == '%') {
-      if (line.size() > 1 && line[1] == '%') {
-        std::vector<std::string> tok;
-        size_t i = 0;
-        while (i < line.size()) {
-          while (i < line.size() && isspace((unsigned char)line[i])) ++i;
-          size_t j = i;
-          while (j < line.size() && !isspace((unsigned char)line[j])) ++j;
-          if (j > i) tok.push_back(line.substr(i, j - i));
-          i = j;
-        }
-        *coordinate = tok.size() > 2 && tok[1] == "matrix" && tok[2] == "coordinate";
-        *symmetric = tok.size() > 4 && (tok[4] == "symmetric" || tok[4] == "skew-symmetric");
-      }
-      p = next;
-      continue;
-    }
-    unsigned long long r = 0, c = 0, n = 0;
-    sscanf(line.c_str(), "%llu %llu %llu", &r, &c, &n);
-    *rows = r; *cols = c; *size = n;
-    return next;
-  }
-  return bytes;
-}
-
 int nlp_ingest_mtx(nlp_handle* h, const char* text, uint64_t bytes, uint32_t flags, uint32_t* span, uint64_t* entries) {
   if (!h) return NLP_ERR_ARG;
   if (!text || !bytes) return fail(h, NLP_ERR_ARG, "nlp_ingest_mtx: no text");
   NLP_CUDA(h, cudaSetDevice(h->device));
   bool coordinate = false, symmetric = false;
   uint64_t rows = 0, cols = 0, size = 0;
-  const uint64_t body0 = mtx_header(text, bytes, &coordinate, &symmetric, &rows, &cols, &size);
+  const uint64_t body0 = nlp::mtx_header(text, bytes, &coordinate, &symmetric, &rows, &cols, &size);
   if (!coordinate) return fail(h, NLP_ERR_ARG, "nlp_ingest_mtx: not a Matrix Market coordinate file");
   const uint64_t n = std::max(rows, cols);
   if (n >= 0xfffffffeull) return fail(h, NLP_ERR_CAPACITY, "nlp_ingest_mtx: more than 2^32 - 3 vertices");

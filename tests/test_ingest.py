@@ -125,3 +125,14 @@ def test_closed_form_of_the_reference_merge():
         if x and only_y and only_y[0] < max(x):
             want = sorted(want + [e for e in sx & sy if e > only_y[0]])
         assert O._set_union_last(x, y) == want, (x, y)
+
+
+def test_header_parse_on_the_host(tmp_path):
+    """csrc/mtx_header.hpp (the host half of nlp_ingest_mtx) compiled and run without a GPU."""
+    import subprocess
+    exe = tmp_path / "mtx_header_check"
+    src = os.path.join(ROOT, "tests", "host", "mtx_header_check.cxx")
+    inc = os.path.join(ROOT, "neighborhood-link-prediction-openmp_b200", "csrc")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", inc, src, "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
